@@ -1,0 +1,459 @@
+"""TEST INFRASTRUCTURE (the oracle) — a CPU restatement of the reference's joint det+seg forward path and
+post-process.  NOT product code: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` arm may import this module.  The product (multiyolov5_b200/) never does.
+
+Parity status: PINNED.  The reference ships no golden vectors, so this restatement is
+pinned by (a) oracle/make_golden.py, which runs the UNMODIFIED reference in the build container and
+commits its outputs under tests/golden/, and (b) tests/test_oracle_golden.py, which checks this file
+against those fixtures on every CPU test run.
+
+Floating-point work is restated with torch fp32 CPU ops (the reference's own substrate); index work
+(NMS ordering / suppression, class-id argmax) is restated in numpy so its order of operations is explicit.
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+`state_dict` keys are the reference's own (e.g. ``model.2.m.0.cv1.conv.weight``).
+
+A `q` hook (default identity) is applied wherever the CUDA path rounds to fp16 storage, so that
+`quantised=True` gives an "fp16-storage emulation" of the same graph for tight kernel-level checks.
+"""
+import math
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-3  # reference utils/torch_utils.py:150 (initialize_weights sets eps=1e-3 on every BN instance)
+
+
+def make_divisible(x, divisor):
+    # reference utils/general.py:176-178
+    return math.ceil(x / divisor) * divisor
+
+
+def _ident(t):
+    return t
+
+
+def q16(t: torch.Tensor) -> torch.Tensor:
+    """fp16 storage rounding used by the fp16-emulation mode."""
+    return t.to(torch.float16).to(torch.float32)
+
+
+class Ctx:
+    def __init__(self, sd: Dict[str, torch.Tensor], quantised: bool = False):
+        self.sd = {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in sd.items()}
+        self.quantised = quantised
+        self.q: Callable = q16 if quantised else _ident
+        self.taps: Dict[str, torch.Tensor] = {}  # optional named intermediates
+
+
+# ---------------------------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------------------------
+def _bn_affine(cx: Ctx, p: str):
+    # eval-mode BatchNorm as a per-channel affine; reference utils/torch_utils.py:182-202 (fuse algebra)
+    g, b = cx.sd[p + ".weight"], cx.sd[p + ".bias"]
+    m, v = cx.sd[p + ".running_mean"], cx.sd[p + ".running_var"]
+    scale = g / torch.sqrt(v + BN_EPS)
+    return scale, b - m * scale
+
+
+def conv_bn_act(cx: Ctx, x, wkey: str, bnp: Optional[str], k: int, s: int = 1, d: int = 1, act: bool = True,
+                bias_key: Optional[str] = None, residual=None):
+    """`Conv.forward` = act(bn(conv(x)))  (reference models/common.py:42-43); pad = k//2 (autopad :22-26),
+    dilated bare branches use padding=dilation (models/common.py:482,487,243-253)."""
+    w = cx.sd[wkey]
+    pad = d * (k // 2)
+    if bnp is not None:
+        scale, shift = _bn_affine(cx, bnp)
+        if cx.quantised:  # fold BN into fp16 weights exactly like the CUDA pack kernel
+            w = q16(w * scale.view(-1, 1, 1, 1))
+            y = F.conv2d(x, w, None, s, pad, d) + shift.view(1, -1, 1, 1)
+        else:
+            y = F.conv2d(x, w, None, s, pad, d)
+            y = y * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    else:
+        if cx.quantised:
+            w = q16(w)
+        y = F.conv2d(x, w, None, s, pad, d)
+        if bias_key is not None:
+            y = y + cx.sd[bias_key].view(1, -1, 1, 1)
+    if act:
+        y = y * torch.sigmoid(y)  # nn.SiLU
+    if residual is not None:
+        y = residual + y  # Bottleneck shortcut, reference models/common.py:105
+    return y
+
+
+def Conv(cx, p, x, k=1, s=1, residual=None, quant_out=True):
+    y = conv_bn_act(cx, x, p + ".conv.weight", p + ".bn", k, s, residual=residual)
+    return cx.q(y) if quant_out else y
+
+
+def bare_conv_bn_silu(cx, p, x, d):
+    # nn.Sequential(Conv2d(k3, dilation d, bias False), BatchNorm2d, SiLU): reference models/common.py:481-490
+    return cx.q(conv_bn_act(cx, x, p + ".0.weight", p + ".1", 3, 1, d))
+
+
+def Bottleneck(cx, p, x, shortcut):
+    # reference models/common.py:95-105 (c1 == c2 always holds inside C3 because e=1.0, :135)
+    h = Conv(cx, p + ".cv1", x, 1)
+    return Conv(cx, p + ".cv2", h, 3, residual=x if shortcut else None)
+
+
+def C3(cx, p, x, n, shortcut):
+    # reference models/common.py:127-139
+    y = Conv(cx, p + ".cv1", x, 1)
+    for i in range(n):
+        y = Bottleneck(cx, f"{p}.m.{i}", y, shortcut)
+    return Conv(cx, p + ".cv3", torch.cat((y, Conv(cx, p + ".cv2", x, 1)), 1), 1)
+
+
+def SPP(cx, p, x, ks=(5, 9, 13)):
+    # reference models/common.py:163-174
+    x = Conv(cx, p + ".cv1", x, 1)
+    return Conv(cx, p + ".cv2", torch.cat([x] + [F.max_pool2d(x, k, 1, k // 2) for k in ks], 1), 1)
+
+
+def C3SPP(cx, p, x):
+    # reference models/common.py:142-152
+    return Conv(cx, p + ".cv3", torch.cat((SPP(cx, p + ".m", Conv(cx, p + ".cv1", x, 1)), Conv(cx, p + ".cv2", x, 1)), 1), 1)
+
+
+def Focus(cx, p, x):
+    # reference models/common.py:542-551: space-to-depth (order [::2,::2],[1::2,::2],[::2,1::2],[1::2,1::2]) then Conv k3
+    x = cx.q(x)
+    return Conv(cx, p + ".conv", torch.cat([x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]], 1), 3)
+
+
+def bilinear(cx, x, size=None, scale=None):
+    # nn.Upsample(mode='bilinear', align_corners=True) / F.interpolate(..., align_corners=True)
+    if size is None:
+        size = (x.shape[2] * scale, x.shape[3] * scale)
+    return F.interpolate(x, size, mode="bilinear", align_corners=True)
+
+
+def RFB2(cx, p, x, d=(2, 3), has_globel=False):
+    # reference models/common.py:470-511
+    x3 = Conv(cx, p + ".branch3.0", x, 1)
+    x0 = Conv(cx, p + ".branch0.1", Conv(cx, p + ".branch0.0", x, 1), 3)
+    x1 = bare_conv_bn_silu(cx, p + ".branch1", x0, d[0])
+    x2 = bare_conv_bn_silu(cx, p + ".branch2", x1, d[1])
+    feats = [x0, x1, x2, x3]
+    if has_globel:
+        g = Conv(cx, p + ".branch4.1", cx.q(F.adaptive_avg_pool2d(x2, 1)), 1)
+        feats.append(F.interpolate(g, (x.shape[2], x.shape[3]), mode="nearest"))
+    return Conv(cx, p + ".ConvLinear", torch.cat(feats, 1), 1)
+
+
+def ASPP(cx, p, x, d=(3, 6, 9)):
+    # reference models/common.py:233-275 (has_globel=False is the only shipped use, models/yolo.py:109)
+    x0 = Conv(cx, p + ".branch0.0", x, 1)
+    xs = [x0] + [bare_conv_bn_silu(cx, f"{p}.branch{i + 1}", x, d[i]) for i in range(3)]
+    return Conv(cx, p + ".ConvLinear", torch.cat(xs, 1), 1)
+
+
+def PyramidPooling(cx, p, x, ks=(1, 2, 3, 6)):
+    # reference models/common.py:514-539
+    h, w = x.shape[2:]
+    feats = [x]
+    for i, k in enumerate(ks):
+        pooled = cx.q(F.adaptive_avg_pool2d(x, k))
+        feats.append(cx.q(bilinear(cx, Conv(cx, f"{p}.conv{i + 1}", pooled, 1), (h, w))))
+    return torch.cat(feats, 1)
+
+
+def FFM(cx, p, x, k):
+    # reference models/common.py:210-230 ; x is already concatenated when is_cat
+    feat = Conv(cx, p + ".convblk", x, k)
+    a = F.adaptive_avg_pool2d(feat, 1)
+    wa, wb = cx.sd[p + ".channel_attention.1.weight"], cx.sd[p + ".channel_attention.3.weight"]
+    a = F.conv2d(a, wa)
+    a = a * torch.sigmoid(a)
+    a = torch.sigmoid(F.conv2d(a, wb))
+    return cx.q(feat * a + feat)
+
+
+# ---------------------------------------------------------------------------------------------
+# segmentation heads (return logits at input resolution, i.e. after the final x8 bilinear)
+# ---------------------------------------------------------------------------------------------
+def _classifier(cx, p, x, k=1, bias=True):
+    return conv_bn_act(cx, x, p + ".weight", None, k, act=False, bias_key=(p + ".bias") if bias else None)
+
+
+def SegMaskPSP(cx, p, xs, c_hid):
+    # reference models/yolo.py:149-186
+    f8 = Conv(cx, p + ".m8.0", xs[0], 1)
+    f16 = cx.q(bilinear(cx, Conv(cx, p + ".m16.0", xs[1], 1), scale=2))
+    f32 = cx.q(bilinear(cx, Conv(cx, p + ".m32.0", xs[2], 1), scale=4))
+    y = RFB2(cx, p + ".out.0", torch.cat([f8, f16, f32], 1), d=(2, 3))
+    y = PyramidPooling(cx, p + ".out.1", y)
+    y = FFM(cx, p + ".out.2", y, 3)
+    lo = _classifier(cx, p + ".out.3", y)
+    cx.taps["seg_lowres"] = lo
+    return bilinear(cx, lo, scale=8)
+
+
+def SegMaskLab(cx, p, xs, c_hid, n):
+    # reference models/yolo.py:93-124
+    e = Conv(cx, p + ".encoder.0", xs[1], 1)
+    e = ASPP(cx, p + ".encoder.1", e, d=(3, 6, 9))
+    e = cx.q(bilinear(cx, e, scale=2))
+    dt = Conv(cx, p + ".detail.1", Conv(cx, p + ".detail.0", xs[0], 1), 3)
+    y = FFM(cx, p + ".decoder.0", torch.cat([dt, e], 1), 1)
+    y = Conv(cx, p + ".decoder.1", y, 3)
+    lo = _classifier(cx, p + ".decoder.2", y)
+    cx.taps["seg_lowres"] = lo
+    return bilinear(cx, lo, scale=8)
+
+
+def SegMaskBiSe(cx, p, xs):
+    # reference models/yolo.py:30-86 (eval branch: returns self.out(feat1) only)
+    f3 = RFB2(cx, p + ".m32.0", xs[2], d=(2, 3), has_globel=True)
+    f3 = cx.q(bilinear(cx, Conv(cx, p + ".up32.0", f3, 3), scale=2))
+    f2 = cx.q(RFB2(cx, p + ".m16.0", xs[1], d=(2, 3)) + f3)
+    f2 = cx.q(bilinear(cx, Conv(cx, p + ".up16.0", f2, 3), scale=2))
+    y = FFM(cx, p + ".out.0", torch.cat([Conv(cx, p + ".m8.0", xs[0], 1), f2], 1), 3)
+    lo = _classifier(cx, p + ".out.2", y)  # out.1 is Dropout (identity in eval)
+    cx.taps["seg_lowres"] = lo
+    return bilinear(cx, lo, scale=8)
+
+
+def SegMaskBase(cx, p, xs, n, shortcut):
+    # reference models/yolo.py:129-146
+    y = C3(cx, p + ".m.0", xs[0], n, shortcut)
+    y = C3SPP(cx, p + ".m.1", y)
+    lo = _classifier(cx, p + ".m.3", y, k=3, bias=False)  # m.2 is Dropout
+    cx.taps["seg_lowres"] = lo
+    return bilinear(cx, lo, scale=8)
+
+
+# ---------------------------------------------------------------------------------------------
+# Detect
+# ---------------------------------------------------------------------------------------------
+def Detect(cx, p, xs, nc, anchors_px: Sequence[Sequence[float]], strides: Sequence[float]):
+    """reference models/yolo.py:206-225 (eval branch).  `anchors_px` are the yaml anchors in pixels
+    (== anchor_grid buffer); returns (z (B,sumA,no), [x_i (B,na,ny,nx,no)])."""
+    no = nc + 5
+    z, raw = [], []
+    for i, x in enumerate(xs):
+        y = conv_bn_act(cx, x, f"{p}.m.{i}.weight", None, 1, act=False, bias_key=f"{p}.m.{i}.bias")
+        bs, _, ny, nx = y.shape
+        na = y.shape[1] // no
+        y = y.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
+        raw.append(y)
+        s = y.sigmoid()
+        yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
+        grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()
+        ag = torch.tensor(anchors_px[i], dtype=torch.float32).view(1, na, 1, 1, 2)
+        s[..., 0:2] = (s[..., 0:2] * 2.0 - 0.5 + grid) * strides[i]
+        s[..., 2:4] = (s[..., 2:4] * 2) ** 2 * ag
+        z.append(s.view(bs, -1, no))
+    return torch.cat(z, 1), raw
+
+
+# ---------------------------------------------------------------------------------------------
+# whole model
+# ---------------------------------------------------------------------------------------------
+def parse_cfg(cfg: dict):
+    """Channel / depth bookkeeping of reference models/yolo.py:373-429 (parse_model), restated for the
+    module kinds the shipped *_city_seg.yaml files use."""
+    gd, gw = cfg["depth_multiple"], cfg["width_multiple"]
+    nc, nseg = cfg["nc"], cfg["n_segcls"]
+    anchors = cfg["anchors"]
+    na = len(anchors[0]) // 2
+    no = na * (nc + 5)
+    ch = [cfg.get("ch", 3)]
+    layers = []
+    for i, (f, n, m, args) in enumerate(cfg["backbone"] + cfg["head"]):
+        args = [nseg if a == "n_segcls" else nc if a == "nc" else anchors if a == "anchors" else
+                (None if a == "None" else (False if a == "False" else a)) for a in args]
+        n = max(round(n * gd), 1) if n > 1 else n
+        spec = {"i": i, "f": f, "type": m}
+        if m in ("Conv", "Focus", "SPP", "C3"):
+            c1, c2 = ch[f], args[0]
+            if c2 != no:
+                c2 = make_divisible(c2 * gw, 8)
+            spec.update(c1=c1, c2=c2)
+            if m == "Conv":
+                spec.update(k=args[1] if len(args) > 1 else 1, s=args[2] if len(args) > 2 else 1)
+            elif m == "Focus":
+                spec.update(k=args[1] if len(args) > 1 else 1)
+            elif m == "SPP":
+                spec.update(ks=tuple(args[1]))
+            else:
+                spec.update(n=n, shortcut=args[1] if len(args) > 1 else True)
+        elif m == "nn.Upsample":
+            c2 = ch[f]
+            spec.update(scale=args[1], mode=args[2])
+        elif m == "Concat":
+            c2 = sum(ch[x] for x in f)
+        elif m == "Detect":
+            c2 = None
+            spec.update(nc=nc, anchors=anchors, ch=[ch[x] for x in f])
+        elif m.startswith("SegMask"):
+            n_ = max(round(args[1] * gd), 1) if args[1] > 1 else args[1]
+            c2 = ch[f[0]] if False else None
+            spec.update(n_segcls=args[0], n=n_, c_hid=make_divisible(args[2] * gw, 8), shortcut=args[3],
+                        ch=[ch[x] for x in f])
+        else:
+            raise NotImplementedError(m)
+        layers.append(spec)
+        if i == 0:
+            ch = []
+        ch.append(c2)
+    return layers
+
+
+def model_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, quantised: bool = False,
+                  keep: Sequence[int] = ()):
+    """`Model.forward_once` (reference models/yolo.py:293-316) in eval mode.
+    Returns dict(z, raw=[x0,x1,x2], seg, seg_lowres, layers={i: tensor})."""
+    cx = Ctx(sd, quantised)
+    layers = parse_cfg(cfg)
+    ys: List[Optional[torch.Tensor]] = []
+    x = x.to(torch.float32)
+    det = seg = None
+    strides = []
+    with torch.no_grad():
+        for sp in layers:
+            i, f, t = sp["i"], sp["f"], sp["type"]
+            p = f"model.{i}"
+            inp = x if f == -1 else (ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f])
+            if t == "Focus":
+                x = Focus(cx, p, inp)
+            elif t == "Conv":
+                x = Conv(cx, p, inp, sp["k"], sp["s"])
+            elif t == "C3":
+                x = C3(cx, p, inp, sp["n"], sp["shortcut"])
+            elif t == "SPP":
+                x = SPP(cx, p, inp, sp["ks"])
+            elif t == "nn.Upsample":
+                x = F.interpolate(inp, scale_factor=sp["scale"], mode=sp["mode"])
+            elif t == "Concat":
+                x = torch.cat(inp, 1)
+            elif t == "SegMaskPSP":
+                x = seg = SegMaskPSP(cx, p, inp, sp["c_hid"])
+            elif t == "SegMaskLab":
+                x = seg = SegMaskLab(cx, p, inp, sp["c_hid"], sp["n"])
+            elif t == "SegMaskBiSe":
+                x = seg = SegMaskBiSe(cx, p, inp)
+            elif t == "SegMaskBase":
+                x = seg = SegMaskBase(cx, p, inp, sp["n"], sp["shortcut"])
+            elif t == "Detect":
+                H = ys[0].shape[2] * 2
+                strides = [H / a.shape[2] for a in inp]
+                anchors_px = [[(a[2 * j], a[2 * j + 1]) for j in range(len(a) // 2)] for a in sp["anchors"]]
+                det = Detect(cx, p, inp, sp["nc"], anchors_px, strides)
+                x = det
+            ys.append(x)
+    out = dict(z=det[0], raw=det[1], seg=seg, seg_lowres=cx.taps.get("seg_lowres"),
+               layers={i: ys[i] for i in keep})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# post-process: NMS (index work -> numpy, explicit op order) and seg argmax
+# ---------------------------------------------------------------------------------------------
+def nms_greedy(boxes: np.ndarray, scores: np.ndarray, iou_thres: float) -> np.ndarray:
+    """torchvision.ops.nms (0.26.0 CPU kernel; third-party, un-vendored — call site reference
+    utils/general.py:493).  Published algorithm, restated: candidates are visited in STABLE descending score
+    order; j is suppressed by a kept i iff inter/(area_i+area_j-inter) > thr with every operation in fp32;
+    returns kept ORIGINAL indices (int64) in visiting order.  NaN IoU (zero areas) never suppresses."""
+    boxes = np.ascontiguousarray(boxes, dtype=np.float32)
+    scores = np.asarray(scores, dtype=np.float32)
+    n = boxes.shape[0]
+    if n == 0:
+        return np.zeros((0,), np.int64)
+    order = np.argsort(-scores, kind="stable")
+    x1, y1, x2, y2 = (boxes[order, k] for k in range(4))
+    areas = ((x2 - x1) * (y2 - y1)).astype(np.float32)
+    suppressed = np.zeros(n, bool)
+    keep = []
+    thr = np.float32(iou_thres)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        for i in range(n):
+            if suppressed[i]:
+                continue
+            keep.append(order[i])
+            if i + 1 == n:
+                break
+            xx1 = np.maximum(x1[i], x1[i + 1:])
+            yy1 = np.maximum(y1[i], y1[i + 1:])
+            xx2 = np.minimum(x2[i], x2[i + 1:])
+            yy2 = np.minimum(y2[i], y2[i + 1:])
+            w = np.maximum(np.float32(0), (xx2 - xx1).astype(np.float32))
+            h = np.maximum(np.float32(0), (yy2 - yy1).astype(np.float32))
+            inter = (w * h).astype(np.float32)
+            ovr = inter / ((areas[i] + areas[i + 1:]).astype(np.float32) - inter).astype(np.float32)
+            suppressed[i + 1:] |= ovr > thr
+    return np.asarray(keep, np.int64)
+
+
+def non_max_suppression(prediction: np.ndarray, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False,
+                        multi_label=False, max_det=300, max_nms=30000, max_wh=4096) -> List[np.ndarray]:
+    """reference utils/general.py:421-509, restated in numpy fp32 (labels=() and merge=False, the shipped
+    settings; the 10 s wall-clock bail-out :505-507 is not restated).  Returns list of (n,6) fp32."""
+    pred = np.asarray(prediction, dtype=np.float32)
+    nc = pred.shape[2] - 5
+    multi_label = multi_label and nc > 1
+    ct = np.float32(conf_thres)
+    out = []
+    for x in pred:
+        x = x[x[:, 4] > ct].copy()                                   # :430,446
+        if not x.shape[0]:
+            out.append(np.zeros((0, 6), np.float32)); continue
+        x[:, 5:] = (x[:, 5:] * x[:, 4:5]).astype(np.float32)         # :462
+        half_w = (x[:, 2] / np.float32(2)).astype(np.float32)
+        half_h = (x[:, 3] / np.float32(2)).astype(np.float32)
+        box = np.stack([x[:, 0] - half_w, x[:, 1] - half_h, x[:, 0] + half_w, x[:, 1] + half_h], 1).astype(np.float32)  # :265-272
+        if multi_label:                                              # :468-470
+            i, j = np.nonzero(x[:, 5:] > ct)
+            x = np.concatenate([box[i], x[i, j + 5, None], j[:, None].astype(np.float32)], 1)
+        else:                                                        # :471-473
+            j = x[:, 5:].argmax(1)
+            conf = x[np.arange(x.shape[0]), j + 5]
+            x = np.concatenate([box, conf[:, None], j[:, None].astype(np.float32)], 1)[conf > ct]
+        if classes is not None:                                      # :476-477
+            x = x[np.isin(x[:, 5], np.asarray(classes, np.float32))]
+        n = x.shape[0]
+        if not n:
+            out.append(np.zeros((0, 6), np.float32)); continue
+        if n > max_nms:                                              # :487-488
+            x = x[np.argsort(-x[:, 4], kind="stable")[:max_nms]]
+        c = x[:, 5:6] * np.float32(0 if agnostic else max_wh)        # :491
+        keep = nms_greedy((x[:, :4] + c).astype(np.float32), x[:, 4], iou_thres)[:max_det]  # :492-495
+        out.append(x[keep].astype(np.float32))
+    return out
+
+
+def bilinear_align_corners_np(x: np.ndarray, out_hw) -> np.ndarray:
+    """ATen upsample_bilinear2d(align_corners=True) restated in numpy fp32: scale=(in-1)/(out-1) (0 if out==1),
+    src=scale*dst, i0=floor(src), i1=i0+(i0<in-1), l1=src-i0, l0=1-l1,
+    out = lh0*(lw0*a + lw1*b) + lh1*(lw0*c + lw1*d).   x: (...,h,w) -> (...,H,W)."""
+    x = np.asarray(x, np.float32)
+    h, w = x.shape[-2:]
+    H, W = out_hw
+
+    def axis(n_in, n_out):
+        scale = np.float32(n_in - 1) / np.float32(n_out - 1) if n_out > 1 else np.float32(0)
+        src = (scale * np.arange(n_out, dtype=np.float32)).astype(np.float32)
+        i0 = np.minimum(src.astype(np.int64), n_in - 1)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        l0 = (np.float32(1) - l1).astype(np.float32)
+        return i0, i1, l0, l1
+
+    y0, y1, ly0, ly1 = axis(h, H)
+    x0, x1, lx0, lx1 = axis(w, W)
+    top = (lx0 * x[..., y0, :][..., x0] + lx1 * x[..., y0, :][..., x1]).astype(np.float32)
+    bot = (lx0 * x[..., y1, :][..., x0] + lx1 * x[..., y1, :][..., x1]).astype(np.float32)
+    return (ly0[:, None] * top + ly1[:, None] * bot).astype(np.float32)
+
+
+def seg_postprocess(seg: np.ndarray, out_hw) -> np.ndarray:
+    """reference detect.py:191-193: F.interpolate(seg,(H0,W0),'bilinear',align_corners=True) then
+    `.max(axis=0)[1]` (first maximum wins) per image.  seg: (B,C,h,w) -> (B,H0,W0) int64."""
+    up = bilinear_align_corners_np(seg, out_hw)
+    return up.argmax(axis=1).astype(np.int64)

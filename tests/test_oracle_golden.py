@@ -1,0 +1,77 @@
+"""CPU: pins oracle/restate.py against fixtures produced by the UNMODIFIED reference (oracle/make_golden.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+
+GOLD = synth.GOLDEN_DIR
+NETS = {"s_psp": "yolov5s_city_seg.yaml", "m_lab": "yolov5m_city_seg_lab.yaml", "s_bise": "yolov5s_city_seg_bise.yaml",
+        "s_base": "yolov5s_city_seg_base.yaml", "m_psp": "yolov5m_city_seg.yaml"}
+
+
+def relmax(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+@pytest.mark.parametrize("tag", list(NETS))
+def test_forward_restatement_matches_reference(tag):
+    cfg = synth.load_cfg(NETS[tag])
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1)
+    g = np.load(os.path.join(GOLD, f"net_{tag}.npz"))
+    out = restate.model_forward(cfg, sd, torch.from_numpy(g["x"]), keep=(0, 4, 9, 17, 23))
+    # fp32 CPU both sides; differences are only BN-fold order / oneDNN kernel choice
+    assert relmax(out["z"].numpy(), g["z"]) < 2e-4
+    assert relmax(out["seg"].numpy(), g["seg"]) < 2e-4
+    assert relmax(out["seg_lowres"].numpy(), g["seg_lowres"]) < 2e-4
+    for i in range(3):
+        assert out["raw"][i].shape == g[f"raw{i}"].shape
+        assert relmax(out["raw"][i].numpy(), g[f"raw{i}"]) < 2e-4
+    for i in (0, 4, 9, 17, 23):
+        assert relmax(out["layers"][i].numpy(), g[f"layer{i}"].astype(np.float32)) < 2e-3  # taps stored as fp16
+
+
+@pytest.mark.parametrize("tag", ["s_psp", "m_lab"])
+def test_fp16_emulation_mode_is_close(tag):
+    """The `quantised=True` graph (fp16 storage, fp32 accumulate — what the CUDA path computes) must stay within the
+    north_star tolerance class of the fp32 reference: this is the budget the GPU parity tests are judged against."""
+    cfg = synth.load_cfg(NETS[tag])
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1)
+    g = np.load(os.path.join(GOLD, f"net_{tag}.npz"))
+    out = restate.model_forward(cfg, sd, torch.from_numpy(g["x"]), quantised=True)
+    assert relmax(out["seg"].numpy(), g["seg"]) < 2e-2
+    assert relmax(out["raw"][0].numpy(), g["raw0"]) < 2e-2
+
+
+def test_nms_restatement_bit_exact():
+    g = np.load(os.path.join(GOLD, "nms_cases.npz"))
+    settings = json.load(open(os.path.join(GOLD, "nms_settings.json")))
+    n_checked = 0
+    for name, kw in settings.items():
+        for pn in ("big", "small"):
+            if f"out_{name}_{pn}_0" not in g:
+                continue
+            outs = restate.non_max_suppression(g[f"pred_{pn}"], **kw)
+            for b, o in enumerate(outs):
+                ref = g[f"out_{name}_{pn}_{b}"]
+                assert o.shape == ref.shape, (name, pn, b, o.shape, ref.shape)
+                assert np.array_equal(o, ref), (name, pn, b)   # bit-exact rows incl. order
+                n_checked += 1
+    assert n_checked >= 16
+
+
+def test_segpost_restatement():
+    g = np.load(os.path.join(GOLD, "segpost_cases.npz"))
+    for name, hw in {"x8": (128, 256), "odd": (40, 77), "same": (24, 24), "up2": (64, 128)}.items():
+        am = restate.seg_postprocess(g[f"in_{name}"], hw)[0]
+        ref = g[f"argmax_{name}"].astype(np.int64)
+        mism = (am != ref)
+        if f"up_{name}" in g:
+            up = restate.bilinear_align_corners_np(g[f"in_{name}"], hw)[0]
+            assert np.abs(up - g[f"up_{name}"]).max() <= 1e-5 * np.abs(g[f"up_{name}"]).max()
+        # ATen's vectorised CPU kernel may contract a*b+c*d to FMA; argmax may only differ at 1-ulp near-ties
+        assert mism.mean() < 1e-4, (name, mism.sum())
