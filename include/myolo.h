@@ -1,0 +1,146 @@
+/*
+ * libmyolo_sm100a — C ABI of the B200-native joint detection+segmentation hot path.
+ *
+ * The reference (TomMao23/multiyolov5) is pure Python: the interfaces this library sits behind are
+ *   - models.yolo.Model.forward / forward_once          (reference models/yolo.py:273-316)
+ *   - models.yolo.Model.fuse  (BN folding)              (reference models/yolo.py:339-347, utils/torch_utils.py:182-202)
+ *   - utils.general.non_max_suppression                 (reference utils/general.py:421-509)
+ *   - detect.py's seg upsample + argmax                 (reference detect.py:191-193)
+ * so the "FFI binding" a maintainer adds on the reference side is a ctypes stub.
+ *
+ * Conventions
+ *   - every entry point returns 0 on success, a negative MYOLO_E_* code otherwise; myolo_last_error()
+ *     returns a thread-local human readable message.  No C++ exceptions cross the ABI.
+ *   - all data pointers are DEVICE pointers unless the name says `host_`; the library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream); the library never
+ *     synchronises the device on its own.
+ *   - there is NO CPU fallback: every function needs an sm_100 device and fails loudly otherwise.
+ */
+#ifndef MYOLO_H_
+#define MYOLO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MYOLO_ABI_VERSION 1
+
+/* error codes */
+#define MYOLO_OK 0
+#define MYOLO_E_INVALID (-1)  /* bad argument / unsupported shape           */
+#define MYOLO_E_CUDA (-2)     /* CUDA runtime / driver error                */
+#define MYOLO_E_NODEVICE (-3) /* no sm_100 device                           */
+#define MYOLO_E_STATE (-4)    /* call order (e.g. forward before weights)   */
+
+/* dtypes */
+#define MYOLO_F16 0
+#define MYOLO_F32 1
+#define MYOLO_U8 2
+#define MYOLO_I64 3
+
+/* activation of a conv op */
+#define MYOLO_ACT_NONE 0
+#define MYOLO_ACT_SILU 1    /* nn.SiLU, reference models/common.py:40 */
+#define MYOLO_ACT_SIGMOID 2 /* nn.Sigmoid in FFM attention, reference models/common.py:220 */
+
+/* op kinds of the layer plan (what Model.forward_once executes, reference models/yolo.py:293-316) */
+#define MYOLO_OP_INPUT_FOCUS 1   /* NCHW image -> 2x2 space-to-depth NHWC fp16 (Focus.forward, models/common.py:549-550) */
+#define MYOLO_OP_CONV 2          /* conv(+folded BN)+bias+act(+residual): Conv/Bottleneck, models/common.py:42-46,104-105 */
+#define MYOLO_OP_UPSAMPLE_NEAREST 3 /* nn.Upsample(None,2,'nearest'), yaml layers 11/15 */
+#define MYOLO_OP_SPP_POOL 4      /* cascaded stride-1 max pools 5/9/13, models/common.py:170-174 */
+#define MYOLO_OP_BILINEAR 5      /* bilinear align_corners=True NHWC->NHWC, models/yolo.py:163,170,174; models/common.py:534-537 */
+#define MYOLO_OP_REGION_SUM 6    /* fp32 sums over rectangular atoms (stage 1 of AdaptiveAvgPool2d / GAP) */
+#define MYOLO_OP_REGION_COMBINE 7 /* bins = sum(atoms)/count   (stage 2; models/common.py:521-524, :214) */
+#define MYOLO_OP_CHANNEL_SCALE 8 /* FFM: feat*att+feat in place, models/common.py:228-229 */
+#define MYOLO_OP_ADD 9           /* elementwise add (SegMaskBiSe m16 + up32, models/yolo.py:83) */
+#define MYOLO_OP_DETECT_DECODE 10 /* Detect.forward view/permute/sigmoid/decode, models/yolo.py:211-225 */
+#define MYOLO_OP_SEG_UPSAMPLE 11 /* final x8 bilinear of the seg head -> NCHW logits, models/yolo.py:163 */
+#define MYOLO_OP_BROADCAST 12    /* F.interpolate(nearest) of a 1x1 map (RFB2 global branch), models/common.py:509 */
+
+/* conv op flags */
+#define MYOLO_CONV_FORCE_SIMT 1 /* run on the generic CUDA-core kernel (tiny M / odd shapes / debugging) */
+
+typedef struct {
+  int32_t h, w, c; /* per-image NHWC extents; batch is the plan's B */
+  int32_t dtype;   /* MYOLO_F16 or MYOLO_F32 */
+  int64_t offset;  /* byte offset inside the plan workspace (liveness-packed by the host-side planner) */
+} myolo_buf_desc;
+
+typedef struct {
+  int32_t buf;   /* index into the buffer table, -1 = none */
+  int32_t c_off; /* first channel of the slice */
+  int32_t c;     /* channels in the slice */
+} myolo_view;
+
+typedef struct {
+  int32_t kind;
+  myolo_view in;  /* main input                                      */
+  myolo_view in2; /* residual (CONV) / second addend (ADD) / attention (CHANNEL_SCALE) */
+  myolo_view out;
+  int32_t k, stride, dil; /* CONV geometry; pad = dil*(k/2)             */
+  int32_t act;
+  int32_t flags;
+  int32_t weight_slot;    /* CONV: index used with myolo_plan_set_conv_weights */
+  int32_t aux[8];         /* kind specific (documented in multiyolov5_b200/plan.py) */
+  float faux[4];
+} myolo_op;
+
+typedef struct myolo_plan myolo_plan;
+
+/* ---- library ---- */
+int myolo_abi_version(void);
+const char* myolo_last_error(void);
+/* fills name (<=255 chars), SM count, compute capability major/minor of the current device */
+int myolo_device_info(char* name, int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- layer plan: what Model.__init__/fuse + forward_once become ---- */
+int myolo_plan_create(const myolo_op* ops, int n_ops, const myolo_buf_desc* bufs, int n_bufs,
+                      const int32_t* extra, int n_extra, /* variable-length tables referenced by aux[] */
+                      int B, int H, int W, int64_t workspace_bytes, int n_weight_slots, myolo_plan** out);
+void myolo_plan_destroy(myolo_plan* plan);
+/* folds BN (eval: w' = w*g/sqrt(var+eps), b' = beta - g*mean/sqrt(var+eps); reference utils/torch_utils.py:182-202),
+ * converts to fp16 and packs [Co][Ci][k][k] fp32 -> [Co_pad][k*k][Ci_pad].  gamma..var / bias may be NULL. */
+int myolo_plan_set_conv_weights(myolo_plan* plan, int weight_slot, const float* w, int co, int ci, int k,
+                                const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                                const float* bias, void* stream);
+/* One forward pass.  x: (B,3,H,W) NCHW of x_dtype (F32/F16 in [0,1], or U8 scaled by 1/255 like detect.py:137).
+ * z: (B, sum_i 3*ny_i*nx_i, 5+nc) fp32;  raw[i]: (B,3,ny_i,nx_i,5+nc) fp32 (nullable);
+ * seg: (B,n_segcls,H,W) of seg_dtype (nullable); seg_argmax: (B,H,W) int64 class ids (nullable, fused path). */
+int myolo_plan_forward(myolo_plan* plan, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
+                       int64_t* seg_argmax, void* stream);
+/* debugging / per-layer parity: copies the NHWC buffer slice of a view into dst as (B,C,H,W) fp32 */
+int myolo_plan_read_view(myolo_plan* plan, myolo_view view, float* dst_nchw, void* stream);
+/* number of kernels the last myolo_plan_forward launched (bench.py's gpu_launches) */
+int64_t myolo_plan_last_launch_count(const myolo_plan* plan);
+/* per-op device time of the next forward (CUDA events around every op; host array of n_ops floats, ms) */
+int myolo_plan_profile(myolo_plan* plan, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
+                       int64_t* seg_argmax, float* host_ms_per_op, void* stream);
+
+/* ---- post-process ---- */
+/* utils.general.non_max_suppression (reference utils/general.py:421-509).  pred: (B,A,no) fp32.
+ * out: (B,max_det,6) fp32 rows [x1,y1,x2,y2,conf,cls] in the reference's order; out_count: (B) int32.
+ * classes: device int32 list or NULL.  workspace: >= myolo_nms_workspace_bytes(B,A,no,multi_label). */
+int64_t myolo_nms_workspace_bytes(int B, int A, int no, int multi_label);
+int myolo_nms(const float* pred, int B, int A, int no, float conf_thres, float iou_thres, const int32_t* classes,
+              int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float max_wh, float* out,
+              int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream);
+/* detect.py:191-193: bilinear(align_corners=True) to (H,W) then argmax over C (first max wins).
+ * logits: (B,C,h,w) NCHW fp32/fp16.  out: (B,H,W) int64 (out_dtype I64) or uint8 (U8). */
+int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, int C, int h, int w, int H, int W, void* out,
+                              int out_dtype, void* stream);
+/* F.interpolate(seg,(H,W),'bilinear',align_corners=True) on NCHW fp32 (materialised logits) */
+int myolo_bilinear_nchw(const float* src, int B, int C, int h, int w, int H, int W, float* dst, void* stream);
+
+/* ---- standalone kernels for per-op parity tests and ncu captures ---- */
+/* SiLU(conv(x)*bnscale+bnshift) on NHWC fp16: x (B,H,W,Ci) -> y (B,Ho,Wo,Co); w fp32 [Co][Ci][k][k]; path: 0 auto, 1 tcgen05, 2 simt */
+int myolo_conv_bn_silu(const void* x_nhwc_f16, int B, int H, int W, int ci, const float* w, int co, int k, int stride,
+                       int dil, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                       const float* bias, int act, const void* residual_nhwc_f16, void* y_nhwc_f16, int path, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYOLO_H_ */

@@ -1,0 +1,475 @@
+// Fused Conv(+folded BN)+bias+SiLU(+residual) as an implicit GEMM on the 5th-gen tensor cores (tcgen05), sm_100a only.
+//
+//   D[128 pixels x BN channels] (fp32, TMEM)  +=  A[128 x kc] (NHWC activations, fp16)  *  B[BN x kc]^T (packed weights, fp16)
+//
+// * M tile  = a tw x th rectangle of output pixels of ONE image (tw*th = 128).  For every filter tap the A operand is the
+//   same rectangle shifted by (dx,dy): one 4-D TMA box load {kc channels, tw, th, 1} with hardware zero fill at the
+//   image border (that is the conv padding).  Stride-2 convs use four "parity" tensor maps (even/odd rows x cols)
+//   so that the stride-2 gather is again a dense box.  No im2col buffer ever exists in HBM.
+// * K loop  = taps x (Ci/kc) chunks, grouped 64 K-elements per pipeline stage; both operands are K-major with the
+//   32/64/128-byte TMA swizzle that the UMMA shared-memory descriptor names.
+// * warp roles (192 threads): warp0 = TMA producer (1 thread), warp1 = MMA issuer (1 thread; the warp owns TMEM
+//   alloc/dealloc), warps 2..5 = epilogue (TMEM -> regs -> bias/SiLU/residual -> fp16 -> swizzled smem -> TMA store
+//   into the channel slice of the consumer's concat buffer).  Two TMEM accumulator stages overlap epilogue and MMA.
+// * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+//
+// Reference semantics: Conv.fuseforward (reference models/common.py:45-46) with BN folded as in
+// utils/torch_utils.py:182-202; Bottleneck shortcut add (models/common.py:105).
+#include "conv.h"
+
+namespace myolo {
+
+static constexpr int kTileM = 128;
+static constexpr int kKStage = 64;        // K elements per pipeline stage
+static constexpr int kABytesStage = kTileM * kKStage * 2;  // 16 KB
+static constexpr int kNumThreads = 192;
+static constexpr int kTmemCols = 256;     // 2 accumulator stages x 128 columns
+static constexpr int kAccStride = 128;
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
+  // K-major canonical layout, rows of kc*2 bytes, 8-row groups (reference: PTX ISA "matrix descriptor", sm_100 version=1)
+  const uint32_t sw_bytes = kc * 2;
+  const uint64_t layout = sw_bytes == 128 ? 2ull : (sw_bytes == 64 ? 4ull : 6ull);
+  const uint64_t sbo = (8u * sw_bytes) >> 4;
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major), bits [16,30)
+  d |= sbo << 32;                            // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= layout << 61;                         // swizzle mode
+  return d;
+}
+
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+               const __grid_constant__ ConvTcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (everything 1024-aligned; dynamic smem base is only guaranteed 16B aligned -> align by hand)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_stages;
+  const int b_bytes_stage = p.BN * kKStage * 2;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + S * kABytesStage;
+  uint8_t* smem_o = smem_b + S * b_bytes_stage;
+  const int sub_bytes = kTileM * p.ow * 2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + p.n_sub * sub_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + S;
+  uint64_t* tfull_bar = bars + 2 * S;
+  uint64_t* tempty_bar = bars + 2 * S + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmB);
+    if (p.out_mode == 0) tma_prefetch_desc(&tmO);
+    for (int i = 0; i < S; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int a_sub_bytes = kTileM * p.kc * 2;
+  const int b_sub_bytes = p.BN * p.kc * 2;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int b = m_tile / tiles_per_img;
+      const int r = m_tile - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * p.th;
+      const int x0 = (r % p.tiles_x) * p.tw;
+      const int n0 = n_tile * p.BN;
+      for (int ks = 0; ks < p.n_kstages; ++ks) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const int q0 = ks * p.chunks_per_stage;
+        const int nch = min(p.chunks_per_stage, p.n_chunks - q0);
+        mbar_arrive_expect_tx(&full_bar[stage], nch * (a_sub_bytes + b_sub_bytes));
+        uint8_t* sa = smem_a + stage * kABytesStage;
+        uint8_t* sb = smem_b + stage * b_bytes_stage;
+        for (int j = 0; j < nch; ++j) {
+          const int q = q0 + j;
+          const int tap = q / p.cblocks;
+          const int cb = q - tap * p.cblocks;
+          const int mi = p.tap_map[tap];
+          const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+          tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b);
+          tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, n0);
+        }
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer (single thread) =====================
+    const uint32_t idesc = (1u << 4)                       // D format: fp32
+                           | (0u << 7) | (0u << 10)        // A, B format: fp16
+                           | (0u << 15) | (0u << 16)       // A, B K-major
+                           | ((uint32_t)(p.BN >> 3) << 17) // N
+                           | ((uint32_t)(kTileM >> 4) << 24);  // M
+    int stage = 0;
+    uint32_t phase = 0;
+    int as = 0;
+    uint32_t aphase = 0;
+    const int kmma = p.kc / 16;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      for (int ks = 0; ks < p.n_kstages; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tcgen05_fence_after();
+        const int q0 = ks * p.chunks_per_stage;
+        const int nch = min(p.chunks_per_stage, p.n_chunks - q0);
+        const uint32_t sa = smem_u32(smem_a + stage * kABytesStage);
+        const uint32_t sb = smem_u32(smem_b + stage * b_bytes_stage);
+        for (int j = 0; j < nch; ++j) {
+          const uint64_t da = make_smem_desc(sa + j * a_sub_bytes, p.kc);
+          const uint64_t db = make_smem_desc(sb + j * b_sub_bytes, p.kc);
+          for (int k = 0; k < kmma; ++k) {
+            // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+            umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((ks | j | k) != 0));
+          }
+        }
+        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+  } else if (warp >= 2) {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;   // tile row == pixel index inside the tw x th rectangle
+    const int et = threadIdx.x - 64;       // 0..127
+    int as = 0;
+    uint32_t aphase = 0;
+    const int nchunk16 = p.BN / 16;
+    const int units_per_row = p.ow / 8;    // 16-byte units per staging row
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles_n;
+      const int m_tile = tile / p.n_tiles_n;
+      const int b = m_tile / tiles_per_img;
+      const int r = m_tile - b * tiles_per_img;
+      const int y0 = (r / p.tiles_x) * p.th;
+      const int x0 = (r % p.tiles_x) * p.tw;
+      const int n0 = n_tile * p.BN;
+      const int py = y0 + row / p.tw;
+      const int px = x0 + row % p.tw;
+      const bool pix_ok = (py < p.Ho) && (px < p.Wo);
+      const size_t pix = ((size_t)b * p.Ho + py) * p.Wo + px;
+
+      mbar_wait(&tfull_bar[as], aphase);
+      tcgen05_fence_after();
+      if (p.out_mode == 0) {
+        // staging smem is about to be overwritten: the previous tile's TMA stores must have finished reading it
+        if (et == 0) tma_store_wait_read0();
+        named_bar_sync(1, 128);
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride;
+      for (int c = 0; c < nchunk16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(taddr + c * 16, v);
+        tmem_ld_wait();
+        const int nb = n0 + c * 16;
+        float f[16];
+        const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = __ldg(bp + i);
+          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
+          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
+          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
+          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
+        }
+        if (p.act == MYOLO_ACT_SILU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
+        } else if (p.act == MYOLO_ACT_SIGMOID) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = sigmoid_f(f[i]);
+        }
+        if (p.residual != nullptr && pix_ok) {
+          const __half* rp = p.residual + pix * p.res_ctot + nb;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (nb + h * 8 < p.Co) {
+              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + h * 8));
+              const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 rf = __half22float2(r2[i]);
+                f[h * 8 + 2 * i] += rf.x;
+                f[h * 8 + 2 * i + 1] += rf.y;
+              }
+            }
+          }
+        }
+        if (p.out_mode == 0) {
+          const int sub = (c * 16) / p.ow;
+          const int u0 = ((c * 16) % p.ow) / 8;
+          uint8_t* srow = smem_o + sub * sub_bytes + row * (p.ow * 2);
+          int sw;
+          if (units_per_row == 8) sw = row & 7;
+          else if (units_per_row == 4) sw = (row >> 1) & 3;
+          else sw = (row >> 2) & 1;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint4 o;
+            __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[h * 8 + 2 * i], f[h * 8 + 2 * i + 1]);
+            *reinterpret_cast<uint4*>(srow + (((u0 + h) ^ sw) * 16)) = o;
+          }
+        } else if (pix_ok) {
+          float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (nb + 4 * i < p.out_f32_ctot)
+              *reinterpret_cast<float4*>(op + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tcgen05_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      if (p.out_mode == 0) {
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (et == 0) {
+          for (int s = 0; s < p.n_sub; ++s) {
+            if (n0 + s * p.ow < p.Co) tma_store_4d(&tmO, smem_o + s * sub_bytes, n0 + s * p.ow, x0, y0, b);
+          }
+          tma_store_commit();
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (p.out_mode == 0 && et == 0) tma_store_wait_all();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+static int encode_map(CUtensorMap* m, int rank, void* addr, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return MYOLO_E_CUDA;
+  }
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, addr, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu box %u %u %u %u sw %d", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+              swizzle_bytes);
+    return MYOLO_E_CUDA;
+  }
+  return 0;
+}
+
+static void choose_tile(int W, int H, int* tw, int* th) {
+  long best = -1;
+  for (int t = 128; t >= 8; t >>= 1) {
+    const int hh = 128 / t;
+    const long tiles = (long)ceil_div(W, t) * ceil_div(H, hh);
+    if (best < 0 || tiles < best) {
+      best = tiles;
+      *tw = t;
+      *th = hh;
+    }
+  }
+}
+
+bool conv_tc_eligible(const ConvOp& op) {
+  if (op.in.dtype != MYOLO_F16) return false;
+  if (op.Ci_pad % 16 != 0 || op.in.C != op.Ci_pad) return false;
+  if (!(op.k == 1 || op.k == 3)) return false;
+  if (!(op.stride == 1 || (op.stride == 2 && op.k == 3 && op.dil == 1))) return false;
+  if (op.stride == 2 && ((op.in.H | op.in.W) & 1)) return false;
+  if (op.in.ctot % 8 != 0) return false;
+  if (op.out.dtype == MYOLO_F16) {
+    if (op.out.C % 8 != 0 || op.out.ctot % 8 != 0) return false;
+    if (op.has_res && (op.res.dtype != MYOLO_F16 || op.res.ctot % 8 != 0 || op.Co % 16 != 0)) return false;
+  } else {
+    if (op.has_res || op.out.ctot % 4 != 0) return false;
+  }
+  // tiny maps run on the generic kernel (TMA boxes larger than the tensor are avoided on purpose)
+  if (op.out.W < 8 || op.out.H < 2 || op.out.W * op.out.H < 128) return false;
+  return true;
+}
+
+int conv_tc_prepare(ConvOp& op, int num_sms) {
+  ConvTcParams& p = op.p;
+  memset(&p, 0, sizeof(p));
+  const int Ho = op.out.H, Wo = op.out.W;
+  p.B = op.in.B;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  choose_tile(Wo, Ho, &p.tw, &p.th);
+  p.tiles_x = ceil_div(Wo, p.tw);
+  p.tiles_y = ceil_div(Ho, p.th);
+  p.Co = op.Co;
+  // N tile: whole Co if it fits in 128, else 128 (Co_pad was sized as a multiple of BN by the planner)
+  const int co16 = (int)align_up(op.Co, 16);
+  p.BN = co16 <= 128 ? co16 : 128;
+  if (co16 > 128 && co16 % 128 != 0) {
+    // e.g. Co = 192, 384: use the largest multiple of 16 <= 128 that divides co16
+    for (int bn = 128; bn >= 16; bn -= 16)
+      if (co16 % bn == 0) { p.BN = bn; break; }
+  }
+  p.n_tiles_n = ceil_div(co16, p.BN);
+  MYOLO_REQUIRE(op.Co_pad >= p.n_tiles_n * p.BN, "conv_tc: Co_pad %d < %d", op.Co_pad, p.n_tiles_n * p.BN);
+  p.total_tiles = p.B * p.tiles_x * p.tiles_y * p.n_tiles_n;
+  p.kc = op.Ci_pad % 64 == 0 ? 64 : (op.Ci_pad % 32 == 0 ? 32 : 16);
+  p.cblocks = op.Ci_pad / p.kc;
+  p.taps = op.k * op.k;
+  p.n_chunks = p.taps * p.cblocks;
+  p.chunks_per_stage = kKStage / p.kc;
+  p.n_kstages = ceil_div(p.n_chunks, p.chunks_per_stage);
+  p.act = op.act;
+  p.bias = op.bias;
+  p.residual = op.has_res ? reinterpret_cast<const __half*>(op.res.base) : nullptr;
+  p.res_ctot = op.has_res ? op.res.ctot : 0;
+  p.out_mode = op.out.dtype == MYOLO_F16 ? 0 : 1;
+  p.out_f32 = p.out_mode ? reinterpret_cast<float*>(op.out.base) : nullptr;
+  p.out_f32_ctot = p.out_mode ? op.out.ctot : 0;
+  p.ow = p.BN >= 64 ? 64 : (p.BN >= 32 ? 32 : 16);
+  p.n_sub = p.out_mode == 0 ? ceil_div(p.BN, p.ow) : 0;
+  for (int t = 0; t < p.taps; ++t) {
+    const int ky = op.k == 3 ? t / 3 : 1, kx = op.k == 3 ? t % 3 : 1;
+    if (op.stride == 1) {
+      p.tap_map[t] = 0;
+      p.tap_dx[t] = (kx - 1) * op.dil;
+      p.tap_dy[t] = (ky - 1) * op.dil;
+    } else {  // stride 2, k 3, pad 1: input row = 2*oy + ky - 1
+      const int pyb = (ky == 1) ? 0 : 1, pxb = (kx == 1) ? 0 : 1;
+      p.tap_map[t] = pyb * 2 + pxb;
+      p.tap_dy[t] = (ky == 0) ? -1 : 0;
+      p.tap_dx[t] = (kx == 0) ? -1 : 0;
+    }
+  }
+  // shared memory budget
+  const int stage_bytes = kABytesStage + p.BN * kKStage * 2;
+  const int fixed = p.n_sub * kTileM * p.ow * 2 + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  int S = (220 * 1024 - fixed) / stage_bytes;
+  if (S > 8) S = 8;
+  MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");
+  p.num_stages = S;
+  op.smem = S * stage_bytes + fixed;
+  op.grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+
+  // ---- tensor maps ----
+  const int esz = 2;
+  const int sw = p.kc * 2;
+  const TensorView& in = op.in;
+  if (op.stride == 1) {
+    uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)in.B};
+    uint64_t str[3] = {(uint64_t)in.ctot * esz, (uint64_t)in.W * in.ctot * esz, (uint64_t)in.H * in.W * in.ctot * esz};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    int rc = encode_map(&op.tmA[0], 4, in.base, dims, str, box, sw);
+    if (rc) return rc;
+    op.tmA[1] = op.tmA[2] = op.tmA[3] = op.tmA[0];
+  } else {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W / 2, (uint64_t)in.H / 2, (uint64_t)in.B};
+        uint64_t str[3] = {(uint64_t)2 * in.ctot * esz, (uint64_t)2 * in.W * in.ctot * esz,
+                           (uint64_t)in.H * in.W * in.ctot * esz};
+        uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.tw, (uint32_t)p.th, 1};
+        void* base = reinterpret_cast<__half*>(in.base) + ((size_t)py * in.W + px) * in.ctot;
+        int rc = encode_map(&op.tmA[py * 2 + px], 4, base, dims, str, box, sw);
+        if (rc) return rc;
+      }
+  }
+  {
+    const uint64_t Kt = (uint64_t)p.taps * op.Ci_pad;
+    uint64_t dims[2] = {Kt, (uint64_t)op.Co_pad};
+    uint64_t str[1] = {Kt * esz};
+    uint32_t box[2] = {(uint32_t)p.kc, (uint32_t)p.BN};
+    int rc = encode_map(&op.tmB, 2, const_cast<__half*>(op.w), dims, str, box, sw);
+    if (rc) return rc;
+  }
+  if (p.out_mode == 0) {
+    const TensorView& o = op.out;
+    uint64_t dims[4] = {(uint64_t)o.C, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)o.B};
+    uint64_t str[3] = {(uint64_t)o.ctot * esz, (uint64_t)o.W * o.ctot * esz, (uint64_t)o.H * o.W * o.ctot * esz};
+    uint32_t box[4] = {(uint32_t)p.ow, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    int rc = encode_map(&op.tmO, 4, o.base, dims, str, box, p.ow * 2);
+    if (rc) return rc;
+  } else {
+    op.tmO = op.tmB;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  return 0;
+}
+
+int conv_tc_launch(const ConvOp& op, cudaStream_t stream) {
+  conv_tc_kernel<<<op.grid, kNumThreads, op.smem, stream>>>(op.tmA[0], op.tmA[1], op.tmA[2], op.tmA[3], op.tmB, op.tmO, op.p);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace myolo

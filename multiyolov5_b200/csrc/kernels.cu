@@ -1,0 +1,545 @@
+// HBM-bound kernels of the path: layout/boundary conversion, pooling pyramids, bilinear/nearest resampling, Detect decode,
+// seg-logit upsample (+argmax).  All are coalesced 16-byte-vector kernels over NHWC fp16 slices; none of this work is
+// reshaped into GEMMs.
+#include "kernels.h"
+
+namespace myolo {
+
+static inline int grid_for(long items, int block, int max_blocks = 148 * 32) {
+  long b = (items + block - 1) / block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+__device__ __forceinline__ __half* vptr(const TensorView& v, int b, int y, int x) {
+  return reinterpret_cast<__half*>(v.base) + (((size_t)b * v.H + y) * v.W + x) * v.ctot;
+}
+__device__ __forceinline__ float* vptr_f(const TensorView& v, int b, int y, int x) {
+  return reinterpret_cast<float*>(v.base) + (((size_t)b * v.H + y) * v.W + x) * v.ctot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// input: NCHW image -> Focus space-to-depth NHWC fp16 (12 channels, zero padded to the view's 16)
+//   channel = g*3 + c with g enumerating (dy,dx) = (0,0),(1,0),(0,1),(1,1)  [reference models/common.py:550]
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float to_unit(T v);
+template <> __device__ __forceinline__ float to_unit<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_unit<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_unit<uint8_t>(uint8_t v) { return (float)v / 255.0f; }  // detect.py:137
+
+template <typename T>
+__global__ void input_focus_kernel(const T* __restrict__ x, int B, int H, int W, TensorView out) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long total = (long)B * Ho * Wo;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Wo);
+    const int oy = (int)((i / Wo) % Ho);
+    const int b = (int)(i / ((long)Wo * Ho));
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T* p = x + (((size_t)b * 3 + c) * H + 2 * oy) * W + 2 * ox;
+      v[0 * 3 + c] = __float2half_rn(to_unit<T>(p[0]));
+      v[2 * 3 + c] = __float2half_rn(to_unit<T>(p[1]));
+      v[1 * 3 + c] = __float2half_rn(to_unit<T>(p[W]));
+      v[3 * 3 + c] = __float2half_rn(to_unit<T>(p[W + 1]));
+    }
+#pragma unroll
+    for (int c = 12; c < 16; ++c) v[c] = __float2half_rn(0.f);
+    uint4* o = reinterpret_cast<uint4*>(vptr(out, b, oy, ox));
+    o[0] = reinterpret_cast<uint4*>(v)[0];
+    o[1] = reinterpret_cast<uint4*>(v)[1];
+  }
+}
+
+int launch_input_focus(const void* x, int x_dtype, int B, int H, int W, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(out.C == 16 && out.dtype == MYOLO_F16 && out.H == H / 2 && out.W == W / 2 && H % 2 == 0 && W % 2 == 0,
+                "input_focus: bad output view");
+  const long total = (long)B * (H / 2) * (W / 2);
+  const int g = grid_for(total, 256);
+  if (x_dtype == MYOLO_F32) input_focus_kernel<float><<<g, 256, 0, s>>>((const float*)x, B, H, W, out);
+  else if (x_dtype == MYOLO_F16) input_focus_kernel<__half><<<g, 256, 0, s>>>((const __half*)x, B, H, W, out);
+  else if (x_dtype == MYOLO_U8) input_focus_kernel<uint8_t><<<g, 256, 0, s>>>((const uint8_t*)x, B, H, W, out);
+  else MYOLO_REQUIRE(false, "input_focus: unsupported dtype %d", x_dtype);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// nearest x2 (yaml layers 11, 15)
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample_nearest2x_kernel(TensorView in, TensorView out) {
+  const int nv = out.C / 8;
+  const long total = (long)out.B * out.H * out.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % out.W);
+    p /= out.W;
+    const int y = (int)(p % out.H);
+    const int b = (int)(p / out.H);
+    const uint4 val = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, y >> 1, x >> 1)) + v);
+    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = val;
+  }
+}
+int launch_upsample_nearest2x(const TensorView& in, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0,
+                "upsample_nearest2x: bad views");
+  upsample_nearest2x_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// SPP: three cascaded 5x5 stride-1 "same" max pools == maxpool 5 / 9 / 13 (max is idempotent over window unions)
+// one CTA per (image, 8-channel vector); the whole H x W map of that vector lives in shared memory.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
+  uint4 r;
+  __half2* rr = reinterpret_cast<__half2*>(&r);
+  const __half2* aa = reinterpret_cast<const __half2*>(&a);
+  const __half2* bb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) rr[i] = __hmax2(aa[i], bb[i]);
+  return r;
+}
+
+__global__ void spp_pool_kernel(TensorView in, TensorView out, int n_cascade) {
+  extern __shared__ uint4 spp_smem[];
+  const int HW = in.H * in.W;
+  uint4* cur = spp_smem;
+  uint4* tmp = spp_smem + HW;
+  const int nv = in.C / 8;
+  const int b = blockIdx.x / nv, v = blockIdx.x % nv;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x)
+    cur[i] = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, i / in.W, i % in.W)) + v);
+  __syncthreads();
+  for (int stage = 0; stage < n_cascade; ++stage) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int y = i / in.W, x = i % in.W;
+      uint4 m = cur[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int xx = x + d;
+        if (d != 0 && xx >= 0 && xx < in.W) m = hmax8(m, cur[y * in.W + xx]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const int y = i / in.W, x = i % in.W;
+      uint4 m = tmp[i];
+#pragma unroll
+      for (int d = -2; d <= 2; ++d) {
+        const int yy = y + d;
+        if (d != 0 && yy >= 0 && yy < in.H) m = hmax8(m, tmp[yy * in.W + x]);
+      }
+      // output slice `stage` sits stage*C channels after the first output slice
+      reinterpret_cast<uint4*>(vptr(out, b, y, x) + stage * in.C)[v] = m;
+      cur[i] = m;  // each thread rewrites only the element it owns in this pass; readers of `cur` are behind the barrier
+    }
+    __syncthreads();
+  }
+}
+int launch_spp_pool(const TensorView& in, const TensorView& out5, int n_cascade, cudaStream_t s) {
+  MYOLO_REQUIRE(in.C % 8 == 0 && in.ctot % 8 == 0 && out5.ctot % 8 == 0 && in.H == out5.H && in.W == out5.W, "spp_pool: bad views");
+  const size_t smem = (size_t)in.H * in.W * 16 * 2;
+  MYOLO_REQUIRE(smem <= 200 * 1024, "spp_pool: map %dx%d too large for the shared-memory kernel", in.H, in.W);
+  static bool attr = false;
+  if (!attr) {
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  spp_pool_kernel<<<in.B * (in.C / 8), 256, smem, s>>>(in, out5, n_cascade);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear, align_corners=True, NHWC fp16 -> NHWC fp16 slice (ATen upsample_bilinear2d index math)
+// ------------------------------------------------------------------------------------------------
+struct Lerp { int i0, i1; float l0, l1; };
+__device__ __forceinline__ Lerp lerp_axis(int dst, int n_in, int n_out) {
+  const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  const float src = __fmul_rn(scale, (float)dst);
+  Lerp r;
+  r.i0 = min((int)src, n_in - 1);
+  r.i1 = r.i0 + (r.i0 < n_in - 1 ? 1 : 0);
+  r.l1 = __fsub_rn(src, (float)r.i0);
+  r.l0 = __fsub_rn(1.0f, r.l1);
+  return r;
+}
+// exact ATen order, no FMA contraction: lh0*(lw0*a + lw1*b) + lh1*(lw0*c + lw1*d)
+__device__ __forceinline__ float bilerp(float a, float b, float c, float d, const Lerp& ly, const Lerp& lx) {
+  const float top = __fadd_rn(__fmul_rn(lx.l0, a), __fmul_rn(lx.l1, b));
+  const float bot = __fadd_rn(__fmul_rn(lx.l0, c), __fmul_rn(lx.l1, d));
+  return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
+}
+
+__global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
+  const int nv = out.C / 8;
+  const long total = (long)out.B * out.H * out.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % out.W);
+    p /= out.W;
+    const int y = (int)(p % out.H);
+    const int b = (int)(p / out.H);
+    const Lerp ly = lerp_axis(y, in.H, out.H), lx = lerp_axis(x, in.W, out.W);
+    const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i0)) + v);
+    const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i1)) + v);
+    const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i0)) + v);
+    const uint4 qd = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i1)) + v);
+    const __half* ha = reinterpret_cast<const __half*>(&qa);
+    const __half* hb = reinterpret_cast<const __half*>(&qb);
+    const __half* hc = reinterpret_cast<const __half*>(&qc);
+    const __half* hd = reinterpret_cast<const __half*>(&qd);
+    uint4 o;
+    __half* ho = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
+    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = o;
+  }
+}
+int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0 && in.dtype == MYOLO_F16 &&
+                    out.dtype == MYOLO_F16,
+                "bilinear_nhwc: bad views");
+  bilinear_nhwc_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptive average pooling in two deterministic stages.
+//   stage 1: fp32 sums over "atoms" = cells of the grid formed by the union of all bin boundaries (one CTA per atom)
+//   stage 2: bin = sum of a rectangle of atoms / pixel count   (AdaptiveAvgPool2d bins: start=floor(i*H/k), end=ceil((i+1)*H/k))
+// ------------------------------------------------------------------------------------------------
+__global__ void region_sum_kernel(TensorView in, const int* __restrict__ yb, int ny, const int* __restrict__ xb, int nx,
+                                  TensorView out) {
+  __shared__ float red[256 * 8];
+  const int atom = blockIdx.x % (ny * nx);
+  const int b = blockIdx.x / (ny * nx);
+  const int ay = atom / nx, ax = atom % nx;
+  const int y0 = yb[ay], y1 = yb[ay + 1], x0 = xb[ax], x1 = xb[ax + 1];
+  const int nv = in.C / 8;
+  const int lanes = blockDim.x / nv;  // pixel lanes
+  const int v = threadIdx.x % nv, pl = threadIdx.x / nv;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  const int w = x1 - x0, npx = (y1 - y0) * w;
+  if (pl < lanes) {
+    for (int i = pl; i < npx; i += lanes) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, y0 + i / w, x0 + i % w)) + v);
+      const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        acc[2 * k] += f.x;
+        acc[2 * k + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[threadIdx.x * 8 + k] = acc[k];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < lanes; ++l)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += red[(l * nv + v) * 8 + k];
+    float* o = vptr_f(out, b, ay, ax) + v * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = acc[k];
+  }
+}
+int launch_region_sum(const TensorView& in, const int* d_yb, int ny, const int* d_xb, int nx, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(in.dtype == MYOLO_F16 && out.dtype == MYOLO_F32 && in.C % 8 == 0 && in.C / 8 <= 256 && out.C == in.C &&
+                    out.H == ny && out.W == nx && in.ctot % 8 == 0,
+                "region_sum: bad views");
+  region_sum_kernel<<<in.B * ny * nx, 256, 0, s>>>(in, d_yb, ny, d_xb, nx, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void region_combine_kernel(TensorView atoms, const int* __restrict__ bins, int nbins, TensorView out) {
+  const long total = (long)out.B * nbins * out.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % out.C);
+    const int bin = (int)((i / out.C) % nbins);
+    const int b = (int)(i / ((long)out.C * nbins));
+    const int* bd = bins + bin * 5;
+    float sum = 0.f;
+    for (int ay = bd[0]; ay < bd[1]; ++ay)
+      for (int ax = bd[2]; ax < bd[3]; ++ax) sum += vptr_f(atoms, b, ay, ax)[c];
+    const float val = sum / (float)bd[4];
+    const int oy = bin / out.W, ox = bin % out.W;
+    if (out.dtype == MYOLO_F32) vptr_f(out, b, oy, ox)[c] = val;
+    else vptr(out, b, oy, ox)[c] = __float2half_rn(val);
+  }
+}
+int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bins, int nbins, const TensorView& out,
+                          cudaStream_t s) {
+  MYOLO_REQUIRE(atoms.dtype == MYOLO_F32 && out.H * out.W == nbins && atoms.C == out.C && atoms.W == atoms_nx,
+                "region_combine: bad views");
+  region_combine_kernel<<<grid_for((long)out.B * nbins * out.C, 256), 256, 0, s>>>(atoms, d_bins, nbins, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FFM: feat = feat*att + feat (in place); att is a (B,1,1,C) map (reference models/common.py:228-229)
+// ------------------------------------------------------------------------------------------------
+__global__ void channel_scale_kernel(TensorView feat, TensorView att) {
+  const int nv = feat.C / 8;
+  const long total = (long)feat.B * feat.H * feat.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % feat.W);
+    p /= feat.W;
+    const int y = (int)(p % feat.H);
+    const int b = (int)(p / feat.H);
+    uint4* ptr = reinterpret_cast<uint4*>(vptr(feat, b, y, x)) + v;
+    uint4 q = *ptr;
+    __half* h = reinterpret_cast<__half*>(&q);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = att.dtype == MYOLO_F32 ? vptr_f(att, b, 0, 0)[v * 8 + k] : __half2float(vptr(att, b, 0, 0)[v * 8 + k]);
+      const float f = __half2float(h[k]);
+      h[k] = __float2half_rn(fmaf(f, a, f));
+    }
+    *ptr = q;
+  }
+}
+int launch_channel_scale(const TensorView& feat, const TensorView& att, cudaStream_t s) {
+  MYOLO_REQUIRE(feat.dtype == MYOLO_F16 && feat.C % 8 == 0 && feat.ctot % 8 == 0 && att.C == feat.C && att.H == 1 && att.W == 1,
+                "channel_scale: bad views");
+  channel_scale_kernel<<<grid_for((long)feat.B * feat.H * feat.W * (feat.C / 8), 256), 256, 0, s>>>(feat, att);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void add_kernel(TensorView a, TensorView bb, TensorView out) {
+  const int nv = out.C / 8;
+  const long total = (long)out.B * out.H * out.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % out.W);
+    p /= out.W;
+    const int y = (int)(p % out.H);
+    const int b = (int)(p / out.H);
+    const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(a, b, y, x)) + v);
+    const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(bb, b, y, x)) + v);
+    const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+    const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+    uint4 o;
+    __half2* ho = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
+      ho[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    }
+    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = o;
+  }
+}
+int launch_add(const TensorView& a, const TensorView& b, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(a.C == out.C && b.C == out.C && out.C % 8 == 0 && a.H == out.H && b.H == out.H && a.W == out.W && b.W == out.W,
+                "add: bad views");
+  add_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(a, b, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void broadcast_kernel(TensorView in, TensorView out) {
+  const int nv = out.C / 8;
+  const long total = (long)out.B * out.H * out.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % out.W);
+    p /= out.W;
+    const int y = (int)(p % out.H);
+    const int b = (int)(p / out.H);
+    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, 0, 0)) + v);
+  }
+}
+int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(in.C == out.C && in.H == 1 && in.W == 1 && in.dtype == MYOLO_F16 && out.C % 8 == 0, "broadcast: bad views");
+  broadcast_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Detect.forward (eval): view (bs,na,no,ny,nx) -> permute (bs,na,ny,nx,no); sigmoid; xy=(s*2-0.5+grid)*stride;
+// wh=(s*2)^2*anchor; z = cat over levels                                     [reference models/yolo.py:211-225]
+// ------------------------------------------------------------------------------------------------
+__global__ void detect_decode_kernel(TensorView in, int na, int no, float stride, const float* __restrict__ anchors, float* raw,
+                                     float* z, int z_off, int z_rows) {
+  const long total = (long)in.B * na * in.H * in.W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % in.W);
+    long p = i / in.W;
+    const int y = (int)(p % in.H);
+    p /= in.H;
+    const int a = (int)(p % na);
+    const int b = (int)(p / na);
+    const float* src = vptr_f(in, b, y, x) + a * no;
+    const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
+    float* r = raw ? raw + row * no : nullptr;
+    float* zz = z + ((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no;
+    for (int o = 0; o < no; ++o) {
+      const float v = src[o];
+      if (r) r[o] = v;
+      float sg = 1.0f / (1.0f + expf(-v));
+      if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
+      else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
+      else if (o == 2 || o == 3) {
+        const float t = sg * 2.0f;
+        sg = t * t * anchors[a * 2 + (o - 2)];
+      }
+      zz[o] = sg;
+    }
+  }
+}
+int launch_detect_decode(const TensorView& in, int na, int no, float stride, const float* d_anchors, float* raw, float* z,
+                         int z_row_offset, int z_rows_total, cudaStream_t s) {
+  MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.C >= na * no, "detect_decode: bad view");
+  detect_decode_kernel<<<grid_for((long)in.B * na * in.H * in.W, 128), 128, 0, s>>>(in, na, no, stride, d_anchors, raw, z,
+                                                                                   z_row_offset, z_rows_total);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// final seg upsample: fp32 NHWC low-res logits (ctot-padded) -> NCHW logits and/or fused argmax (first max wins)
+// one thread per output pixel; x fastest so every per-class store is a coalesced 128-byte line per warp.
+// ------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void seg_upsample_kernel(TensorView in, int ncls, int H, int W, TOut* seg, int64_t* amax) {
+  const long total = (long)in.B * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int b = (int)(i / ((long)W * H));
+    const Lerp ly = lerp_axis(y, in.H, H), lx = lerp_axis(x, in.W, W);
+    const float* pa = vptr_f(in, b, ly.i0, lx.i0);
+    const float* pb = vptr_f(in, b, ly.i0, lx.i1);
+    const float* pc = vptr_f(in, b, ly.i1, lx.i0);
+    const float* pd = vptr_f(in, b, ly.i1, lx.i1);
+    float best = 0.f;
+    int bi = 0;
+    for (int c4 = 0; c4 < ncls; c4 += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pa + c4));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(pb + c4));
+      const float4 cq = __ldg(reinterpret_cast<const float4*>(pc + c4));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(pd + c4));
+      const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {bq.x, bq.y, bq.z, bq.w}, vc[4] = {cq.x, cq.y, cq.z, cq.w},
+                  vd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int c = c4 + k;
+        if (c < ncls) {
+          const float val = bilerp(va[k], vb[k], vc[k], vd[k], ly, lx);
+          if (seg) seg[(((size_t)b * ncls + c) * H + y) * W + x] = (TOut)val;
+          if (c == 0 || val > best) { best = val; bi = c; }
+        }
+      }
+    }
+    if (amax) amax[i] = bi;
+  }
+}
+int launch_seg_upsample(const TensorView& in, int n_cls, int H, int W, void* seg, int seg_dtype, int64_t* argmax, cudaStream_t s) {
+  MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.ctot % 4 == 0 && in.ctot >= ((n_cls + 3) / 4) * 4, "seg_upsample: bad view");
+  const int g = grid_for((long)in.B * H * W, 256, 148 * 64);
+  if (seg_dtype == MYOLO_F16) seg_upsample_kernel<__half><<<g, 256, 0, s>>>(in, n_cls, H, W, (__half*)seg, argmax);
+  else seg_upsample_kernel<float><<<g, 256, 0, s>>>(in, n_cls, H, W, (float*)seg, argmax);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone post-process entry points on NCHW logits (detect.py:191-193)
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void seg_argmax_nchw_kernel(const TIn* __restrict__ src, int B, int C, int h, int w, int H, int W, TOut* out) {
+  const long total = (long)B * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int b = (int)(i / ((long)W * H));
+    const Lerp ly = lerp_axis(y, h, H), lx = lerp_axis(x, w, W);
+    float best = 0.f;
+    int bi = 0;
+    for (int c = 0; c < C; ++c) {
+      const TIn* pl = src + ((size_t)b * C + c) * h * w;
+      const float val = bilerp((float)pl[ly.i0 * w + lx.i0], (float)pl[ly.i0 * w + lx.i1], (float)pl[ly.i1 * w + lx.i0],
+                               (float)pl[ly.i1 * w + lx.i1], ly, lx);
+      if (c == 0 || val > best) { best = val; bi = c; }
+    }
+    out[i] = (TOut)bi;
+  }
+}
+
+__global__ void bilinear_nchw_kernel(const float* __restrict__ src, int B, int C, int h, int w, int H, int W, float* dst) {
+  const long total = (long)B * C * H * W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const long bc = i / ((long)W * H);
+    const Lerp ly = lerp_axis(y, h, H), lx = lerp_axis(x, w, W);
+    const float* pl = src + (size_t)bc * h * w;
+    dst[i] = bilerp(pl[ly.i0 * w + lx.i0], pl[ly.i0 * w + lx.i1], pl[ly.i1 * w + lx.i0], pl[ly.i1 * w + lx.i1], ly, lx);
+  }
+}
+
+__global__ void read_view_kernel(TensorView v, float* dst) {
+  const long total = (long)v.B * v.C * v.H * v.W;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % v.W);
+    const int y = (int)((i / v.W) % v.H);
+    const int c = (int)((i / ((long)v.W * v.H)) % v.C);
+    const int b = (int)(i / ((long)v.W * v.H * v.C));
+    dst[i] = v.dtype == MYOLO_F32 ? vptr_f(v, b, y, x)[c] : __half2float(vptr(v, b, y, x)[c]);
+  }
+}
+int launch_read_view(const TensorView& v, float* dst, cudaStream_t s) {
+  read_view_kernel<<<grid_for((long)v.B * v.C * v.H * v.W, 256), 256, 0, s>>>(v, dst);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace myolo
+
+using namespace myolo;
+
+extern "C" int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, int C, int h, int w, int H, int W, void* out,
+                                         int out_dtype, void* stream) {
+  MYOLO_REQUIRE(logits && out && B > 0 && C > 0 && h > 0 && w > 0 && H > 0 && W > 0, "seg_upsample_argmax: bad arguments");
+  MYOLO_REQUIRE((dtype == MYOLO_F32 || dtype == MYOLO_F16) && (out_dtype == MYOLO_I64 || out_dtype == MYOLO_U8),
+                "seg_upsample_argmax: unsupported dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = grid_for((long)B * H * W, 256, 148 * 64);
+  if (dtype == MYOLO_F32) {
+    if (out_dtype == MYOLO_I64) seg_argmax_nchw_kernel<float, int64_t><<<g, 256, 0, s>>>((const float*)logits, B, C, h, w, H, W, (int64_t*)out);
+    else seg_argmax_nchw_kernel<float, uint8_t><<<g, 256, 0, s>>>((const float*)logits, B, C, h, w, H, W, (uint8_t*)out);
+  } else {
+    if (out_dtype == MYOLO_I64) seg_argmax_nchw_kernel<__half, int64_t><<<g, 256, 0, s>>>((const __half*)logits, B, C, h, w, H, W, (int64_t*)out);
+    else seg_argmax_nchw_kernel<__half, uint8_t><<<g, 256, 0, s>>>((const __half*)logits, B, C, h, w, H, W, (uint8_t*)out);
+  }
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int myolo_bilinear_nchw(const float* src, int B, int C, int h, int w, int H, int W, float* dst, void* stream) {
+  MYOLO_REQUIRE(src && dst && B > 0 && C > 0, "bilinear_nchw: bad arguments");
+  bilinear_nchw_kernel<<<grid_for((long)B * C * H * W, 256, 148 * 64), 256, 0, (cudaStream_t)stream>>>(src, B, C, h, w, H, W, dst);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}

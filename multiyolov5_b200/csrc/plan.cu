@@ -1,0 +1,386 @@
+// C ABI + layer-plan executor: what Model.__init__/fuse() and Model.forward_once (reference models/yolo.py:293-316,339-347)
+// become on the device.  The host-side planner (multiyolov5_b200/plan.py) lowers the module tree to a flat op list over
+// liveness-packed NHWC buffers; this file resolves views, owns packed weights / tensor maps and replays the list on a stream.
+#include <stdarg.h>
+
+#include <string>
+#include <vector>
+
+#include "conv.h"
+#include "kernels.h"
+
+namespace myolo {
+
+thread_local char g_err[1024] = "";
+thread_local int64_t g_launch_count = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_device(int* sms) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no CUDA device: %s", cudaGetErrorString(e));
+    return MYOLO_E_NODEVICE;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return MYOLO_E_NODEVICE;
+  }
+  if (prop.major != 10) {
+    set_error("libmyolo_sm100a needs an sm_100 (Blackwell B200) device, found sm_%d%d (%s); there is no fallback path", prop.major,
+              prop.minor, prop.name);
+    return MYOLO_E_NODEVICE;
+  }
+  if (sms) *sms = prop.multiProcessorCount;
+  return 0;
+}
+
+struct WeightSlot {
+  __half* w = nullptr;
+  float* bias = nullptr;
+  int co = 0, ci = 0, k = 0, co_pad = 0, ci_pad = 0;
+  bool set = false;
+};
+
+}  // namespace myolo
+
+using namespace myolo;
+
+struct myolo_plan {
+  int B = 0, H = 0, W = 0, num_sms = 148;
+  std::vector<myolo_op> ops;
+  std::vector<myolo_buf_desc> bufs;
+  std::vector<int32_t> extra;
+  int32_t* d_extra = nullptr;
+  unsigned char* ws = nullptr;
+  int64_t ws_bytes = 0;
+  std::vector<WeightSlot> slots;
+  std::vector<ConvOp> convs;      // parallel to ops (valid for CONV ops)
+  std::vector<int> conv_ready;    // tensor maps built
+  int64_t last_launches = 0;
+  bool force_simt = false;
+  cudaEvent_t* ev = nullptr;
+};
+
+static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
+  MYOLO_REQUIRE(v.buf >= 0 && v.buf < (int)pl->bufs.size(), "view: buffer index %d out of range", v.buf);
+  const myolo_buf_desc& bd = pl->bufs[v.buf];
+  MYOLO_REQUIRE(v.c_off >= 0 && v.c > 0 && v.c_off + v.c <= bd.c, "view: channel slice [%d,+%d) outside buffer %d (c=%d)", v.c_off,
+                v.c, v.buf, bd.c);
+  out->dtype = bd.dtype;
+  const size_t es = bd.dtype == MYOLO_F16 ? 2 : 4;
+  out->base = pl->ws + bd.offset + (size_t)v.c_off * es;
+  out->B = pl->B;
+  out->H = bd.h;
+  out->W = bd.w;
+  out->C = v.c;
+  out->ctot = bd.c;
+  return 0;
+}
+
+extern "C" int myolo_abi_version(void) { return MYOLO_ABI_VERSION; }
+extern "C" const char* myolo_last_error(void) { return g_err; }
+
+extern "C" int myolo_device_info(char* name, int* sm_count, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  MYOLO_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  MYOLO_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (name) {
+    strncpy(name, prop.name, 255);
+    name[255] = 0;
+  }
+  if (sm_count) *sm_count = prop.multiProcessorCount;
+  if (cc_major) *cc_major = prop.major;
+  if (cc_minor) *cc_minor = prop.minor;
+  return 0;
+}
+
+extern "C" int myolo_plan_create(const myolo_op* ops, int n_ops, const myolo_buf_desc* bufs, int n_bufs, const int32_t* extra,
+                                 int n_extra, int B, int H, int W, int64_t workspace_bytes, int n_weight_slots, myolo_plan** out) {
+  MYOLO_REQUIRE(ops && bufs && out && n_ops > 0 && n_bufs > 0 && B > 0 && H > 0 && W > 0, "plan_create: bad arguments");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  myolo_plan* pl = new myolo_plan();
+  pl->B = B;
+  pl->H = H;
+  pl->W = W;
+  pl->num_sms = sms;
+  pl->ops.assign(ops, ops + n_ops);
+  pl->bufs.assign(bufs, bufs + n_bufs);
+  if (n_extra > 0) pl->extra.assign(extra, extra + n_extra);
+  pl->slots.resize(n_weight_slots);
+  pl->convs.resize(n_ops);
+  pl->conv_ready.assign(n_ops, 0);
+  const char* fs = getenv("MYOLO_FORCE_SIMT");
+  pl->force_simt = fs && fs[0] == '1';
+  for (int i = 0; i < n_bufs; ++i) {
+    const myolo_buf_desc& bd = bufs[i];
+    const int64_t bytes = (int64_t)B * bd.h * bd.w * bd.c * (bd.dtype == MYOLO_F16 ? 2 : 4);
+    if (bd.offset < 0 || bd.offset % 256 != 0 || bd.offset + bytes > workspace_bytes) {
+      set_error("plan_create: buffer %d (offset %lld, %lld bytes) outside workspace of %lld bytes", i, (long long)bd.offset,
+                (long long)bytes, (long long)workspace_bytes);
+      delete pl;
+      return MYOLO_E_INVALID;
+    }
+  }
+  cudaError_t e = cudaMalloc(&pl->ws, workspace_bytes);
+  if (e == cudaSuccess) e = cudaMemset(pl->ws, 0, workspace_bytes);
+  if (e == cudaSuccess && n_extra > 0) {
+    e = cudaMalloc(&pl->d_extra, (size_t)n_extra * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(pl->d_extra, extra, (size_t)n_extra * 4, cudaMemcpyHostToDevice);
+  }
+  if (e != cudaSuccess) {
+    set_error("plan_create: device allocation failed: %s", cudaGetErrorString(e));
+    if (pl->ws) cudaFree(pl->ws);
+    if (pl->d_extra) cudaFree(pl->d_extra);
+    delete pl;
+    return MYOLO_E_CUDA;
+  }
+  pl->ws_bytes = workspace_bytes;
+  *out = pl;
+  return 0;
+}
+
+extern "C" void myolo_plan_destroy(myolo_plan* pl) {
+  if (!pl) return;
+  for (auto& s : pl->slots) {
+    if (s.w) cudaFree(s.w);
+    if (s.bias) cudaFree(s.bias);
+  }
+  if (pl->ws) cudaFree(pl->ws);
+  if (pl->d_extra) cudaFree(pl->d_extra);
+  delete pl;
+}
+
+static int conv_n_pad(int co) {
+  // Co_pad must cover n_tiles_n * BN of the tcgen05 kernel (see conv_tc_prepare) and stay a multiple of 16 for the simt kernel
+  const int co16 = (int)align_up(co, 16);
+  if (co16 <= 128) return co16;
+  for (int bn = 128; bn >= 16; bn -= 16)
+    if (co16 % bn == 0) return co16;
+  return co16;
+}
+
+extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float* w, int co, int ci, int k, const float* gamma,
+                                           const float* beta, const float* mean, const float* var, float eps, const float* bias,
+                                           void* stream) {
+  MYOLO_REQUIRE(pl && w && slot >= 0 && slot < (int)pl->slots.size(), "set_conv_weights: bad slot %d", slot);
+  MYOLO_REQUIRE((gamma && beta && mean && var) || (!gamma && !beta && !mean && !var), "set_conv_weights: partial BN parameters");
+  WeightSlot& s = pl->slots[slot];
+  const int co_pad = conv_n_pad(co), ci_pad = (int)align_up(ci, 16);
+  if (!s.w || s.co_pad != co_pad || s.ci_pad != ci_pad || s.k != k) {
+    if (s.w) cudaFree(s.w);
+    if (s.bias) cudaFree(s.bias);
+    s.w = nullptr;
+    s.bias = nullptr;
+    MYOLO_CHECK_CUDA(cudaMalloc(&s.w, (size_t)co_pad * k * k * ci_pad * 2));
+    MYOLO_CHECK_CUDA(cudaMalloc(&s.bias, (size_t)co_pad * 4));
+    for (size_t i = 0; i < pl->ops.size(); ++i)
+      if (pl->ops[i].kind == MYOLO_OP_CONV && pl->ops[i].weight_slot == slot) pl->conv_ready[i] = 0;
+  }
+  s.co = co;
+  s.ci = ci;
+  s.k = k;
+  s.co_pad = co_pad;
+  s.ci_pad = ci_pad;
+  s.set = true;
+  return pack_conv_weights(w, co, ci, k, gamma, beta, mean, var, eps, bias, s.w, s.bias, co_pad, ci_pad, (cudaStream_t)stream);
+}
+
+static int prepare_conv(myolo_plan* pl, int i) {
+  const myolo_op& op = pl->ops[i];
+  MYOLO_REQUIRE(op.weight_slot >= 0 && op.weight_slot < (int)pl->slots.size(), "op %d: bad weight slot", i);
+  const WeightSlot& s = pl->slots[op.weight_slot];
+  if (!s.set) {
+    set_error("op %d: weights of slot %d were never set (call myolo_plan_set_conv_weights first)", i, op.weight_slot);
+    return MYOLO_E_STATE;
+  }
+  ConvOp& c = pl->convs[i];
+  c = ConvOp();
+  int rc;
+  if ((rc = resolve_view(pl, op.in, &c.in))) return rc;
+  if ((rc = resolve_view(pl, op.out, &c.out))) return rc;
+  c.has_res = op.in2.buf >= 0;
+  if (c.has_res && (rc = resolve_view(pl, op.in2, &c.res))) return rc;
+  c.k = op.k;
+  c.stride = op.stride;
+  c.dil = op.dil;
+  c.act = op.act;
+  c.w = s.w;
+  c.bias = s.bias;
+  c.Ci_pad = s.ci_pad;
+  c.Co_pad = s.co_pad;
+  c.Co = s.co;
+  MYOLO_REQUIRE(s.k == op.k, "op %d: kernel size %d != packed weights %d", i, op.k, s.k);
+  MYOLO_REQUIRE(c.in.C == s.ci_pad, "op %d: input view has %d channels, packed weights expect %d", i, c.in.C, s.ci_pad);
+  MYOLO_REQUIRE(c.out.dtype == MYOLO_F32 || c.out.C == s.co, "op %d: output view has %d channels, weights produce %d", i, c.out.C, s.co);
+  const int pad = op.dil * (op.k / 2);
+  const int ho = (c.in.H + 2 * pad - op.dil * (op.k - 1) - 1) / op.stride + 1;
+  const int wo = (c.in.W + 2 * pad - op.dil * (op.k - 1) - 1) / op.stride + 1;
+  MYOLO_REQUIRE(ho == c.out.H && wo == c.out.W, "op %d: conv output %dx%d does not match buffer %dx%d", i, ho, wo, c.out.H, c.out.W);
+  c.use_tc = !pl->force_simt && !(op.flags & MYOLO_CONV_FORCE_SIMT) && conv_tc_eligible(c);
+  if (c.use_tc && (rc = conv_tc_prepare(c, pl->num_sms))) return rc;
+  pl->conv_ready[i] = 1;
+  return 0;
+}
+
+static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
+                  int64_t* seg_argmax, cudaStream_t s) {
+  const myolo_op& op = pl->ops[i];
+  TensorView in, in2, out;
+  int rc;
+  switch (op.kind) {
+    case MYOLO_OP_INPUT_FOCUS:
+      if ((rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_input_focus(x, x_dtype, pl->B, pl->H, pl->W, out, s);
+    case MYOLO_OP_CONV:
+      if (!pl->conv_ready[i] && (rc = prepare_conv(pl, i))) return rc;
+      return pl->convs[i].use_tc ? conv_tc_launch(pl->convs[i], s) : conv_simt_launch(pl->convs[i], s);
+    case MYOLO_OP_UPSAMPLE_NEAREST:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_upsample_nearest2x(in, out, s);
+    case MYOLO_OP_SPP_POOL:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      MYOLO_REQUIRE(op.aux[0] == 3 && op.aux[1] == 5, "spp_pool: only the (5,9,13) pyramid is supported");
+      return launch_spp_pool(in, out, op.aux[0], s);
+    case MYOLO_OP_BILINEAR:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_bilinear_nhwc(in, out, s);
+    case MYOLO_OP_REGION_SUM:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_region_sum(in, pl->d_extra + op.aux[0], op.aux[1], pl->d_extra + op.aux[2], op.aux[3], out, s);
+    case MYOLO_OP_REGION_COMBINE:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_region_combine(in, op.aux[2], pl->d_extra + op.aux[0], op.aux[1], out, s);
+    case MYOLO_OP_CHANNEL_SCALE:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.in2, &in2))) return rc;
+      return launch_channel_scale(in, in2, s);
+    case MYOLO_OP_ADD:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.in2, &in2)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_add(in, in2, out, s);
+    case MYOLO_OP_BROADCAST:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_broadcast(in, out, s);
+    case MYOLO_OP_DETECT_DECODE: {
+      if ((rc = resolve_view(pl, op.in, &in))) return rc;
+      const int level = op.aux[0];
+      MYOLO_REQUIRE(z != nullptr, "detect_decode: z output pointer is null");
+      return launch_detect_decode(in, op.aux[1], op.aux[2], op.faux[0], reinterpret_cast<const float*>(pl->d_extra + op.aux[5]),
+                                  raw ? raw[level] : nullptr, z, op.aux[3], op.aux[4], s);
+    }
+    case MYOLO_OP_SEG_UPSAMPLE:
+      if ((rc = resolve_view(pl, op.in, &in))) return rc;
+      if (!seg && !seg_argmax) return 0;
+      return launch_seg_upsample(in, op.aux[0], pl->H, pl->W, seg, seg_dtype, seg_argmax, s);
+    default:
+      set_error("op %d: unknown kind %d", i, op.kind);
+      return MYOLO_E_INVALID;
+  }
+}
+
+extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
+                                  int64_t* seg_argmax, void* stream) {
+  MYOLO_REQUIRE(pl && x, "plan_forward: null plan / input");
+  const int64_t l0 = g_launch_count;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  pl->last_launches = g_launch_count - l0;
+  return 0;
+}
+
+extern "C" int myolo_plan_profile(myolo_plan* pl, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
+                                  int64_t* seg_argmax, float* host_ms_per_op, void* stream) {
+  MYOLO_REQUIRE(pl && x && host_ms_per_op, "plan_profile: null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = pl->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) MYOLO_CHECK_CUDA(cudaEventCreate(&e));
+  MYOLO_CHECK_CUDA(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
+    if (rc) return rc;
+    MYOLO_CHECK_CUDA(cudaEventRecord(ev[i + 1], s));
+  }
+  MYOLO_CHECK_CUDA(cudaEventSynchronize(ev[n]));
+  for (size_t i = 0; i < n; ++i) MYOLO_CHECK_CUDA(cudaEventElapsedTime(&host_ms_per_op[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  return 0;
+}
+
+extern "C" int64_t myolo_plan_last_launch_count(const myolo_plan* pl) { return pl ? pl->last_launches : 0; }
+
+extern "C" int myolo_plan_read_view(myolo_plan* pl, myolo_view view, float* dst, void* stream) {
+  MYOLO_REQUIRE(pl && dst, "read_view: null argument");
+  TensorView v;
+  int rc = resolve_view(pl, view, &v);
+  if (rc) return rc;
+  return launch_read_view(v, dst, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// standalone fused conv (per-op parity tests, ncu captures)
+// ------------------------------------------------------------------------------------------------
+extern "C" int myolo_conv_bn_silu(const void* x, int B, int H, int W, int ci, const float* w, int co, int k, int stride, int dil,
+                                  const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                                  const float* bias, int act, const void* residual, void* y, int path, void* stream) {
+  MYOLO_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0 && ci > 0 && co > 0, "conv_bn_silu: bad arguments");
+  MYOLO_REQUIRE(ci % 16 == 0 && co % 8 == 0, "conv_bn_silu: standalone entry needs ci %% 16 == 0 and co %% 8 == 0");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int co_pad = conv_n_pad(co), ci_pad = ci;
+  __half* wp = nullptr;
+  float* bp = nullptr;
+  MYOLO_CHECK_CUDA(cudaMalloc(&wp, (size_t)co_pad * k * k * ci_pad * 2));
+  MYOLO_CHECK_CUDA(cudaMalloc(&bp, (size_t)co_pad * 4));
+  rc = pack_conv_weights(w, co, ci, k, gamma, beta, mean, var, eps, bias, wp, bp, co_pad, ci_pad, s);
+  ConvOp c;
+  const int pad = dil * (k / 2);
+  const int ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  c.in = TensorView{const_cast<void*>(x), B, H, W, ci, ci, MYOLO_F16};
+  c.out = TensorView{y, B, ho, wo, co, co, MYOLO_F16};
+  c.has_res = residual != nullptr;
+  if (c.has_res) c.res = TensorView{const_cast<void*>(residual), B, ho, wo, co, co, MYOLO_F16};
+  c.k = k;
+  c.stride = stride;
+  c.dil = dil;
+  c.act = act;
+  c.w = wp;
+  c.bias = bp;
+  c.Ci_pad = ci_pad;
+  c.Co_pad = co_pad;
+  c.Co = co;
+  if (!rc) {
+    const bool elig = conv_tc_eligible(c);
+    if (path == 1 && !elig) {
+      set_error("conv_bn_silu: shape not eligible for the tcgen05 path");
+      rc = MYOLO_E_INVALID;
+    } else if (path == 2 || (path == 0 && !elig)) {
+      rc = conv_simt_launch(c, s);
+    } else {
+      rc = conv_tc_prepare(c, sms);
+      if (!rc) rc = conv_tc_launch(c, s);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(s);
+  cudaFree(wp);
+  cudaFree(bp);
+  if (!rc && e != cudaSuccess) {
+    set_error("conv_bn_silu: kernel failed: %s", cudaGetErrorString(e));
+    rc = MYOLO_E_CUDA;
+  }
+  return rc;
+}

@@ -1,0 +1,124 @@
+"""Runtime glue between the nn.Module shells and libmyolo_sm100a.so: compiles one plan per input shape, uploads
+(BN-folded, fp16-packed) weights, allocates caller-owned output tensors and launches the plan on the current stream."""
+import ctypes as C
+from typing import Dict, Tuple
+
+import torch
+
+from . import _lib
+from .plan import build_plan, to_ctypes
+
+
+class CompiledPlan:
+    def __init__(self, model, B, H, W):
+        self.pb = build_plan(model, B, H, W)
+        self.ops, self.bufs, self.extra = to_ctypes(self.pb)
+        L = _lib.lib()
+        h = C.c_void_p()
+        _lib.check(L.myolo_plan_create(self.ops, len(self.pb.ops), self.bufs, len(self.pb.bufs), self.extra, len(self.pb.extra),
+                                       B, H, W, int(self.pb.workspace_bytes), len(self.pb.slots), C.byref(h)))
+        self.handle = h
+        self.B, self.H, self.W = B, H, W
+        self.weights_uploaded = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _lib.lib().myolo_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def upload_weights(self):
+        L = _lib.lib()
+        sp = _lib.stream_ptr()
+        keep = []
+
+        def f32(t):
+            if t is None:
+                return None
+            t = t.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            assert t.is_cuda, "model parameters must live on the CUDA device (model.cuda())"
+            keep.append(t)
+            return t
+
+        for i, s in enumerate(self.pb.slots):
+            w = f32(s.conv.weight)
+            bias = f32(s.conv.bias)
+            if s.bn is not None:
+                g, b, m, v = f32(s.bn.weight), f32(s.bn.bias), f32(s.bn.running_mean), f32(s.bn.running_var)
+                eps = float(s.bn.eps)
+            else:
+                g = b = m = v = None
+                eps = 0.0
+            co, ci, k = w.shape[0], w.shape[1], w.shape[2]
+            _lib.check(L.myolo_plan_set_conv_weights(self.handle, i, _lib.ptr(w), co, ci, k, _lib.ptr(g), _lib.ptr(b), _lib.ptr(m),
+                                                     _lib.ptr(v), eps, _lib.ptr(bias), sp))
+        self.weights_uploaded = True
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.plans: Dict[Tuple[int, int, int], CompiledPlan] = {}
+        self.weights_dirty = True
+        self.last_plan = None
+
+    def plan_for(self, B, H, W) -> CompiledPlan:
+        key = (B, H, W)
+        if key not in self.plans:
+            self.plans[key] = CompiledPlan(self.model, B, H, W)
+        p = self.plans[key]
+        if self.weights_dirty:
+            for q in self.plans.values():
+                q.weights_uploaded = False
+            self.weights_dirty = False
+        if not p.weights_uploaded:
+            p.upload_weights()
+        self.last_plan = p
+        return p
+
+    def forward(self, x: torch.Tensor, seg_argmax=False, want_seg=True, want_raw=True, profile=False):
+        if not x.is_cuda:
+            raise _lib.MyoloError("Model.forward needs a CUDA tensor: multiyolov5_b200 has no CPU path (use the oracle for CPU numbers)")
+        assert x.dim() == 4 and x.shape[1] == 3, "expected (B,3,H,W)"
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        p = self.plan_for(B, H, W)
+        det = self.model.model[-1]
+        seg_head = self.model.model[-2]
+        rows = p.pb.det_rows
+        dev = x.device
+        z = torch.empty((B, sum(rows), det.no), dtype=torch.float32, device=dev)
+        raws = []
+        for i, v in enumerate([o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]):
+            raws.append(torch.empty((B, det.na, v.h, v.w, det.no), dtype=torch.float32, device=dev) if want_raw else None)
+        seg_dt = torch.float16 if x.dtype == torch.float16 else torch.float32
+        seg = torch.empty((B, seg_head.c_out, H, W), dtype=seg_dt, device=dev) if (want_seg and not seg_argmax) else None
+        amax = torch.empty((B, H, W), dtype=torch.int64, device=dev) if seg_argmax else None
+        raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])
+        L = _lib.lib()
+        args = (p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), _lib.ptr(z), raw_ptrs if want_raw else None, _lib.ptr(seg),
+                _lib.torch_dtype_code(seg_dt), _lib.ptr(amax))
+        if profile:
+            ms = (C.c_float * len(p.pb.ops))()
+            _lib.check(L.myolo_plan_profile(*args, ms, _lib.stream_ptr()))
+            self.last_profile = list(ms)
+        else:
+            _lib.check(L.myolo_plan_forward(*args, _lib.stream_ptr()))
+        out = [(z, raws), seg]
+        if seg_argmax:
+            out.append(amax)
+        return out
+
+    def launches(self):
+        return int(_lib.lib().myolo_plan_last_launch_count(self.last_plan.handle)) if self.last_plan else 0
+
+    def read_view(self, v, plan=None):
+        """debug: NHWC slice -> (B,C,H,W) fp32 torch tensor"""
+        p = plan or self.last_plan
+        out = torch.empty((p.B, v.c, v.h, v.w), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().myolo_plan_read_view(p.handle, _lib.View(v.buf.id, v.c_off, v.c), _lib.ptr(out), _lib.stream_ptr()))
+        return out

@@ -1,0 +1,493 @@
+"""Host-side planner: lowers the module tree built by models.yolo.parse_model to the flat op list that
+libmyolo_sm100a.so replays (include/myolo.h `myolo_op`), i.e. the compiled form of Model.forward_once
+(reference models/yolo.py:293-316).
+
+Design points
+  * activations are NHWC fp16; every tensor is a *view* (buffer, channel offset, channels).  torch.cat never runs:
+    producers write straight into channel slices of the consumer's concat buffer (C3, SPP, yaml Concat layers, PSP / RFB2 /
+    PyramidPooling / FFM concatenations).
+  * buffers are liveness-packed into one workspace (first-fit over [first-def, last-use] intervals).
+  * aux[] conventions per op kind are documented next to each emit_* helper.
+"""
+import math
+import struct
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch.nn as nn
+
+from . import _lib
+from ._lib import (ACT_NONE, ACT_SIGMOID, ACT_SILU, F16, F32, OP_ADD, OP_BILINEAR, OP_BROADCAST, OP_CHANNEL_SCALE, OP_CONV,
+                   OP_DETECT_DECODE, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
+                   OP_UPSAMPLE_NEAREST)
+from .models import common as cm
+
+
+@dataclass
+class Buf:
+    id: int
+    h: int
+    w: int
+    c: int
+    dtype: int = F16
+    first: int = -1
+    last: int = -1
+    offset: int = 0
+
+    def nbytes(self, B):
+        return B * self.h * self.w * self.c * (2 if self.dtype == F16 else 4)
+
+
+@dataclass
+class V:
+    """channel slice of a buffer"""
+    buf: Buf
+    c_off: int
+    c: int
+
+    @property
+    def h(self):
+        return self.buf.h
+
+    @property
+    def w(self):
+        return self.buf.w
+
+    def sub(self, off, c):
+        assert off + c <= self.c
+        return V(self.buf, self.c_off + off, c)
+
+
+@dataclass
+class WeightSlot:
+    conv: nn.Conv2d
+    bn: Optional[nn.BatchNorm2d]
+    name: str = ""
+
+
+@dataclass
+class OpRec:
+    kind: int
+    in_: Optional[V] = None
+    in2: Optional[V] = None
+    out: Optional[V] = None
+    k: int = 1
+    stride: int = 1
+    dil: int = 1
+    act: int = ACT_NONE
+    flags: int = 0
+    slot: int = -1
+    aux: List[int] = field(default_factory=lambda: [0] * 8)
+    faux: List[float] = field(default_factory=lambda: [0.0] * 4)
+    tag: str = ""
+
+
+def adaptive_bins(n_in: int, k: int):
+    """AdaptiveAvgPool2d bin edges: start=floor(i*n/k), end=ceil((i+1)*n/k)  (ATen adaptive pooling index math)."""
+    return [(math.floor(i * n_in / k), math.ceil((i + 1) * n_in / k)) for i in range(k)]
+
+
+class PlanBuilder:
+    def __init__(self, B: int, H: int, W: int):
+        self.B, self.H, self.W = B, H, W
+        self.bufs: List[Buf] = []
+        self.ops: List[OpRec] = []
+        self.slots: List[WeightSlot] = []
+        self.extra: List[int] = []
+        self.tag = ""
+
+    # ---- bookkeeping ----
+    def new_buf(self, h, w, c, dtype=F16) -> V:
+        b = Buf(len(self.bufs), h, w, c, dtype)
+        self.bufs.append(b)
+        return V(b, 0, c)
+
+    def _touch(self, v: Optional[V], idx: int):
+        if v is None:
+            return
+        if v.buf.first < 0:
+            v.buf.first = idx
+        v.buf.last = idx
+
+    def emit(self, rec: OpRec):
+        idx = len(self.ops)
+        rec.tag = rec.tag or self.tag
+        for v in (rec.in_, rec.in2, rec.out):
+            self._touch(v, idx)
+        self.ops.append(rec)
+        return rec
+
+    def add_extra(self, ints: Sequence[int]) -> int:
+        off = len(self.extra)
+        self.extra.extend(int(x) for x in ints)
+        return off
+
+    def add_extra_floats(self, fl: Sequence[float]) -> int:
+        return self.add_extra(struct.unpack(f"{len(fl)}i", struct.pack(f"{len(fl)}f", *fl)))
+
+    # ---- primitive emitters ----
+    def conv(self, x: V, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d], act: int, dst: Optional[V] = None,
+             residual: Optional[V] = None, out_dtype=F16, name="") -> V:
+        """OP_CONV. in2 = residual.  Geometry from the nn.Conv2d (square kernels, symmetric stride/dilation only)."""
+        k, s, d = conv.kernel_size[0], conv.stride[0], conv.dilation[0]
+        assert conv.kernel_size[0] == conv.kernel_size[1] and conv.groups == 1
+        assert conv.padding[0] == d * (k // 2), "only 'same'-style padding is on the path"
+        ho = (x.h + 2 * d * (k // 2) - d * (k - 1) - 1) // s + 1
+        wo = (x.w + 2 * d * (k // 2) - d * (k - 1) - 1) // s + 1
+        co = conv.out_channels
+        if dst is None:
+            if out_dtype == F32:   # fp32 NHWC head outputs are padded to a multiple of 16 channels (full-row stores)
+                dst = self.new_buf(ho, wo, (co + 15) // 16 * 16, F32)
+            else:
+                dst = self.new_buf(ho, wo, co, F16)
+        assert dst.h == ho and dst.w == wo, (dst.h, dst.w, ho, wo)
+        assert x.c == (conv.in_channels + 15) // 16 * 16, f"{name}: input view {x.c}ch vs conv {conv.in_channels}ch"
+        slot = len(self.slots)
+        self.slots.append(WeightSlot(conv, bn, name))
+        self.emit(OpRec(OP_CONV, x, residual, dst, k, s, d, act, 0, slot))
+        return dst
+
+    def Conv(self, m: cm.Conv, x: V, dst=None, residual=None) -> V:
+        act = ACT_SILU if isinstance(m.act, nn.SiLU) else ACT_NONE
+        assert isinstance(m.act, (nn.SiLU, nn.Identity)), "only SiLU / identity activations are on the path"
+        return self.conv(x, m.conv, m.bn, act, dst, residual)
+
+    def dilated(self, seq: nn.Sequential, x: V, dst=None) -> V:
+        return self.conv(x, seq[0], seq[1], ACT_SILU, dst)
+
+    def bilinear(self, x: V, h, w, dst: Optional[V] = None) -> V:
+        dst = dst or self.new_buf(h, w, x.c)
+        assert dst.h == h and dst.w == w and dst.c == x.c
+        self.emit(OpRec(OP_BILINEAR, x, None, dst))
+        return dst
+
+    def nearest2x(self, x: V, dst: Optional[V] = None) -> V:
+        dst = dst or self.new_buf(2 * x.h, 2 * x.w, x.c)
+        self.emit(OpRec(OP_UPSAMPLE_NEAREST, x, None, dst))
+        return dst
+
+    def pool_pyramid(self, x: V, ks: Sequence[int], out_dtype=F16) -> List[V]:
+        """AdaptiveAvgPool2d(k) for each k via one atom pass + one combine per level.
+        REGION_SUM aux = [ybounds_off, ny, xbounds_off, nx];  REGION_COMBINE aux = [bins_off, nbins, atoms_nx]."""
+        ys = sorted({e for k in ks for be in adaptive_bins(x.h, k) for e in be})
+        xs = sorted({e for k in ks for be in adaptive_bins(x.w, k) for e in be})
+        if len(ys) == 2 and x.h >= 16:      # a single huge bin (global pool): split into strips for parallelism
+            ys = sorted(set(list(range(0, x.h, max(1, x.h // 16))) + [x.h]))
+        ny, nx = len(ys) - 1, len(xs) - 1
+        atoms = self.new_buf(ny, nx, x.c, F32)
+        rec = OpRec(OP_REGION_SUM, x, None, atoms)
+        rec.aux[0], rec.aux[1], rec.aux[2], rec.aux[3] = self.add_extra(ys), ny, self.add_extra(xs), nx
+        self.emit(rec)
+        outs = []
+        for k in ks:
+            by, bx = adaptive_bins(x.h, k), adaptive_bins(x.w, k)
+            table = []
+            for (y0, y1) in by:
+                for (x0, x1) in bx:
+                    table += [ys.index(y0), ys.index(y1), xs.index(x0), xs.index(x1), (y1 - y0) * (x1 - x0)]
+            o = self.new_buf(k, k, x.c, out_dtype)
+            rec = OpRec(OP_REGION_COMBINE, atoms, None, o)
+            rec.aux[0], rec.aux[1], rec.aux[2] = self.add_extra(table), k * k, nx
+            self.emit(rec)
+            outs.append(o)
+        return outs
+
+    # ---- reference blocks ----
+    def Bottleneck(self, m: cm.Bottleneck, x: V, dst=None) -> V:
+        h = self.Conv(m.cv1, x)
+        return self.Conv(m.cv2, h, dst, residual=x if m.add else None)
+
+    def C3(self, m: cm.C3, x: V, dst=None) -> V:
+        c_ = m.cv1.conv.out_channels
+        cat = self.new_buf(x.h, x.w, 2 * c_)
+        n = len(m.m)
+        y = self.Conv(m.cv1, x, cat.sub(0, c_) if n == 0 else None)
+        for i, bt in enumerate(m.m):
+            y = self.Bottleneck(bt, y, cat.sub(0, c_) if i == n - 1 else None)
+        self.Conv(m.cv2, x, cat.sub(c_, c_))
+        return self.Conv(m.cv3, cat, dst)
+
+    def SPP(self, m: cm.SPP, x: V, dst=None) -> V:
+        assert tuple(m.k) == (5, 9, 13), "SPP kernel pyramid other than (5,9,13) is not on the path"
+        c_ = m.cv1.conv.out_channels
+        cat = self.new_buf(x.h, x.w, 4 * c_)
+        self.Conv(m.cv1, x, cat.sub(0, c_))
+        rec = OpRec(OP_SPP_POOL, cat.sub(0, c_), None, cat.sub(c_, c_))   # aux = [n_cascade, kernel]; writes 3 slices
+        rec.aux[0], rec.aux[1] = 3, 5
+        rec.out = cat.sub(c_, 3 * c_)
+        self.emit(rec)
+        return self.Conv(m.cv2, cat, dst)
+
+    def C3SPP(self, m: cm.C3SPP, x: V, dst=None) -> V:
+        c_ = m.cv1.conv.out_channels
+        c_spp = m.m.cv2.conv.out_channels
+        cat = self.new_buf(x.h, x.w, c_spp + c_)
+        self.SPP(m.m, self.Conv(m.cv1, x), cat.sub(0, c_spp))
+        self.Conv(m.cv2, x, cat.sub(c_spp, c_))
+        return self.Conv(m.cv3, cat, dst)
+
+    def Focus(self, m: cm.Focus, dst=None) -> V:
+        assert m.conv.conv.in_channels == 12
+        s2d = self.new_buf(self.H // 2, self.W // 2, 16)
+        self.emit(OpRec(OP_INPUT_FOCUS, None, None, s2d))
+        return self.Conv(m.conv, s2d, dst)
+
+    def RFB2(self, m: cm.RFB2, x: V, dst=None) -> V:
+        ip = m.branch3[0].conv.out_channels
+        nb = 5 if m.has_globel else 4
+        cat = self.new_buf(x.h, x.w, nb * ip)
+        self.Conv(m.branch3[0], x, cat.sub(3 * ip, ip))
+        x0 = self.Conv(m.branch0[1], self.Conv(m.branch0[0], x), cat.sub(0, ip))
+        x1 = self.dilated(m.branch1, x0, cat.sub(ip, ip))
+        x2 = self.dilated(m.branch2, x1, cat.sub(2 * ip, ip))
+        if m.has_globel:
+            g = self.pool_pyramid(x2, [1])[0]
+            g = self.Conv(m.branch4[1], g)
+            self.emit(OpRec(OP_BROADCAST, g, None, cat.sub(4 * ip, ip)))
+        return self.Conv(m.ConvLinear, cat, dst)
+
+    def ASPP(self, m: cm.ASPP, x: V, dst=None) -> V:
+        assert not m.has_globel, "ASPP(has_globel=True) is not used by the shipped heads"
+        hid = m.hid
+        cat = self.new_buf(x.h, x.w, 4 * hid)
+        self.Conv(m.branch0[0], x, cat.sub(0, hid))
+        for i, br in enumerate((m.branch1, m.branch2, m.branch3)):
+            self.dilated(br, x, cat.sub((i + 1) * hid, hid))
+        return self.Conv(m.ConvLinear, cat, dst)
+
+    def PyramidPooling(self, m: cm.PyramidPooling, x_in_cat: V, cat: V) -> V:
+        """x_in_cat is slice 0 of `cat` (2C channels); fills slices 1..4 and returns cat."""
+        C = x_in_cat.c
+        pooled = self.pool_pyramid(x_in_cat, m.k)
+        for i, (p, conv) in enumerate(zip(pooled, (m.conv1, m.conv2, m.conv3, m.conv4))):
+            f = self.Conv(conv, p)
+            self.bilinear(f, x_in_cat.h, x_in_cat.w, cat.sub(C + i * (C // 4), C // 4))
+        return cat
+
+    def FFM(self, m: cm.FFM, x: V, dst=None) -> V:
+        feat = self.Conv(m.convblk, x, dst)
+        gap = self.pool_pyramid(feat, [1], out_dtype=F32)[0]
+        a = self.conv(gap, m.channel_attention[1], None, ACT_SILU, out_dtype=F32, name="ffm.att1")
+        a = self.conv(a, m.channel_attention[3], None, ACT_SIGMOID, out_dtype=F32, name="ffm.att2")
+        self.emit(OpRec(OP_CHANNEL_SCALE, feat, a.sub(0, feat.c), None))
+        return feat
+
+    def classifier(self, conv: nn.Conv2d, x: V, n_cls: int):
+        lo = self.conv(x, conv, None, ACT_NONE, out_dtype=F32, name="seg.classifier")
+        rec = OpRec(OP_SEG_UPSAMPLE, lo, None, None)   # aux = [n_cls]
+        rec.aux[0] = n_cls
+        self.emit(rec)
+        return lo
+
+    # ---- seg heads ----
+    def SegMaskPSP(self, m, xs: List[V]):
+        ch = m.c_hid
+        h, w = xs[0].h, xs[0].w
+        cat3 = self.new_buf(h, w, 3 * ch)
+        self.Conv(m.m8[0], xs[0], cat3.sub(0, ch))
+        self.bilinear(self.Conv(m.m16[0], xs[1]), h, w, cat3.sub(ch, ch))
+        self.bilinear(self.Conv(m.m32[0], xs[2]), h, w, cat3.sub(2 * ch, ch))
+        ppm_cat = self.new_buf(h, w, 2 * ch)
+        y = self.RFB2(m.out[0], cat3, ppm_cat.sub(0, ch))
+        self.PyramidPooling(m.out[1], y, ppm_cat)
+        y = self.FFM(m.out[2], ppm_cat)
+        return self.classifier(m.out[3], y, m.c_out)
+
+    def SegMaskLab(self, m, xs: List[V]):
+        h, w = xs[0].h, xs[0].w
+        cat = self.new_buf(h, w, 48 + 256)
+        e = self.ASPP(m.encoder[1], self.Conv(m.encoder[0], xs[1]))
+        self.Conv(m.detail[1], self.Conv(m.detail[0], xs[0]), cat.sub(0, 48))
+        self.bilinear(e, h, w, cat.sub(48, 256))
+        y = self.FFM(m.decoder[0], cat)
+        y = self.Conv(m.decoder[1], y)
+        return self.classifier(m.decoder[2], y, m.c_out)
+
+    def SegMaskBiSe(self, m, xs: List[V]):
+        h, w = xs[0].h, xs[0].w
+        f3 = self.RFB2(m.m32[0], xs[2])
+        f3 = self.bilinear(self.Conv(m.up32[0], f3), xs[1].h, xs[1].w)
+        f2 = self.RFB2(m.m16[0], xs[1])
+        s = self.new_buf(f2.h, f2.w, f2.c)
+        self.emit(OpRec(OP_ADD, f2, f3, s))
+        cat = self.new_buf(h, w, 256)
+        self.Conv(m.m8[0], xs[0], cat.sub(0, 128))
+        self.bilinear(self.Conv(m.up16[0], s), h, w, cat.sub(128, 128))
+        y = self.FFM(m.out[0], cat)
+        return self.classifier(m.out[2], y, m.c_out)
+
+    def SegMaskBase(self, m, xs: List[V]):
+        y = self.C3(m.m[0], xs[0])
+        y = self.C3SPP(m.m[1], y)
+        return self.classifier(m.m[3], y, m.c_out)
+
+    # ---- Detect ----
+    def Detect(self, m, xs: List[V]):
+        """DETECT_DECODE aux = [level, na, no, z_row_offset, z_rows_total, anchors_off(extra, 2*na float bits)]; faux[0]=stride."""
+        rows = [m.na * v.h * v.w for v in xs]
+        total, off = sum(rows), 0
+        for i, v in enumerate(xs):
+            raw = self.conv(v, m.m[i], None, ACT_NONE, out_dtype=F32, name=f"detect.m.{i}")
+            rec = OpRec(OP_DETECT_DECODE, raw, None, None)
+            anchors_px = [float(a) for a in m.anchor_grid[i].view(-1).tolist()]
+            rec.aux[0:6] = [i, m.na, m.no, off, total, self.add_extra_floats(anchors_px)]
+            rec.faux[0] = float(m.stride[i])
+            self.emit(rec)
+            off += rows[i]
+        return rows
+
+
+# ------------------------------------------------------------------------------------------------
+def _layer_meta(model):
+    """static (channels, stride) per yaml layer, without running anything."""
+    from .models import yolo as Y
+    ch, st = [], []
+    for m in model.model:
+        f = m.f
+        src = (len(ch) - 1 if f == -1 else f) if isinstance(f, int) else [len(ch) - 1 if j == -1 else j for j in f]
+        mod = m
+        if type(m) is nn.Sequential:
+            raise NotImplementedError("depth-repeated nn.Sequential layers are not on the shipped *_city_seg path")
+        if isinstance(mod, cm.Focus):
+            c, s = mod.conv.conv.out_channels, 2
+        elif isinstance(mod, cm.Conv):
+            c, s = mod.conv.out_channels, st[src] * mod.conv.stride[0]
+        elif isinstance(mod, cm.C3):
+            c, s = mod.cv3.conv.out_channels, st[src]
+        elif isinstance(mod, cm.SPP):
+            c, s = mod.cv2.conv.out_channels, st[src]
+        elif isinstance(mod, nn.Upsample):
+            c, s = ch[src], st[src] / 2
+        elif isinstance(mod, cm.Concat):
+            c, s = sum(ch[j] for j in src), st[src[0]]
+        else:  # seg head / Detect
+            c, s = 0, 0
+        ch.append(c)
+        st.append(s)
+    return ch, st
+
+
+def infer_strides(model):
+    return _layer_meta(model)[1]
+
+
+def build_plan(model, B: int, H: int, W: int) -> PlanBuilder:
+    """Lowers model.model (yaml layers) for a fixed input shape."""
+    from .models import yolo as Y
+    assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of the max stride 32 (reference check_img_size)"
+    pb = PlanBuilder(B, H, W)
+    ch, st = _layer_meta(model)
+    layers = list(model.model)
+    n = len(layers)
+    absf = lambda i, f: (i - 1 if f == -1 else f)  # noqa: E731
+    # where does each layer's output go?  (first Concat that consumes it gets it written in place)
+    cat_of: Dict[int, tuple] = {}
+    cat_buf: Dict[int, V] = {}
+    for j, m in enumerate(layers):
+        if isinstance(m, cm.Concat):
+            off = 0
+            for f in m.f:
+                src = absf(j, f)
+                if src in cat_of:
+                    raise NotImplementedError(f"layer {src} feeds two Concat layers; a copy op would be needed")
+                cat_of[src] = (j, off)
+                off += ch[src]
+
+    def dst_for(i):
+        if i not in cat_of:
+            return None
+        j, off = cat_of[i]
+        if j not in cat_buf:
+            s = int(st[j])
+            cat_buf[j] = pb.new_buf(H // s, W // s, ch[j])
+        return cat_buf[j].sub(off, ch[i])
+
+    outs: List[Optional[V]] = [None] * n
+    for i, m in enumerate(layers):
+        pb.tag = f"L{i}:{type(m).__name__}"
+        f = m.f
+        x = None
+        if isinstance(f, int):
+            x = outs[absf(i, f)] if i > 0 else None
+        else:
+            x = [outs[absf(i, j)] for j in f]
+        dst = dst_for(i)
+        if isinstance(m, cm.Focus):
+            y = pb.Focus(m, dst)
+        elif isinstance(m, cm.Conv):
+            y = pb.Conv(m, x, dst)
+        elif isinstance(m, cm.C3):
+            y = pb.C3(m, x, dst)
+        elif isinstance(m, cm.SPP):
+            y = pb.SPP(m, x, dst)
+        elif isinstance(m, nn.Upsample):
+            assert m.mode == "nearest" and float(m.scale_factor) == 2.0
+            y = pb.nearest2x(x, dst)
+        elif isinstance(m, cm.Concat):
+            y = cat_buf[i]
+            for v in x:
+                assert v.buf is y.buf, "concat input was not produced in place"
+        elif isinstance(m, Y.SegMaskPSP):
+            y = pb.SegMaskPSP(m, x)
+        elif isinstance(m, Y.SegMaskLab):
+            y = pb.SegMaskLab(m, x)
+        elif isinstance(m, Y.SegMaskBiSe):
+            y = pb.SegMaskBiSe(m, x)
+        elif isinstance(m, Y.SegMaskBase):
+            y = pb.SegMaskBase(m, x)
+        elif isinstance(m, Y.Detect):
+            pb.det_rows = pb.Detect(m, x)
+            y = None
+        else:
+            raise NotImplementedError(f"layer {i}: {type(m).__name__} (a depth-repeated nn.Sequential of Conv is not on the shipped path)")
+        outs[i] = y
+        # keep saved layers alive until their last consumer: extend liveness at consumption time (done by emit/_touch)
+    pb.layer_views = outs
+    assign_offsets(pb)
+    return pb
+
+
+def assign_offsets(pb: PlanBuilder, align: int = 256):
+    """first-fit packing of [first,last] live intervals (ops run sequentially on one stream, so disjoint lifetimes may alias)."""
+    placed = []  # (offset, size, first, last)
+    order = sorted((b for b in pb.bufs if b.first >= 0), key=lambda b: (-b.nbytes(pb.B), b.first))
+    total = 0
+    for b in order:
+        size = (b.nbytes(pb.B) + align - 1) // align * align
+        busy = sorted((o, s) for (o, s, f, l) in placed if not (l < b.first or f > b.last))
+        off = 0
+        for (o, s) in busy:
+            if off + size <= o:
+                break
+            off = max(off, o + s)
+        b.offset = off
+        placed.append((off, size, b.first, b.last))
+        total = max(total, off + size)
+    for b in pb.bufs:
+        if b.first < 0:
+            b.offset = 0
+    pb.workspace_bytes = max(total, align)
+    return pb.workspace_bytes
+
+
+def to_ctypes(pb: PlanBuilder):
+    ops = (_lib.Op * len(pb.ops))()
+    for o, r in zip(ops, pb.ops):
+        o.kind = r.kind
+        for name, v in (("in_", r.in_), ("in2", r.in2), ("out", r.out)):
+            cv = getattr(o, name)
+            if v is None:
+                cv.buf, cv.c_off, cv.c = -1, 0, 0
+            else:
+                cv.buf, cv.c_off, cv.c = v.buf.id, v.c_off, v.c
+        o.k, o.stride, o.dil, o.act, o.flags, o.weight_slot = r.k, r.stride, r.dil, r.act, r.flags, r.slot
+        for i in range(8):
+            o.aux[i] = int(r.aux[i])
+        for i in range(4):
+            o.faux[i] = float(r.faux[i])
+    bufs = (_lib.BufDesc * len(pb.bufs))()
+    for d, b in zip(bufs, pb.bufs):
+        d.h, d.w, d.c, d.dtype, d.offset = b.h, b.w, b.c, b.dtype, b.offset
+    import ctypes as C
+    extra = (C.c_int32 * max(1, len(pb.extra)))(*pb.extra)
+    return ops, bufs, extra

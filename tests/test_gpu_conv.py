@@ -1,0 +1,66 @@
+"""GPU: the fused Conv+BN+SiLU(+residual) kernels (tcgen05 path and CUDA-core path) against a torch fp32 restatement of
+Conv.fuseforward (reference models/common.py:45-46, BN fold utils/torch_utils.py:182-202) on identical fp16-rounded inputs.
+Tolerance: |err| <= 2e-3 * max|ref| + fp16 output rounding (the kernels accumulate in fp32; only the sum order differs)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+# (B, H, W, Ci, Co, k, stride, dil, residual)
+SHAPES = [
+    (2, 32, 64, 64, 64, 1, 1, 1, False),      # plain 1x1, SW128
+    (1, 64, 128, 128, 128, 1, 1, 1, False),
+    (2, 16, 32, 512, 256, 1, 1, 1, False),    # 2 N tiles, 8 K stages
+    (1, 16, 32, 1024, 512, 1, 1, 1, False),   # SPP.cv2 class
+    (2, 64, 64, 16, 32, 3, 1, 1, False),      # Focus conv class: kc=16 (SW32), 9 taps
+    (2, 32, 64, 32, 32, 3, 1, 1, True),       # Bottleneck.cv2 + residual, kc=32 (SW64)
+    (1, 32, 64, 64, 64, 3, 1, 1, True),
+    (1, 16, 32, 128, 128, 3, 1, 1, False),
+    (2, 64, 128, 32, 64, 3, 2, 1, False),     # stride-2 parity maps
+    (1, 32, 64, 64, 128, 3, 2, 1, False),
+    (1, 32, 64, 64, 64, 3, 1, 2, False),      # dilated (RFB2 branch1/2)
+    (1, 32, 64, 64, 64, 3, 1, 3, False),
+    (1, 16, 32, 256, 128, 3, 1, 6, False),    # ASPP-like dilation
+    (1, 24, 40, 64, 64, 3, 1, 1, False),      # W, H not multiples of the tile -> OOB zero fill / clipped stores
+    (1, 16, 12, 64, 48, 1, 1, 1, False),      # box wider than the map, Co=48 (m model)
+    (1, 32, 32, 48, 96, 3, 1, 1, False),      # kc=16 with Ci=48, Co=96
+    (1, 16, 32, 192, 192, 1, 1, 1, False),    # Co=192 -> BN=96 x 2
+    (3, 8, 16, 64, 64, 1, 1, 1, False),       # exactly one tile per image
+]
+
+
+def torch_ref(x_nhwc, w, bn, stride, dil, residual, eps=1e-3):
+    x = x_nhwc.float().permute(0, 3, 1, 2).cpu()
+    g, b, m, v = [t.cpu() for t in bn]
+    scale = g / torch.sqrt(v + eps)
+    wf = (w.cpu() * scale.view(-1, 1, 1, 1)).half().float()      # the pack kernel rounds folded weights to fp16
+    k = w.shape[2]
+    y = F.conv2d(x, wf, None, stride, dil * (k // 2), dil) + (b - m * scale).view(1, -1, 1, 1)
+    y = y * torch.sigmoid(y)
+    if residual is not None:
+        y = y + residual.float().permute(0, 3, 1, 2).cpu()
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("path", [2, 1])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_conv_bn_silu(shape, path):
+    from multiyolov5_b200 import ops
+    B, H, W, Ci, Co, k, s, d, res = shape
+    gsd = torch.Generator().manual_seed(hash(shape) % (2 ** 31))
+    x = torch.randn(B, H, W, Ci, generator=gsd).half().cuda()
+    w = (torch.randn(Co, Ci, k, k, generator=gsd) * (2.0 / (Ci * k * k)) ** 0.5).cuda()
+    bn = [torch.rand(Co, generator=gsd) * 0.4 + 0.8, torch.randn(Co, generator=gsd) * 0.1, torch.randn(Co, generator=gsd) * 0.1,
+          torch.rand(Co, generator=gsd) + 0.5]
+    bn = [t.cuda() for t in bn]
+    Ho = (H + 2 * d * (k // 2) - d * (k - 1) - 1) // s + 1
+    Wo = (W + 2 * d * (k // 2) - d * (k - 1) - 1) // s + 1
+    r = torch.randn(B, Ho, Wo, Co, generator=gsd).half().cuda() if res else None
+    y = ops.conv_bn_silu(x, w, bn, stride=s, dil=d, residual=r, path=path)
+    torch.cuda.synchronize()
+    ref = torch_ref(x, w, bn, s, d, r)
+    err = (y.float().cpu() - ref).abs().max().item()
+    tol = 2e-3 * ref.abs().max().item() + 1e-3
+    assert err <= tol, f"path={path} shape={shape}: max err {err:.4g} > {tol:.4g}"

@@ -1,0 +1,96 @@
+"""GPU: post-process parity - NMS rows bit-exact with the reference fixtures / the numpy oracle; seg class ids bit-exact."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restate, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = synth.GOLDEN_DIR
+
+
+def run_nms(pred_np, **kw):
+    from multiyolov5_b200.utils.general import non_max_suppression
+    outs = non_max_suppression(torch.from_numpy(pred_np).cuda(), **kw)
+    torch.cuda.synchronize()
+    return [o.cpu().numpy() for o in outs]
+
+
+def test_nms_reference_fixtures_bit_exact():
+    g = np.load(os.path.join(GOLD, "nms_cases.npz"))
+    settings = json.load(open(os.path.join(GOLD, "nms_settings.json")))
+    n = 0
+    for name, kw in settings.items():
+        for pn in ("big", "small"):
+            if f"out_{name}_{pn}_0" not in g:
+                continue
+            outs = run_nms(g[f"pred_{pn}"], **kw)
+            for b, o in enumerate(outs):
+                ref = g[f"out_{name}_{pn}_{b}"]
+                assert o.shape == ref.shape, (name, pn, b, o.shape, ref.shape)
+                assert np.array_equal(o, ref), (name, pn, b, np.abs(o - ref).max())
+                n += 1
+    assert n >= 16
+
+
+@pytest.mark.parametrize("n,conf,iou", [(10000, 0.25, 0.45), (500, 0.5, 0.3), (33, 0.25, 0.45), (1, 0.25, 0.45)])
+def test_nms_vs_oracle_config5(n, conf, iou):
+    pred = synth.synth_predictions(2, n, seed=n)
+    ref = restate.non_max_suppression(pred, conf, iou)
+    got = run_nms(pred, conf_thres=conf, iou_thres=iou)
+    for r, o in zip(ref, got):
+        assert o.shape == r.shape and np.array_equal(o, r)
+
+
+def test_nms_multilabel_large_and_properties():
+    # 3000 anchors x 10 classes at conf 0.001 -> ~30k candidates: global-memory sort path + max_nms truncation
+    pred = synth.synth_predictions(1, 3200, seed=11)
+    got = run_nms(pred, conf_thres=0.001, iou_thres=0.6, multi_label=True)[0]
+    ref = restate.non_max_suppression(pred, 0.001, 0.6, multi_label=True)[0]
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+    assert got.shape[0] <= 300 and np.all(np.diff(got[:, 4]) <= 0)   # sorted by descending confidence
+
+
+def test_nms_edge_cases():
+    pred = synth.synth_predictions(2, 64, seed=5)
+    assert all(o.shape == (0, 6) for o in run_nms(pred, conf_thres=1.5, iou_thres=0.45))     # nothing passes
+    same = np.repeat(pred[:, :1], 64, axis=1)                                                 # 64 identical boxes -> one survivor
+    outs = run_nms(same, conf_thres=0.01, iou_thres=0.45)
+    refs = restate.non_max_suppression(same, 0.01, 0.45)
+    for o, r in zip(outs, refs):
+        assert np.array_equal(o, r) and o.shape[0] == 1
+    deg = pred.copy(); deg[..., 2:4] = 0.0                                                     # zero-area boxes: NaN IoU never suppresses
+    for o, r in zip(run_nms(deg, conf_thres=0.25, iou_thres=0.45), restate.non_max_suppression(deg, 0.25, 0.45)):
+        assert np.array_equal(o, r)
+
+
+def test_seg_argmax_fixtures_bit_exact():
+    from multiyolov5_b200.utils.general import bilinear_align_corners, seg_argmax
+    g = np.load(os.path.join(GOLD, "segpost_cases.npz"))
+    for name, hw in {"x8": (128, 256), "odd": (40, 77), "same": (24, 24), "up2": (64, 128)}.items():
+        seg = torch.from_numpy(g[f"in_{name}"]).cuda()
+        am = seg_argmax(seg, hw)[0].cpu().numpy()
+        assert np.array_equal(am, g[f"argmax_{name}"].astype(np.int64)), name
+        am8 = seg_argmax(seg, hw, out_dtype=torch.uint8)[0].cpu().numpy()
+        assert np.array_equal(am8, g[f"argmax_{name}"])
+        if f"up_{name}" in g:
+            up = bilinear_align_corners(seg, hw)[0].cpu().numpy()
+            assert np.abs(up - g[f"up_{name}"]).max() <= 1e-5 * np.abs(g[f"up_{name}"]).max()
+
+
+def test_seg_argmax_full_size_property():
+    """config 5 size (19x512x1024): fused upsample+argmax == argmax of the materialised upsample; identity-size == plain argmax."""
+    from multiyolov5_b200.utils.general import bilinear_align_corners, seg_argmax
+    gsd = torch.Generator().manual_seed(0)
+    lo = torch.randn(2, 19, 64, 128, generator=gsd).cuda()
+    fused = seg_argmax(lo, (512, 1024))
+    mat = bilinear_align_corners(lo, (512, 1024))
+    assert torch.equal(fused, mat.argmax(1))
+    full = torch.randn(1, 19, 512, 1024, generator=gsd).cuda()
+    assert torch.equal(seg_argmax(full), full.argmax(1))
+    # oracle on a crop-sized case
+    small = lo[:1, :, :8, :16].contiguous()
+    assert np.array_equal(seg_argmax(small, (64, 128)).cpu().numpy(), restate.seg_postprocess(small.cpu().numpy(), (64, 128)))
