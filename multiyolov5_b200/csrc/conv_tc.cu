@@ -49,7 +49,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   // carve (everything 1024-aligned; dynamic smem base is only guaranteed 16B aligned -> align by hand)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_stages;
-  const int b_bytes_stage = p.BN * kKStage * 2;
+  const int b_bytes_stage = (p.BN * kKStage * 2 + 1023) & ~1023;   // stage stride must keep the 1024-byte swizzle-atom alignment
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + S * kABytesStage;
   uint8_t* smem_o = smem_b + S * b_bytes_stage;
@@ -408,7 +408,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     }
   }
   // shared memory budget
-  const int stage_bytes = kABytesStage + p.BN * kKStage * 2;
+  const int stage_bytes = kABytesStage + (int)align_up(p.BN * kKStage * 2, 1024);
   const int fixed = p.n_sub * kTileM * p.ow * 2 + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   int S = (220 * 1024 - fixed) / stage_bytes;
   if (S > 8) S = 8;

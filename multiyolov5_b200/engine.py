@@ -10,8 +10,8 @@ from .plan import build_plan, to_ctypes
 
 
 class CompiledPlan:
-    def __init__(self, model, B, H, W):
-        self.pb = build_plan(model, B, H, W)
+    def __init__(self, model, B, H, W, noalias=False):
+        self.pb = build_plan(model, B, H, W, noalias=noalias)
         self.ops, self.bufs, self.extra = to_ctypes(self.pb)
         L = _lib.lib()
         h = C.c_void_p()
@@ -65,11 +65,12 @@ class Engine:
         self.plans: Dict[Tuple[int, int, int], CompiledPlan] = {}
         self.weights_dirty = True
         self.last_plan = None
+        self.noalias = False   # debug: give every buffer private memory so intermediate views stay readable after forward
 
     def plan_for(self, B, H, W) -> CompiledPlan:
         key = (B, H, W)
         if key not in self.plans:
-            self.plans[key] = CompiledPlan(self.model, B, H, W)
+            self.plans[key] = CompiledPlan(self.model, B, H, W, self.noalias)
         p = self.plans[key]
         if self.weights_dirty:
             for q in self.plans.values():

@@ -371,7 +371,7 @@ def infer_strides(model):
     return _layer_meta(model)[1]
 
 
-def build_plan(model, B: int, H: int, W: int) -> PlanBuilder:
+def build_plan(model, B: int, H: int, W: int, noalias: bool = False) -> PlanBuilder:
     """Lowers model.model (yaml layers) for a fixed input shape."""
     from .models import yolo as Y
     assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of the max stride 32 (reference check_img_size)"
@@ -443,18 +443,18 @@ def build_plan(model, B: int, H: int, W: int) -> PlanBuilder:
         outs[i] = y
         # keep saved layers alive until their last consumer: extend liveness at consumption time (done by emit/_touch)
     pb.layer_views = outs
-    assign_offsets(pb)
+    assign_offsets(pb, noalias=noalias)
     return pb
 
 
-def assign_offsets(pb: PlanBuilder, align: int = 256):
+def assign_offsets(pb: PlanBuilder, align: int = 256, noalias: bool = False):
     """first-fit packing of [first,last] live intervals (ops run sequentially on one stream, so disjoint lifetimes may alias)."""
     placed = []  # (offset, size, first, last)
     order = sorted((b for b in pb.bufs if b.first >= 0), key=lambda b: (-b.nbytes(pb.B), b.first))
     total = 0
     for b in order:
         size = (b.nbytes(pb.B) + align - 1) // align * align
-        busy = sorted((o, s) for (o, s, f, l) in placed if not (l < b.first or f > b.last))
+        busy = sorted((o, s) for (o, s, f, l) in placed if noalias or not (l < b.first or f > b.last))
         off = 0
         for (o, s) in busy:
             if off + size <= o:

@@ -44,8 +44,8 @@ def torch_ref(x_nhwc, w, bn, stride, dil, residual, eps=1e-3):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("path", [2, 1])
-@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("path,shape", [(p, s) for p in (2, 1) for s in SHAPES],
+                         ids=[f"{'simt' if p == 2 else 'tc'}-{i}" for p in (2, 1) for i in range(len(SHAPES))])
 def test_conv_bn_silu(shape, path):
     from multiyolov5_b200 import ops
     B, H, W, Ci, Co, k, s, d, res = shape
