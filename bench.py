@@ -81,8 +81,18 @@ def cpu_reference_line(args, tag, steps, warmup, as_main):
     from oracle import synth
     from oracle.cpu_pipeline import CpuPipeline
     yml, cfg, sd = make_weights(tag)
-    pipe = CpuPipeline(cfg, sd, threads=os.cpu_count())
     x = synth.synth_image(1, H, W, seed=0)
+    # the reference would run with torch's default (= all cores); small-batch convs often run faster with fewer threads, so give the
+    # CPU arm its best case: probe a few thread counts and keep the fastest
+    ncpu = os.cpu_count() or 1
+    best = None
+    for th in sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu}):
+        pipe = CpuPipeline(cfg, sd, threads=th)
+        pipe(x)
+        t0 = time.perf_counter(); pipe(x); dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, th)
+    pipe = CpuPipeline(cfg, sd, threads=best[1])
     for _ in range(warmup):
         pipe(x)
     ts, parts = [], []
@@ -95,7 +105,7 @@ def cpu_reference_line(args, tag, steps, warmup, as_main):
     info = {"value": 1.0 / med, "unit": "images/s", "cores": pipe.threads, "kind": "port",
             "sample": f"{steps} steps x 1 image 3x{H}x{W} fp32 (model {np.median([p['model'] for p in parts]) * 1e3:.1f} ms, nms "
                       f"{np.median([p['nms'] for p in parts]) * 1e3:.1f} ms, seg upsample+argmax {np.median([p['segpost'] for p in parts]) * 1e3:.1f} ms), "
-                      f"os.cpu_count()={os.cpu_count()}"}
+                      f"os.cpu_count()={os.cpu_count()}, torch threads={pipe.threads} (fastest of 8/16/32/64/all)"}
     if not as_main:
         return info
     return {"metric": "images/sec @1024x512 (det+seg fwd)", "value": info["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": steps,

@@ -392,7 +392,8 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   p.out_mode = op.out.dtype == MYOLO_F16 ? 0 : 1;
   p.out_f32 = p.out_mode ? reinterpret_cast<float*>(op.out.base) : nullptr;
   p.out_f32_ctot = p.out_mode ? op.out.ctot : 0;
-  p.ow = p.BN >= 64 ? 64 : (p.BN >= 32 ? 32 : 16);
+  // sub-box width must divide BN: a wider last sub-box would spill garbage into the next N tile's channels
+  p.ow = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
   p.n_sub = p.out_mode == 0 ? ceil_div(p.BN, p.ow) : 0;
   for (int t = 0; t < p.taps; ++t) {
     const int ky = op.k == 3 ? t / 3 : 1, kx = op.k == 3 ? t % 3 : 1;
