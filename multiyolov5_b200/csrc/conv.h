@@ -21,6 +21,9 @@ struct ConvTcParams {
   int out_mode;          // 0: fp16 NHWC slice via TMA store, 1: fp32 NHWC direct stores
   int ow;                // output sub-box width in channels (16/32/64)
   int n_sub;             // sub-boxes per N tile
+  int log2_tw, log2_ow;
+  int ws_mode;           // weights-stationary: the whole [BN x K] weight tile stays resident in shared memory
+  int b_res_bytes;       // bytes of the resident weight region (ws_mode)
   const float* bias;
   const __half* residual;  // nullable; base of the residual slice (image 0, pixel 0, channel 0 of the slice)
   int res_ctot;

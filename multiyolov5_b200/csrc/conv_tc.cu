@@ -22,12 +22,15 @@ namespace myolo {
 static constexpr int kTileM = 128;
 static constexpr int kKStage = 64;        // K elements per pipeline stage
 static constexpr int kABytesStage = kTileM * kKStage * 2;  // 16 KB
-static constexpr int kNumThreads = 192;
+static constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, each takes every other 16-column chunk
+static constexpr int kEpiThreads = kEpiWarps * 32;
+static constexpr int kNumThreads = 64 + kEpiThreads;
 static constexpr int kTmemCols = 256;     // 2 accumulator stages x 128 columns
 static constexpr int kAccStride = 128;
+static constexpr int kMaxWsBytes = 72 * 1024;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
-  // K-major canonical layout, rows of kc*2 bytes, 8-row groups (reference: PTX ISA "matrix descriptor", sm_100 version=1)
+  // K-major canonical layout, rows of kc*2 bytes, 8-row groups (PTX ISA "matrix descriptor", sm_100 version=1)
   const uint32_t sw_bytes = kc * 2;
   const uint64_t layout = sw_bytes == 128 ? 2ull : (sw_bytes == 64 ? 4ull : 6ull);
   const uint64_t sbo = (8u * sw_bytes) >> 4;
@@ -40,26 +43,47 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
   return d;
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+struct TileCoord { int b, y0, x0, n0; };
+__device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile, int tiles_per_img) {
+  TileCoord t;
+  const int n_tile = tile % p.n_tiles_n;
+  const int m_tile = tile / p.n_tiles_n;
+  t.b = m_tile / tiles_per_img;
+  const int r = m_tile - t.b * tiles_per_img;
+  const int ty = r / p.tiles_x;
+  t.y0 = ty * p.th;
+  t.x0 = (r - ty * p.tiles_x) * p.tw;
+  t.n0 = n_tile * p.BN;
+  return t;
+}
+
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
                const __grid_constant__ ConvTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve (everything 1024-aligned; dynamic smem base is only guaranteed 16B aligned -> align by hand)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_stages;
-  const int b_bytes_stage = (p.BN * kKStage * 2 + 1023) & ~1023;   // stage stride must keep the 1024-byte swizzle-atom alignment
+  const int b_bytes_stage = p.ws_mode ? 0 : ((p.BN * kKStage * 2 + 1023) & ~1023);  // stage stride keeps the 1024-byte atom alignment
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + S * kABytesStage;
-  uint8_t* smem_o = smem_b + S * b_bytes_stage;
+  uint8_t* smem_b = smem_a + S * kABytesStage;                 // per-stage B, or the resident weight tile (ws_mode)
+  uint8_t* smem_o = smem_b + (p.ws_mode ? p.b_res_bytes : S * b_bytes_stage);
   const int sub_bytes = kTileM * p.ow * 2;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + p.n_sub * sub_bytes);
+  const int stg_bytes = p.n_sub * sub_bytes;                   // one staging buffer; two are allocated (double buffered)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * stg_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint64_t* bres_bar = bars + 2 * S + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -74,8 +98,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], kEpiWarps);
     }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
@@ -90,31 +115,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
+    if (p.ws_mode) {   // whole weight tile once; every tile of this CTA reuses it (n_tiles_n == 1)
+      mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
+      for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
+    }
     int stage = 0;
     uint32_t phase = 0;
+    const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
-      const int b = m_tile / tiles_per_img;
-      const int r = m_tile - b * tiles_per_img;
-      const int y0 = (r / p.tiles_x) * p.th;
-      const int x0 = (r % p.tiles_x) * p.tw;
-      const int n0 = n_tile * p.BN;
+      const TileCoord t = decode_tile(p, tile, tiles_per_img);
+      int tap = 0, cb = 0, q = 0;
       for (int ks = 0; ks < p.n_kstages; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int q0 = ks * p.chunks_per_stage;
-        const int nch = min(p.chunks_per_stage, p.n_chunks - q0);
-        mbar_arrive_expect_tx(&full_bar[stage], nch * (a_sub_bytes + b_sub_bytes));
+        const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+        mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
         uint8_t* sa = smem_a + stage * kABytesStage;
         uint8_t* sb = smem_b + stage * b_bytes_stage;
-        for (int j = 0; j < nch; ++j) {
-          const int q = q0 + j;
-          const int tap = q / p.cblocks;
-          const int cb = q - tap * p.cblocks;
+        for (int j = 0; j < nch; ++j, ++q) {
           const int mi = p.tap_map[tap];
           const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-          tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, x0 + p.tap_dx[tap], y0 + p.tap_dy[tap], b);
-          tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, n0);
+          tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.b);
+          if (!p.ws_mode) tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t.n0);
+          if (++cb == p.cblocks) { cb = 0; ++tap; }
         }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
@@ -131,18 +153,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     const int kmma = p.kc / 16;
+    if (p.ws_mode) mbar_wait(bres_bar, 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + as * kAccStride;
+      int q = 0;
       for (int ks = 0; ks < p.n_kstages; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const int q0 = ks * p.chunks_per_stage;
-        const int nch = min(p.chunks_per_stage, p.n_chunks - q0);
+        const int nch = min(p.chunks_per_stage, p.n_chunks - q);
         const uint32_t sa = smem_u32(smem_a + stage * kABytesStage);
-        const uint32_t sb = smem_u32(smem_b + stage * b_bytes_stage);
-        for (int j = 0; j < nch; ++j) {
+        const uint32_t sb = p.ws_mode ? smem_u32(smem_b) + q * b_sub_bytes : smem_u32(smem_b + stage * b_bytes_stage);
+        for (int j = 0; j < nch; ++j, ++q) {
           const uint64_t da = make_smem_desc(sa + j * a_sub_bytes, p.kc);
           const uint64_t db = make_smem_desc(sb + j * b_sub_bytes, p.kc);
           for (int k = 0; k < kmma; ++k) {
@@ -157,110 +180,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 2) {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., chunks c = half, half+2, ... =====================
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;   // tile row == pixel index inside the tw x th rectangle
-    const int et = threadIdx.x - 64;       // 0..127
+    const int et = threadIdx.x - 64;       // 0..255
+    const int ry = row >> p.log2_tw, rx = row & (p.tw - 1);
+    const int nchunk16 = p.BN >> 4;
+    const int units_log2 = p.log2_ow - 3;  // 16-byte units per staging row: 8 / 4 / 2
+    const int sw = units_log2 == 3 ? (row & 7) : (units_log2 == 2 ? ((row >> 1) & 3) : ((row >> 2) & 1));
+    const uint32_t stg_row0 = smem_u32(smem_o) + row * (p.ow * 2);
     int as = 0;
     uint32_t aphase = 0;
-    const int nchunk16 = p.BN / 16;
-    const int units_per_row = p.ow / 8;    // 16-byte units per staging row
+    int sbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles_n;
-      const int m_tile = tile / p.n_tiles_n;
-      const int b = m_tile / tiles_per_img;
-      const int r = m_tile - b * tiles_per_img;
-      const int y0 = (r / p.tiles_x) * p.th;
-      const int x0 = (r % p.tiles_x) * p.tw;
-      const int n0 = n_tile * p.BN;
-      const int py = y0 + row / p.tw;
-      const int px = x0 + row % p.tw;
+      const TileCoord t = decode_tile(p, tile, tiles_per_img);
+      const int py = t.y0 + ry, px = t.x0 + rx;
       const bool pix_ok = (py < p.Ho) && (px < p.Wo);
-      const size_t pix = ((size_t)b * p.Ho + py) * p.Wo + px;
-
+      const size_t pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
+      // residual rows do not depend on the accumulator: fetch them before waiting for the MMA
+      uint4 rres[4][2];
+      if (p.residual != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = half + 2 * i;
+          if (c < nchunk16 && pix_ok) {
+            const __half* rp = p.residual + pix * p.res_ctot + t.n0 + c * 16;
+            rres[i][0] = (t.n0 + c * 16 < p.Co) ? __ldg(reinterpret_cast<const uint4*>(rp)) : make_uint4(0, 0, 0, 0);
+            rres[i][1] = (t.n0 + c * 16 + 8 < p.Co) ? __ldg(reinterpret_cast<const uint4*>(rp + 8)) : make_uint4(0, 0, 0, 0);
+          } else {
+            rres[i][0] = rres[i][1] = make_uint4(0, 0, 0, 0);
+          }
+        }
+      }
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
       if (p.out_mode == 0) {
-        // staging smem is about to be overwritten: the previous tile's TMA stores must have finished reading it
-        if (et == 0) tma_store_wait_read0();
-        named_bar_sync(1, 128);
+        // this staging buffer was handed to the TMA store engine two tiles ago: it must have been read by now
+        if (et == 0) tma_store_wait_read<1>();
+        named_bar_sync(1, kEpiThreads);
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride;
-      for (int c = 0; c < nchunk16; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + c * 16, v);
-        tmem_ld_wait();
-        const int nb = n0 + c * 16;
-        float f[16];
-        const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+      const uint32_t stg_row = stg_row0 + sbuf * stg_bytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bb = __ldg(bp + i);
-          f[4 * i + 0] = __uint_as_float(v[4 * i + 0]) + bb.x;
-          f[4 * i + 1] = __uint_as_float(v[4 * i + 1]) + bb.y;
-          f[4 * i + 2] = __uint_as_float(v[4 * i + 2]) + bb.z;
-          f[4 * i + 3] = __uint_as_float(v[4 * i + 3]) + bb.w;
-        }
-        if (p.act == MYOLO_ACT_SILU) {
+      for (int i = 0; i < 4; ++i) {
+        const int c = half + 2 * i;
+        if (c < nchunk16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + c * 16, v);
+          const int nb = t.n0 + c * 16;
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+          const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+          tmem_ld_wait();
+          float f[16];
+          f[0] = __uint_as_float(v[0]) + b0.x;   f[1] = __uint_as_float(v[1]) + b0.y;
+          f[2] = __uint_as_float(v[2]) + b0.z;   f[3] = __uint_as_float(v[3]) + b0.w;
+          f[4] = __uint_as_float(v[4]) + b1.x;   f[5] = __uint_as_float(v[5]) + b1.y;
+          f[6] = __uint_as_float(v[6]) + b1.z;   f[7] = __uint_as_float(v[7]) + b1.w;
+          f[8] = __uint_as_float(v[8]) + b2.x;   f[9] = __uint_as_float(v[9]) + b2.y;
+          f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
+          f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y;
+          f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
+          if (p.act == MYOLO_ACT_SILU) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = silu_f(f[i]);
-        } else if (p.act == MYOLO_ACT_SIGMOID) {
+            for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
+          } else if (p.act == MYOLO_ACT_SIGMOID) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = sigmoid_f(f[i]);
-        }
-        if (p.residual != nullptr && pix_ok) {
-          const __half* rp = p.residual + pix * p.res_ctot + nb;
+            for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
+          }
+          if (p.residual != nullptr) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (nb + h * 8 < p.Co) {
-              const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp + h * 8));
-              const __half2* r2 = reinterpret_cast<const __half2*>(&rv);
+            for (int h = 0; h < 2; ++h) {
+              const __half2* r2 = reinterpret_cast<const __half2*>(&rres[i][h]);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 rf = __half22float2(r2[i]);
-                f[h * 8 + 2 * i] += rf.x;
-                f[h * 8 + 2 * i + 1] += rf.y;
+              for (int e = 0; e < 4; ++e) {
+                const float2 rf = __half22float2(r2[e]);
+                f[h * 8 + 2 * e] += rf.x;
+                f[h * 8 + 2 * e + 1] += rf.y;
               }
             }
           }
-        }
-        if (p.out_mode == 0) {
-          const int sub = (c * 16) / p.ow;
-          const int u0 = ((c * 16) % p.ow) / 8;
-          uint8_t* srow = smem_o + sub * sub_bytes + row * (p.ow * 2);
-          int sw;
-          if (units_per_row == 8) sw = row & 7;
-          else if (units_per_row == 4) sw = (row >> 1) & 3;
-          else sw = (row >> 2) & 1;
+          if (p.out_mode == 0) {
+            const int ch = c << 4;
+            const int sub = ch >> p.log2_ow;
+            const int u0 = (ch & (p.ow - 1)) >> 3;
+            const uint32_t srow = stg_row + sub * sub_bytes;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint4 o;
-            __half2* o2 = reinterpret_cast<__half2*>(&o);
+            for (int h = 0; h < 2; ++h) {
+              uint4 o;
+              __half2* o2 = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) o2[i] = __floats2half2_rn(f[h * 8 + 2 * i], f[h * 8 + 2 * i + 1]);
-            *reinterpret_cast<uint4*>(srow + (((u0 + h) ^ sw) * 16)) = o;
-          }
-        } else if (pix_ok) {
-          float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
+              for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(f[h * 8 + 2 * e], f[h * 8 + 2 * e + 1]);
+              sts128(srow + (((u0 + h) ^ sw) << 4), o);
+            }
+          } else if (pix_ok) {
+            float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (nb + 4 * i < p.out_f32_ctot)
-              *reinterpret_cast<float4*>(op + 4 * i) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+            for (int e = 0; e < 4; ++e) {
+              if (nb + 4 * e < p.out_f32_ctot)
+                *reinterpret_cast<float4*>(op + 4 * e) = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+            }
           }
         }
       }
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp (one arrival per warp)
       tcgen05_fence_before();
-      mbar_arrive(&tempty_bar[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (p.out_mode == 0) {
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (et == 0) {
           for (int s = 0; s < p.n_sub; ++s) {
-            if (n0 + s * p.ow < p.Co) tma_store_4d(&tmO, smem_o + s * sub_bytes, n0 + s * p.ow, x0, y0, b);
+            if (t.n0 + s * p.ow < p.Co) tma_store_4d(&tmO, smem_o + sbuf * stg_bytes + s * sub_bytes, t.n0 + s * p.ow, t.x0, t.y0, t.b);
           }
           tma_store_commit();
         }
+        sbuf ^= 1;
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -408,9 +444,16 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
       p.tap_dx[t] = (kx == 0) ? -1 : 0;
     }
   }
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+  p.log2_tw = ilog2(p.tw);
+  p.log2_ow = ilog2(p.ow);
+  // weights-stationary mode: one N tile and the whole [BN x K] weight tile fits next to the A ring
+  const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
+  p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= kMaxWsBytes) ? 1 : 0;
+  p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
   // shared memory budget
-  const int stage_bytes = kABytesStage + (int)align_up(p.BN * kKStage * 2, 1024);
-  const int fixed = p.n_sub * kTileM * p.ow * 2 + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  const int stage_bytes = kABytesStage + (p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024));
+  const int fixed = p.b_res_bytes + 2 * p.n_sub * kTileM * p.ow * 2 + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   int S = (220 * 1024 - fixed) / stage_bytes;
   if (S > 8) S = 8;
   MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");

@@ -382,36 +382,33 @@ int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s
 // ------------------------------------------------------------------------------------------------
 __global__ void detect_decode_kernel(TensorView in, int na, int no, float stride, const float* __restrict__ anchors, float* raw,
                                      float* z, int z_off, int z_rows) {
-  const long total = (long)in.B * na * in.H * in.W;
+  // one thread per output element: (b, a, y, x, o) with o fastest -> reads, raw writes and z writes are all coalesced
+  const long total = (long)in.B * na * in.H * in.W * no;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % in.W);
-    long p = i / in.W;
+    const int o = (int)(i % no);
+    long p = i / no;
+    const int x = (int)(p % in.W);
+    p /= in.W;
     const int y = (int)(p % in.H);
     p /= in.H;
     const int a = (int)(p % na);
     const int b = (int)(p / na);
-    const float* src = vptr_f(in, b, y, x) + a * no;
-    const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
-    float* r = raw ? raw + row * no : nullptr;
-    float* zz = z + ((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no;
-    for (int o = 0; o < no; ++o) {
-      const float v = src[o];
-      if (r) r[o] = v;
-      float sg = 1.0f / (1.0f + expf(-v));
-      if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
-      else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
-      else if (o == 2 || o == 3) {
-        const float t = sg * 2.0f;
-        sg = t * t * anchors[a * 2 + (o - 2)];
-      }
-      zz[o] = sg;
+    const float v = vptr_f(in, b, y, x)[a * no + o];
+    if (raw) raw[i] = v;
+    float sg = 1.0f / (1.0f + expf(-v));
+    if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
+    else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
+    else if (o == 2 || o == 3) {
+      const float t = sg * 2.0f;
+      sg = t * t * anchors[a * 2 + (o - 2)];
     }
+    z[((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no + o] = sg;
   }
 }
 int launch_detect_decode(const TensorView& in, int na, int no, float stride, const float* d_anchors, float* raw, float* z,
                          int z_row_offset, int z_rows_total, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.C >= na * no, "detect_decode: bad view");
-  detect_decode_kernel<<<grid_for((long)in.B * na * in.H * in.W, 128), 128, 0, s>>>(in, na, no, stride, d_anchors, raw, z,
+  detect_decode_kernel<<<grid_for((long)in.B * na * in.H * in.W * no, 256), 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z,
                                                                                    z_row_offset, z_rows_total);
   MYOLO_LAUNCH_CHECK();
   return 0;
@@ -421,45 +418,93 @@ int launch_detect_decode(const TensorView& in, int na, int no, float stride, con
 // final seg upsample: fp32 NHWC low-res logits (ctot-padded) -> NCHW logits and/or fused argmax (first max wins)
 // one thread per output pixel; x fastest so every per-class store is a coalesced 128-byte line per warp.
 // ------------------------------------------------------------------------------------------------
+template <typename TOut> struct Pack4;
+template <> struct Pack4<float> {
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+};
+template <> struct Pack4<__half> {
+  static __device__ __forceinline__ void store(__half* p, float a, float b, float c, float d) {
+    uint2 u;
+    *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(a, b);
+    *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// One CTA = one output row segment of 4*blockDim.x pixels of one image.  The two source rows it needs are staged in shared
+// memory as [row][class][col] (col fastest -> conflict-free), every thread then produces 4 consecutive pixels for all classes
+// with 16-byte stores: per class a warp writes 512 contiguous bytes.  ATen operation order is kept (exact fp32, no FMA).
 template <typename TOut>
-__global__ void seg_upsample_kernel(TensorView in, int ncls, int H, int W, TOut* seg, int64_t* amax) {
-  const long total = (long)in.B * H * W;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int x = (int)(i % W);
-    const int y = (int)((i / W) % H);
-    const int b = (int)(i / ((long)W * H));
-    const Lerp ly = lerp_axis(y, in.H, H), lx = lerp_axis(x, in.W, W);
-    const float* pa = vptr_f(in, b, ly.i0, lx.i0);
-    const float* pb = vptr_f(in, b, ly.i0, lx.i1);
-    const float* pc = vptr_f(in, b, ly.i1, lx.i0);
-    const float* pd = vptr_f(in, b, ly.i1, lx.i1);
-    float best = 0.f;
-    int bi = 0;
-    for (int c4 = 0; c4 < ncls; c4 += 4) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(pa + c4));
-      const float4 bq = __ldg(reinterpret_cast<const float4*>(pb + c4));
-      const float4 cq = __ldg(reinterpret_cast<const float4*>(pc + c4));
-      const float4 d = __ldg(reinterpret_cast<const float4*>(pd + c4));
-      const float va[4] = {a.x, a.y, a.z, a.w}, vb[4] = {bq.x, bq.y, bq.z, bq.w}, vc[4] = {cq.x, cq.y, cq.z, cq.w},
-                  vd[4] = {d.x, d.y, d.z, d.w};
+__global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int ncls, int H, int W, TOut* seg, int64_t* amax) {
+  extern __shared__ float sup_smem[];
+  const int segs = (W + 4 * blockDim.x - 1) / (4 * blockDim.x);
+  const int sx = blockIdx.x % segs;
+  const int y = (blockIdx.x / segs) % H;
+  const int b = blockIdx.x / (segs * H);
+  const int xbeg = sx * 4 * blockDim.x;
+  const int xend = min(W, xbeg + 4 * (int)blockDim.x);
+  const Lerp ly = lerp_axis(y, in.H, H);
+  const int c0 = lerp_axis(xbeg, in.W, W).i0;
+  const int c1 = lerp_axis(xend - 1, in.W, W).i1;
+  const int ncol = c1 - c0 + 1;
+  const int pitch = ncol | 1;                      // odd pitch: rows of different classes start in different banks
+  float* s0 = sup_smem;                            // [ncls][pitch] source row i0
+  float* s1 = sup_smem + ncls * pitch;             // source row i1
+  const int c4n = (ncls + 3) / 4;
+  for (int i = threadIdx.x; i < 2 * ncol * c4n; i += blockDim.x) {
+    const int r = i / (ncol * c4n);
+    const int rem = i - r * ncol * c4n;
+    const int col = rem / c4n, c4 = rem % c4n;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(vptr_f(in, b, r ? ly.i1 : ly.i0, c0 + col)) + c4);
+    float* d = (r ? s1 : s0) + col;
+    const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int c = c4 + k;
-        if (c < ncls) {
-          const float val = bilerp(va[k], vb[k], vc[k], vd[k], ly, lx);
-          if (seg) seg[(((size_t)b * ncls + c) * H + y) * W + x] = (TOut)val;
-          if (c == 0 || val > best) { best = val; bi = c; }
-        }
-      }
+    for (int k = 0; k < 4; ++k)
+      if (c4 * 4 + k < ncls) d[(c4 * 4 + k) * pitch] = vv[k];
+  }
+  __syncthreads();
+  const int x0 = xbeg + 4 * threadIdx.x;
+  if (x0 >= W) return;
+  Lerp lx[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    lx[j] = lerp_axis(min(x0 + j, W - 1), in.W, W);
+    lx[j].i0 -= c0;
+    lx[j].i1 -= c0;
+  }
+  float best[4] = {0.f, 0.f, 0.f, 0.f};
+  int bi[4] = {0, 0, 0, 0};
+  const bool full = (x0 + 3 < W) && (W % 4 == 0);
+  for (int c = 0; c < ncls; ++c) {
+    const float* r0 = s0 + c * pitch;
+    const float* r1 = s1 + c * pitch;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
+      if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
     }
-    if (amax) amax[i] = bi;
+    if (seg) {
+      TOut* o = seg + (((size_t)b * ncls + c) * H + y) * W + x0;
+      if (full) Pack4<TOut>::store(o, v[0], v[1], v[2], v[3]);
+      else
+        for (int j = 0; j < 4 && x0 + j < W; ++j) o[j] = (TOut)v[j];
+    }
+  }
+  if (amax) {
+    int64_t* o = amax + ((size_t)b * H + y) * W + x0;
+    for (int j = 0; j < 4 && x0 + j < W; ++j) o[j] = bi[j];
   }
 }
 int launch_seg_upsample(const TensorView& in, int n_cls, int H, int W, void* seg, int seg_dtype, int64_t* argmax, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.ctot % 4 == 0 && in.ctot >= ((n_cls + 3) / 4) * 4, "seg_upsample: bad view");
-  const int g = grid_for((long)in.B * H * W, 256, 148 * 64);
-  if (seg_dtype == MYOLO_F16) seg_upsample_kernel<__half><<<g, 256, 0, s>>>(in, n_cls, H, W, (__half*)seg, argmax);
-  else seg_upsample_kernel<float><<<g, 256, 0, s>>>(in, n_cls, H, W, (float*)seg, argmax);
+  const int threads = W >= 1024 ? 256 : (W >= 512 ? 128 : 64);
+  const int segs = ceil_div(W, 4 * threads);
+  const size_t smem = (size_t)2 * n_cls * ((in.W + 2) | 1) * 4;
+  MYOLO_REQUIRE(smem <= 48 * 1024, "seg_upsample: source row too wide for the shared-memory kernel (%d cols x %d classes)", in.W, n_cls);
+  const long blocks = (long)in.B * H * segs;
+  if (seg_dtype == MYOLO_F16) seg_upsample_kernel<__half><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, (__half*)seg, argmax);
+  else seg_upsample_kernel<float><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, (float*)seg, argmax);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -484,6 +529,29 @@ __global__ void seg_argmax_nchw_kernel(const TIn* __restrict__ src, int B, int C
       if (c == 0 || val > best) { best = val; bi = c; }
     }
     out[i] = (TOut)bi;
+  }
+}
+
+// same-size case of detect.py:191-193 (bilinear to the identical size is the identity): pure argmax, 4 pixels per thread,
+// one 16-byte load per class plane -> C independent loads in flight per thread.
+template <typename TOut>
+__global__ void argmax_nchw_f32x4_kernel(const float* __restrict__ src, int B, int C, long HW, TOut* out) {
+  const long n4 = (long)B * HW / 4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i * 4;
+    const long b = pix / HW, off = pix - b * HW;
+    const float* p = src + b * C * HW + off;
+    float4 best = __ldg(reinterpret_cast<const float4*>(p));
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+#pragma unroll 6
+    for (int c = 1; c < C; ++c) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(p + (size_t)c * HW));
+      if (v.x > best.x) { best.x = v.x; i0 = c; }
+      if (v.y > best.y) { best.y = v.y; i1 = c; }
+      if (v.z > best.z) { best.z = v.z; i2 = c; }
+      if (v.w > best.w) { best.w = v.w; i3 = c; }
+    }
+    out[pix] = (TOut)i0; out[pix + 1] = (TOut)i1; out[pix + 2] = (TOut)i2; out[pix + 3] = (TOut)i3;
   }
 }
 
@@ -526,6 +594,13 @@ extern "C" int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, i
                 "seg_upsample_argmax: unsupported dtype");
   cudaStream_t s = (cudaStream_t)stream;
   const int g = grid_for((long)B * H * W, 256, 148 * 64);
+  if (dtype == MYOLO_F32 && H == h && W == w && ((long)H * W) % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const int g4 = grid_for((long)B * H * W / 4, 256, 148 * 32);
+    if (out_dtype == MYOLO_I64) argmax_nchw_f32x4_kernel<int64_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (int64_t*)out);
+    else argmax_nchw_f32x4_kernel<uint8_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (uint8_t*)out);
+    MYOLO_LAUNCH_CHECK();
+    return 0;
+  }
   if (dtype == MYOLO_F32) {
     if (out_dtype == MYOLO_I64) seg_argmax_nchw_kernel<float, int64_t><<<g, 256, 0, s>>>((const float*)logits, B, C, h, w, H, W, (int64_t*)out);
     else seg_argmax_nchw_kernel<float, uint8_t><<<g, 256, 0, s>>>((const float*)logits, B, C, h, w, H, W, (uint8_t*)out);
