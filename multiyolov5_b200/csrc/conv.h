@@ -24,6 +24,7 @@ struct ConvTcParams {
   int log2_tw, log2_ow;
   int ws_mode;           // weights-stationary: the whole [BN x K] weight tile stays resident in shared memory
   int b_res_bytes;       // bytes of the resident weight region (ws_mode)
+  int n_stg;             // TMA-store staging buffers (1 or 2)
   const float* bias;
   const __half* residual;  // nullable; base of the residual slice (image 0, pixel 0, channel 0 of the slice)
   int res_ctot;

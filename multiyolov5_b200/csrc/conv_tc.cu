@@ -27,7 +27,9 @@ static constexpr int kEpiThreads = kEpiWarps * 32;
 static constexpr int kNumThreads = 64 + kEpiThreads;
 static constexpr int kTmemCols = 256;     // 2 accumulator stages x 128 columns
 static constexpr int kAccStride = 128;
-static constexpr int kMaxWsBytes = 72 * 1024;
+static constexpr int kMaxWsBytes = 40 * 1024;
+static constexpr int kSmemPerCta = 112 * 1024;   // two CTAs per SM: their epilogues / TMA latencies overlap
+static constexpr int kTileRing = 16;
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
   // K-major canonical layout, rows of kc*2 bytes, 8-row groups (PTX ISA "matrix descriptor", sm_100 version=1)
@@ -63,7 +65,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
   return t;
 }
 
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kNumThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
@@ -77,13 +79,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem_o = smem_b + (p.ws_mode ? p.b_res_bytes : S * b_bytes_stage);
   const int sub_bytes = kTileM * p.ow * 2;
   const int stg_bytes = p.n_sub * sub_bytes;                   // one staging buffer; two are allocated (double buffered)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + 2 * stg_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + p.n_stg * stg_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
   uint64_t* bres_bar = bars + 2 * S + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
+  int4* tile_ring = reinterpret_cast<int4*>(bars + 2 * S + 6);   // {b, y0, x0, n0} per tile iteration, written by the producer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,8 +125,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const TileCoord t = decode_tile(p, tile, tiles_per_img);
+      // the epilogue reads this slot only after tfull of the same tile, i.e. long after this write (released by the mbarrier chain)
+      tile_ring[it & (kTileRing - 1)] = make_int4(t.b, t.y0, t.x0, t.n0);
       int tap = 0, cb = 0, q = 0;
       for (int ks = 0; ks < p.n_kstages; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -193,14 +199,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile, tiles_per_img);
-      const int py = t.y0 + ry, px = t.x0 + rx;
-      const bool pix_ok = (py < p.Ho) && (px < p.Wo);
-      const size_t pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      TileCoord t;
+      if (p.residual != nullptr) {
+        t = decode_tile(p, tile, tiles_per_img);   // needed before the wait (residual prefetch); only 7 of ~80 layers
+      }
+      int py = 0, px = 0;
+      bool pix_ok = false;
+      size_t pix = 0;
       // residual rows do not depend on the accumulator: fetch them before waiting for the MMA
       uint4 rres[4][2];
       if (p.residual != nullptr) {
+        py = t.y0 + ry; px = t.x0 + rx;
+        pix_ok = (py < p.Ho) && (px < p.Wo);
+        pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = half + 2 * i;
@@ -215,9 +228,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
+      if (p.residual == nullptr) {
+        const int4 ti = tile_ring[it & (kTileRing - 1)];
+        t.b = ti.x; t.y0 = ti.y; t.x0 = ti.z; t.n0 = ti.w;
+        if (p.out_mode != 0) {
+          py = t.y0 + ry; px = t.x0 + rx;
+          pix_ok = (py < p.Ho) && (px < p.Wo);
+          pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
+        }
+      }
       if (p.out_mode == 0) {
-        // this staging buffer was handed to the TMA store engine two tiles ago: it must have been read by now
-        if (et == 0) tma_store_wait_read<1>();
+        // the staging buffer about to be overwritten was handed to the TMA store engine n_stg tiles ago: it must have been read
+        if (et == 0) {
+          if (p.n_stg == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
         named_bar_sync(1, kEpiThreads);
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride;
@@ -296,7 +321,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
           tma_store_commit();
         }
-        sbuf ^= 1;
+        if (p.n_stg == 2) sbuf ^= 1;
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -451,15 +476,28 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
   p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= kMaxWsBytes) ? 1 : 0;
   p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
-  // shared memory budget
+  // shared memory budget: aim for two co-resident CTAs per SM (<= 112 KB each); fall back to one big CTA otherwise
   const int stage_bytes = kABytesStage + (p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024));
-  const int fixed = p.b_res_bytes + 2 * p.n_sub * kTileM * p.ow * 2 + 1024 /*barriers*/ + 1024 /*alignment slack*/;
-  int S = (220 * 1024 - fixed) / stage_bytes;
+  const int stg1 = p.n_sub * kTileM * p.ow * 2;
+  const int misc = 2048 /*barriers + tile ring*/ + 1024 /*alignment slack*/;
+  int ctas_per_sm = 2;
+  p.n_stg = p.out_mode == 0 ? 2 : 0;
+  int S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+  if (S < 3 && p.n_stg == 2) {
+    p.n_stg = 1;
+    S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+  }
+  if (S < 2) {
+    ctas_per_sm = 1;
+    p.n_stg = p.out_mode == 0 ? 2 : 0;
+    S = (220 * 1024 - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+  }
   if (S > 8) S = 8;
   MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");
   p.num_stages = S;
-  op.smem = S * stage_bytes + fixed;
-  op.grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  op.smem = S * stage_bytes + p.b_res_bytes + p.n_stg * stg1 + misc;
+  const int max_ctas = num_sms * ctas_per_sm;
+  op.grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
 
   // ---- tensor maps ----
   const int esz = 2;
