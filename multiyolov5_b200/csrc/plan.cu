@@ -67,7 +67,16 @@ struct myolo_plan {
   std::vector<int> conv_ready;    // tensor maps built
   int64_t last_launches = 0;
   bool force_simt = false;
-  cudaEvent_t* ev = nullptr;
+  // CUDA-graph replay of the internal ops (everything that does not touch caller-owned tensors), captured over several
+  // stream "lanes" so that independent branches (C3.cv1 || C3.cv2, seg head || detect head, PSP m8/m16/m32 ...) overlap
+  bool warmed = false, use_graph = true, graph_dirty = true;
+  std::vector<std::vector<int>> deps;
+  std::vector<cudaStream_t> lanes;
+  std::vector<cudaEvent_t> op_ev;
+  cudaEvent_t ev_start = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int n_graph_ops = 0;
 };
 
 static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
@@ -123,6 +132,8 @@ extern "C" int myolo_plan_create(const myolo_op* ops, int n_ops, const myolo_buf
   pl->conv_ready.assign(n_ops, 0);
   const char* fs = getenv("MYOLO_FORCE_SIMT");
   pl->force_simt = fs && fs[0] == '1';
+  const char* ng = getenv("MYOLO_NO_GRAPH");
+  pl->use_graph = !(ng && ng[0] == '1');
   for (int i = 0; i < n_bufs; ++i) {
     const myolo_buf_desc& bd = bufs[i];
     const int64_t bytes = (int64_t)B * bd.h * bd.w * bd.c * (bd.dtype == MYOLO_F16 ? 2 : 4);
@@ -159,6 +170,11 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   }
   if (pl->ws) cudaFree(pl->ws);
   if (pl->d_extra) cudaFree(pl->d_extra);
+  if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
+  if (pl->graph) cudaGraphDestroy(pl->graph);
+  for (auto e : pl->op_ev) cudaEventDestroy(e);
+  if (pl->ev_start) cudaEventDestroy(pl->ev_start);
+  for (auto st : pl->lanes) cudaStreamDestroy(st);
   delete pl;
 }
 
@@ -187,6 +203,7 @@ extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float
     MYOLO_CHECK_CUDA(cudaMalloc(&s.bias, (size_t)co_pad * 4));
     for (size_t i = 0; i < pl->ops.size(); ++i)
       if (pl->ops[i].kind == MYOLO_OP_CONV && pl->ops[i].weight_slot == slot) pl->conv_ready[i] = 0;
+    pl->graph_dirty = true;
   }
   s.co = co;
   s.ci = ci;
@@ -288,15 +305,162 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// dependency analysis + multi-lane graph capture
+// ------------------------------------------------------------------------------------------------
+static bool is_external_op(int kind) {
+  return kind == MYOLO_OP_INPUT_FOCUS || kind == MYOLO_OP_DETECT_DECODE || kind == MYOLO_OP_SEG_UPSAMPLE;
+}
+
+struct Access { int buf, c_lo, c_hi; int64_t lo, hi; bool write; };
+
+static void add_access(const myolo_plan* pl, const myolo_view& v, bool write, std::vector<Access>& out) {
+  if (v.buf < 0) return;
+  const myolo_buf_desc& bd = pl->bufs[v.buf];
+  const int64_t bytes = (int64_t)pl->B * bd.h * bd.w * bd.c * (bd.dtype == MYOLO_F16 ? 2 : 4);
+  out.push_back(Access{v.buf, v.c_off, v.c_off + v.c, bd.offset, bd.offset + bytes, write});
+}
+
+static void op_accesses(const myolo_plan* pl, const myolo_op& op, std::vector<Access>& acc) {
+  acc.clear();
+  add_access(pl, op.in, op.kind == MYOLO_OP_CHANNEL_SCALE, acc);   // channel_scale updates `in` in place
+  if (op.kind == MYOLO_OP_CHANNEL_SCALE) add_access(pl, op.in, false, acc);
+  add_access(pl, op.in2, false, acc);
+  add_access(pl, op.out, true, acc);
+}
+
+static bool conflicts(const Access& a, const Access& b) {
+  if (!(a.write || b.write)) return false;
+  if (a.hi <= b.lo || b.hi <= a.lo) return false;              // disjoint bytes
+  if (a.buf == b.buf) return a.c_lo < b.c_hi && b.c_lo < a.c_hi;  // same buffer: only overlapping channel slices collide
+  return true;                                                  // different buffers sharing workspace bytes (liveness packing)
+}
+
+static void compute_deps(myolo_plan* pl) {
+  const int n = (int)pl->ops.size();
+  pl->deps.assign(n, {});
+  std::vector<std::vector<Access>> acc(n);
+  for (int i = 0; i < n; ++i) op_accesses(pl, pl->ops[i], acc[i]);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < i; ++j) {
+      bool c = false;
+      for (const Access& a : acc[i]) {
+        for (const Access& b : acc[j])
+          if (conflicts(a, b)) { c = true; break; }
+        if (c) break;
+      }
+      if (c) pl->deps[i].push_back(j);
+    }
+}
+
+static int build_graph(myolo_plan* pl) {
+  const int n = (int)pl->ops.size();
+  const int NL = 4;
+  if (pl->deps.empty()) compute_deps(pl);
+  if (pl->lanes.empty()) {
+    pl->lanes.resize(NL);
+    for (auto& st : pl->lanes) MYOLO_CHECK_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    pl->op_ev.resize(n + NL);
+    for (auto& e : pl->op_ev) MYOLO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MYOLO_CHECK_CUDA(cudaEventCreateWithFlags(&pl->ev_start, cudaEventDisableTiming));
+  }
+  if (pl->graph_exec) { cudaGraphExecDestroy(pl->graph_exec); pl->graph_exec = nullptr; }
+  if (pl->graph) { cudaGraphDestroy(pl->graph); pl->graph = nullptr; }
+  std::vector<int> lane_of(n, -1), lane_last(NL, -1);
+  std::vector<char> lane_live(NL, 0);
+  cudaStream_t origin = pl->lanes[0];
+  MYOLO_CHECK_CUDA(cudaStreamBeginCapture(origin, cudaStreamCaptureModeThreadLocal));
+  MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_start, origin));
+  lane_live[0] = 1;
+  int rc = 0, count = 0;
+  for (int i = 0; i < n && !rc; ++i) {
+    if (is_external_op(pl->ops[i].kind)) continue;
+    // lane choice: continue on the lane of the most recent dependency if that lane has not moved on, else least recently used lane
+    int L = -1, latest = -1;
+    for (int d : pl->deps[i])
+      if (lane_of[d] >= 0 && d > latest) latest = d;
+    if (latest >= 0 && lane_last[lane_of[latest]] == latest) L = lane_of[latest];
+    if (L < 0) {
+      L = 0;
+      for (int k = 1; k < NL; ++k)
+        if (lane_last[k] < lane_last[L]) L = k;
+    }
+    cudaStream_t st = pl->lanes[L];
+    if (!lane_live[L]) {
+      if (cudaStreamWaitEvent(st, pl->ev_start, 0) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+      lane_live[L] = 1;
+    }
+    for (int d : pl->deps[i]) {
+      if (lane_of[d] < 0 || lane_of[d] == L) continue;   // external op (ordered by the stream) or same lane (stream order)
+      if (cudaStreamWaitEvent(st, pl->op_ev[d], 0) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+    }
+    if (rc) break;
+    rc = run_op(pl, i, nullptr, 0, nullptr, nullptr, nullptr, 0, nullptr, st);
+    if (rc) break;
+    if (cudaEventRecord(pl->op_ev[i], st) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+    lane_of[i] = L;
+    lane_last[L] = i;
+    ++count;
+  }
+  for (int k = 1; k < NL; ++k) {
+    if (!lane_live[k]) continue;
+    if (cudaEventRecord(pl->op_ev[n + k], pl->lanes[k]) != cudaSuccess || cudaStreamWaitEvent(origin, pl->op_ev[n + k], 0) != cudaSuccess)
+      rc = rc ? rc : MYOLO_E_CUDA;
+  }
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(origin, &g);
+  if (rc || e != cudaSuccess) {
+    if (!rc) { set_error("graph capture failed: %s", cudaGetErrorString(e)); rc = MYOLO_E_CUDA; }
+    else if (e != cudaSuccess) cudaGetLastError();
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  pl->graph = g;
+  MYOLO_CHECK_CUDA(cudaGraphInstantiate(&pl->graph_exec, g, 0));
+  pl->n_graph_ops = count;
+  pl->graph_dirty = false;
+  return 0;
+}
+
 extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
                                   int64_t* seg_argmax, void* stream) {
   MYOLO_REQUIRE(pl && x, "plan_forward: null plan / input");
+  cudaStream_t s = (cudaStream_t)stream;
   const int64_t l0 = g_launch_count;
-  for (size_t i = 0; i < pl->ops.size(); ++i) {
-    int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, (cudaStream_t)stream);
+  if (!pl->warmed || !pl->use_graph) {
+    // first call (lazy tensor-map / attribute setup happens here) or graphs disabled: plain in-order replay
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+      int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
+      if (rc) return rc;
+    }
+    pl->warmed = true;
+    pl->last_launches = g_launch_count - l0;
+    return 0;
+  }
+  if (pl->graph_dirty || !pl->graph_exec) {
+    for (size_t i = 0; i < pl->ops.size(); ++i)   // re-resolve convs whose weights moved (outside capture)
+      if (pl->ops[i].kind == MYOLO_OP_CONV && !pl->conv_ready[i]) {
+        int rc = prepare_conv(pl, (int)i);
+        if (rc) return rc;
+      }
+    int rc = build_graph(pl);
     if (rc) return rc;
   }
-  pl->last_launches = g_launch_count - l0;
+  int n_ext = 0;
+  for (size_t i = 0; i < pl->ops.size(); ++i)     // ops reading the caller's input: before the graph
+    if (pl->ops[i].kind == MYOLO_OP_INPUT_FOCUS) {
+      int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
+      if (rc) return rc;
+      ++n_ext;
+    }
+  MYOLO_CHECK_CUDA(cudaGraphLaunch(pl->graph_exec, s));
+  for (size_t i = 0; i < pl->ops.size(); ++i)     // ops writing caller-owned outputs: after the graph
+    if (pl->ops[i].kind == MYOLO_OP_DETECT_DECODE || pl->ops[i].kind == MYOLO_OP_SEG_UPSAMPLE) {
+      int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
+      if (rc) return rc;
+      ++n_ext;
+    }
+  pl->last_launches = pl->n_graph_ops + n_ext;
   return 0;
 }
 

@@ -443,6 +443,11 @@ def build_plan(model, B: int, H: int, W: int, noalias: bool = False) -> PlanBuil
         outs[i] = y
         # keep saved layers alive until their last consumer: extend liveness at consumption time (done by emit/_touch)
     pb.layer_views = outs
+    # the executor replays all internal ops as one CUDA graph and runs the ops that touch caller-owned tensors afterwards:
+    # whatever those read must stay live until the end of the plan
+    for rec in pb.ops:
+        if rec.kind in (OP_DETECT_DECODE, OP_SEG_UPSAMPLE) and rec.in_ is not None:
+            rec.in_.buf.last = len(pb.ops) + 1
     assign_offsets(pb, noalias=noalias)
     return pb
 
