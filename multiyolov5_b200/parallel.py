@@ -1,0 +1,22 @@
+"""Multi-GPU plumbing of the path.  Inference shards by image: one process per GPU, independent
+replicas, NO data-path collective; torch.distributed (NCCL on GPUs, gloo in CPU tests) is used only for the barrier and the
+max-over-ranks time so that throughput is reported for the whole job."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, world: int, rank: int):
+    """contiguous, balanced shard [lo, hi) of a global batch (sizes differ by at most one)."""
+    base, rem = divmod(n_items, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def aggregate_throughput(images_local: int, ms_local: float, device=None) -> float:
+    """whole-job images/s = sum of images over ranks / max of elapsed time over ranks."""
+    t = torch.tensor([ms_local], dtype=torch.float64, device=device)
+    n = torch.tensor([float(images_local)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    return float(n.item() / (t.item() * 1e-3))

@@ -1,0 +1,111 @@
+"""CPU: host-side logic - state_dict key parity of the shells, planner invariants (liveness packing, concat elimination,
+dependency-safe aliasing), C-ABI library loads and exports every symbol declared in include/myolo.h (no compute calls)."""
+import os
+import re
+
+import pytest
+import torch
+
+from oracle import synth
+
+NETS = {"s_psp": "yolov5s_city_seg.yaml", "m_lab": "yolov5m_city_seg_lab.yaml", "s_bise": "yolov5s_city_seg_bise.yaml",
+        "s_base": "yolov5s_city_seg_base.yaml", "m_psp": "yolov5m_city_seg.yaml"}
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("tag", list(NETS))
+def test_state_dict_keys_match_reference_manifest(tag):
+    from multiyolov5_b200.models.yolo import Model
+    m = Model(NETS[tag])
+    man = synth.load_manifest(tag)
+    sd = m.state_dict()
+    assert [k for k, _, _ in man] == list(sd.keys())
+    assert all(list(sd[k].shape) == s for k, s, _ in man)
+    assert m.stride.tolist() == [8.0, 16.0, 32.0]
+    m.load_state_dict(synth.synth_state_dict(man, synth.load_cfg(NETS[tag]), seed=1))
+    for mod in m.modules():
+        if type(mod) is torch.nn.BatchNorm2d:
+            assert mod.eps == 1e-3 and mod.momentum == 0.03   # reference utils/torch_utils.py:150-152
+
+
+def test_model_surface():
+    from multiyolov5_b200.models.yolo import Detect, Model
+    m = Model("yolov5s_city_seg.yaml")
+    det = m.model[-1]
+    assert isinstance(det, Detect) and (det.nl, det.na, det.nc, det.no) == (3, 3, 10, 15)
+    assert m.save == sorted(m.save[:-1]) + [24] and 24 in m.save
+    assert m.names == [str(i) for i in range(10)]
+    assert m.fuse() is m
+    with pytest.raises(Exception):
+        m.model[1](torch.zeros(1, 32, 8, 8))       # shells hold parameters only: no eager fallback
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 64, 64))
+
+
+@pytest.mark.parametrize("tag,B,H,W", [("s_psp", 16, 512, 1024), ("m_lab", 8, 512, 1024), ("s_bise", 2, 256, 256), ("s_base", 1, 64, 96)])
+def test_planner_invariants(tag, B, H, W):
+    from multiyolov5_b200 import _lib
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.plan import build_plan
+    pb = build_plan(Model(NETS[tag]), B, H, W)
+    n = len(pb.ops)
+    used = [b for b in pb.bufs if b.first >= 0]
+    # liveness packing never overlaps two simultaneously-live buffers, and beats the unpacked footprint
+    for i, a in enumerate(used):
+        assert a.offset % 256 == 0 and a.offset + a.nbytes(B) <= pb.workspace_bytes
+        for b in used[i + 1:]:
+            if not (a.last < b.first or b.last < a.first):
+                assert a.offset + a.nbytes(B) <= b.offset or b.offset + b.nbytes(B) <= a.offset, (a, b)
+    assert pb.workspace_bytes < sum(b.nbytes(B) for b in used)
+    # every conv reads exactly the (16-padded) input channels it was packed for; outputs land in slices (no concat copies)
+    kinds = [o.kind for o in pb.ops]
+    assert kinds.count(_lib.OP_INPUT_FOCUS) == 1 and kinds.count(_lib.OP_DETECT_DECODE) == 3 and kinds.count(_lib.OP_SEG_UPSAMPLE) == 1
+    for o in pb.ops:
+        if o.kind == _lib.OP_CONV:
+            c = pb.slots[o.slot].conv
+            assert o.in_.c == (c.in_channels + 15) // 16 * 16
+            assert o.out.buf.dtype == _lib.F32 or o.out.c == c.out_channels
+    # buffers read by the ops that run after the CUDA graph stay live to the end
+    for o in pb.ops:
+        if o.kind in (_lib.OP_DETECT_DECODE, _lib.OP_SEG_UPSAMPLE):
+            assert o.in_.buf.last > n
+    assert sum(pb.det_rows) == 3 * ((H // 8) * (W // 8) + (H // 16) * (W // 16) + (H // 32) * (W // 32))
+
+
+def test_adaptive_bins_match_torch():
+    from multiyolov5_b200.plan import adaptive_bins
+    import torch.nn.functional as F
+    for n_in, k in [(64, 6), (64, 3), (128, 6), (8, 3), (12, 6), (7, 2), (5, 5)]:
+        x = torch.arange(n_in, dtype=torch.float32).view(1, 1, 1, n_in)
+        ref = F.adaptive_avg_pool2d(x, (1, k)).view(-1)
+        mine = torch.tensor([sum(range(a, b)) / (b - a) for a, b in adaptive_bins(n_in, k)])
+        assert torch.allclose(ref, mine)
+
+
+def test_cabi_library_exports_header_symbols():
+    from multiyolov5_b200 import _lib
+    L = _lib.lib()                       # raises if the .so is missing: build() must have run
+    hdr = open(os.path.join(ROOT, "include", "myolo.h")).read()
+    declared = sorted(set(re.findall(r"\b(myolo_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/myolo.h but not exported"
+    assert sorted(_lib.EXPORTS) == declared
+    assert L.myolo_abi_version() == 1
+    # no device here: entry points must fail loudly, not fall back
+    if not torch.cuda.is_available():
+        import ctypes as C
+        h = C.c_void_p()
+        ops = (_lib.Op * 1)(); bufs = (_lib.BufDesc * 1)()
+        rc = L.myolo_plan_create(ops, 1, bufs, 1, None, 0, 1, 64, 64, 256, 0, C.byref(h))
+        assert rc != 0 and len(L.myolo_last_error()) > 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "multiyolov5_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("use the oracle for CPU numbers", ""), os.path.join(dp, f)

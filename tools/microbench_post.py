@@ -1,0 +1,68 @@
+"""BASELINE.json configs[4]: NMS (10k boxes/img) + seg argmax (19x512x1024) micro-bench, device time via CUDA events.
+Prints one JSON line; compares with torch/torchvision CUDA ops (the reference's own GPU backend) on the same inputs."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from multiyolov5_b200.utils.general import non_max_suppression, seg_argmax  # noqa: E402
+from oracle import restate, synth  # noqa: E402
+
+
+def timeit(fn, n=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3  # us
+
+
+def ref_nms_torch_cuda(pred, conf=0.25, iou=0.45):
+    import torchvision
+    out = []
+    for x in pred:
+        x = x[x[:, 4] > conf]
+        x = x.clone()
+        x[:, 5:] *= x[:, 4:5]
+        box = x[:, :4].clone()
+        box[:, 0] = x[:, 0] - x[:, 2] / 2; box[:, 1] = x[:, 1] - x[:, 3] / 2
+        box[:, 2] = x[:, 0] + x[:, 2] / 2; box[:, 3] = x[:, 1] + x[:, 3] / 2
+        c, j = x[:, 5:].max(1, keepdim=True)
+        x = torch.cat((box, c, j.float()), 1)[c.view(-1) > conf]
+        i = torchvision.ops.nms(x[:, :4] + x[:, 5:6] * 4096, x[:, 4], iou)[:300]
+        out.append(x[i])
+    return out
+
+
+B = 16
+pred_np = synth.synth_predictions(B, 10000, seed=0)
+pred = torch.from_numpy(pred_np).cuda()
+ours = non_max_suppression(pred, 0.25, 0.45)
+ref = restate.non_max_suppression(pred_np[:2], 0.25, 0.45)
+exact = all(np.array_equal(o.cpu().numpy(), r) for o, r in zip(ours[:2], ref))
+t_nms = timeit(lambda: non_max_suppression(pred, 0.25, 0.45, return_padded=True))
+try:
+    t_nms_tv = timeit(lambda: ref_nms_torch_cuda(pred), n=5, warm=2)
+    tv_same = all(torch.equal(a, b) for a, b in zip(ours, ref_nms_torch_cuda(pred)))
+except Exception as e:  # torchvision CUDA ops may be missing
+    t_nms_tv, tv_same = None, str(e)[:80]
+logits = torch.randn(B, 19, 512, 1024, device="cuda")
+lo = torch.randn(B, 19, 64, 128, device="cuda")
+t_arg = timeit(lambda: seg_argmax(logits))
+t_arg_torch = timeit(lambda: logits.max(1)[1])
+t_fused = timeit(lambda: seg_argmax(lo, (512, 1024)))
+t_fused_torch = timeit(lambda: torch.nn.functional.interpolate(lo, (512, 1024), mode="bilinear", align_corners=True).max(1)[1])
+same_arg = bool(torch.equal(seg_argmax(logits), logits.max(1)[1]))
+hbm = logits.numel() * 4 + B * 512 * 1024 * 8
+print(json.dumps({"nms_us_per_img": t_nms / B, "nms_bit_exact_vs_oracle": exact, "nms_torchvision_cuda_us_per_img": None if t_nms_tv is None else t_nms_tv / B,
+                  "nms_equal_torchvision_cuda": tv_same, "argmax_us_per_img": t_arg / B, "argmax_GBps": hbm / (t_arg * 1e-6) / 1e9,
+                  "argmax_torch_cuda_us_per_img": t_arg_torch / B, "argmax_equal_torch": same_arg,
+                  "upsample_argmax_fused_us_per_img": t_fused / B, "upsample_argmax_torch_cuda_us_per_img": t_fused_torch / B, "batch": B}))
