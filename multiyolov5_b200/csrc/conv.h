@@ -30,6 +30,7 @@ struct ConvTcParams {
   int res_ctot;
   float* out_f32;
   int out_f32_ctot;
+  long long* dbg;        // optional timeline buffer [64 tiles][16] of clock64 stamps for CTA 0 (MYOLO_CONV_TIMELINE=1), else null
 };
 
 struct ConvOp {

@@ -51,6 +51,8 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
+#define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+
 struct TileCoord { int b, y0, x0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile, int tiles_per_img) {
   TileCoord t;
@@ -106,11 +108,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool ws_preload = p.ws_mode != 0;
+  if (ws_preload && warp == 0 && lane == 0) {
+    // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
+    mbar_arrive_expect_tx(bres_bar, p.n_chunks * (p.BN * p.kc * 2));
+    for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * (p.BN * p.kc * 2), &tmB, bres_bar, q * p.kc, 0);
+  }
+  // ... and wait here until every predecessor grid has completed and flushed (activations / residual come from them)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int a_sub_bytes = kTileM * p.kc * 2;
   const int b_sub_bytes = p.BN * p.kc * 2;
@@ -118,10 +130,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
-    if (p.ws_mode) {   // whole weight tile once; every tile of this CTA reuses it (n_tiles_n == 1)
-      mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
-      for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
-    }
     int stage = 0;
     uint32_t phase = 0;
     const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
@@ -130,6 +138,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const TileCoord t = decode_tile(p, tile, tiles_per_img);
       // the epilogue reads this slot only after tfull of the same tile, i.e. long after this write (released by the mbarrier chain)
       tile_ring[it & (kTileRing - 1)] = make_int4(t.b, t.y0, t.x0, t.n0);
+      DBG_STAMP(0);
       int tap = 0, cb = 0, q = 0;
       for (int ks = 0; ks < p.n_kstages; ++ks) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -146,6 +155,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
+      DBG_STAMP(1);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (single thread) =====================
@@ -160,14 +170,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t aphase = 0;
     const int kmma = p.kc / 16;
     if (p.ws_mode) mbar_wait(bres_bar, 0);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      DBG_STAMP(2);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
+      DBG_STAMP(3);
       const uint32_t tmem_d = tmem_base + as * kAccStride;
       int q = 0;
       for (int ks = 0; ks < p.n_kstages; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        if (ks == 0) DBG_STAMP(4);
         const int nch = min(p.chunks_per_stage, p.n_chunks - q);
         const uint32_t sa = smem_u32(smem_a + stage * kABytesStage);
         const uint32_t sb = p.ws_mode ? smem_u32(smem_b) + q * b_sub_bytes : smem_u32(smem_b + stage * b_bytes_stage);
@@ -183,6 +197,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
       umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
+      DBG_STAMP(5);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   } else if (warp >= 2) {
@@ -226,8 +241,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+      if (et == 0) DBG_STAMP(6);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
+      if (et == 0) DBG_STAMP(7);
       if (p.residual == nullptr) {
         const int4 ti = tile_ring[it & (kTileRing - 1)];
         t.b = ti.x; t.y0 = ti.y; t.x0 = ti.z; t.n0 = ti.w;
@@ -245,6 +262,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         named_bar_sync(1, kEpiThreads);
       }
+      if (et == 0) DBG_STAMP(8);
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride;
       const uint32_t stg_row = stg_row0 + sbuf * stg_bytes;
 #pragma unroll
@@ -311,6 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp (one arrival per warp)
       tcgen05_fence_before();
       __syncwarp();
+      if (et == 0) DBG_STAMP(9);
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (p.out_mode == 0) {
         fence_proxy_async_smem();
@@ -320,6 +339,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (t.n0 + s * p.ow < p.Co) tma_store_4d(&tmO, smem_o + sbuf * stg_bytes + s * sub_bytes, t.n0 + s * p.ow, t.x0, t.y0, t.b);
           }
           tma_store_commit();
+          DBG_STAMP(10);
         }
         if (p.n_stg == 2) sbuf ^= 1;
       }
@@ -540,6 +560,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   } else {
     op.tmO = op.tmB;
   }
+  p.dbg = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -549,8 +570,23 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
 }
 
 int conv_tc_launch(const ConvOp& op, cudaStream_t stream) {
-  conv_tc_kernel<<<op.grid, kNumThreads, op.smem, stream>>>(op.tmA[0], op.tmA[1], op.tmA[2], op.tmA[3], op.tmB, op.tmO, op.p);
-  MYOLO_LAUNCH_CHECK();
+  static int use_pdl = -1;
+  if (use_pdl < 0) {
+    const char* e = getenv("MYOLO_NO_PDL");
+    use_pdl = (e && e[0] == '1') ? 0 : 1;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(op.grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = op.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  MYOLO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, op.tmA[0], op.tmA[1], op.tmA[2], op.tmA[3], op.tmB, op.tmO, op.p));
+  g_launch_count++;
   return 0;
 }
 

@@ -19,6 +19,21 @@ __device__ __forceinline__ float* vptr_f(const TensorView& v, int b, int y, int 
   return reinterpret_cast<float*>(v.base) + (((size_t)b * v.H + y) * v.W + x) * v.ctot;
 }
 
+
+// Elementwise NHWC kernels use a 3-D grid (x-chunk, y, image): no per-element div/mod chains, only x = i / nv.
+struct RowIdx { int b, y, x, v; bool ok; };
+__device__ __forceinline__ RowIdx row_index(int W, int nv) {
+  RowIdx r;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  r.b = blockIdx.z;
+  r.y = blockIdx.y;
+  r.x = i / nv;
+  r.v = i - r.x * nv;
+  r.ok = r.x < W;
+  return r;
+}
+static inline dim3 row_grid(const TensorView& out, int nv) { return dim3(ceil_div(out.W * nv, 256), out.H, out.B); }
+
 // ------------------------------------------------------------------------------------------------
 // input: NCHW image -> Focus space-to-depth NHWC fp16 (12 channels, zero padded to the view's 16)
 //   channel = g*3 + c with g enumerating (dy,dx) = (0,0),(1,0),(0,1),(1,1)  [reference models/common.py:550]
@@ -71,23 +86,15 @@ int launch_input_focus(const void* x, int x_dtype, int B, int H, int W, const Te
 // nearest x2 (yaml layers 11, 15)
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample_nearest2x_kernel(TensorView in, TensorView out) {
-  const int nv = out.C / 8;
-  const long total = (long)out.B * out.H * out.W * nv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nv);
-    long p = i / nv;
-    const int x = (int)(p % out.W);
-    p /= out.W;
-    const int y = (int)(p % out.H);
-    const int b = (int)(p / out.H);
-    const uint4 val = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, y >> 1, x >> 1)) + v);
-    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = val;
-  }
+  const RowIdx r = row_index(out.W, out.C / 8);
+  if (!r.ok) return;
+  const uint4 val = __ldg(reinterpret_cast<const uint4*>(vptr(in, r.b, r.y >> 1, r.x >> 1)) + r.v);
+  reinterpret_cast<uint4*>(vptr(out, r.b, r.y, r.x))[r.v] = val;
 }
 int launch_upsample_nearest2x(const TensorView& in, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0,
                 "upsample_nearest2x: bad views");
-  upsample_nearest2x_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  upsample_nearest2x_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(in, out);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -179,37 +186,30 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, cons
 }
 
 __global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
-  const int nv = out.C / 8;
-  const long total = (long)out.B * out.H * out.W * nv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nv);
-    long p = i / nv;
-    const int x = (int)(p % out.W);
-    p /= out.W;
-    const int y = (int)(p % out.H);
-    const int b = (int)(p / out.H);
-    const Lerp ly = lerp_axis(y, in.H, out.H), lx = lerp_axis(x, in.W, out.W);
-    const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i0)) + v);
-    const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i1)) + v);
-    const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i0)) + v);
-    const uint4 qd = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i1)) + v);
-    const __half* ha = reinterpret_cast<const __half*>(&qa);
-    const __half* hb = reinterpret_cast<const __half*>(&qb);
-    const __half* hc = reinterpret_cast<const __half*>(&qc);
-    const __half* hd = reinterpret_cast<const __half*>(&qd);
-    uint4 o;
-    __half* ho = reinterpret_cast<__half*>(&o);
+  const RowIdx r = row_index(out.W, out.C / 8);
+  if (!r.ok) return;
+  const int v = r.v, b = r.b;
+  const Lerp ly = lerp_axis(r.y, in.H, out.H), lx = lerp_axis(r.x, in.W, out.W);
+  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i0)) + v);
+  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i1)) + v);
+  const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i0)) + v);
+  const uint4 qd = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i1)) + v);
+  const __half* ha = reinterpret_cast<const __half*>(&qa);
+  const __half* hb = reinterpret_cast<const __half*>(&qb);
+  const __half* hc = reinterpret_cast<const __half*>(&qc);
+  const __half* hd = reinterpret_cast<const __half*>(&qd);
+  uint4 o;
+  __half* ho = reinterpret_cast<__half*>(&o);
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
-    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = o;
-  }
+  for (int k = 0; k < 8; ++k)
+    ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
+  reinterpret_cast<uint4*>(vptr(out, b, r.y, r.x))[v] = o;
 }
 int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0 && in.dtype == MYOLO_F16 &&
                     out.dtype == MYOLO_F16,
                 "bilinear_nhwc: bad views");
-  bilinear_nhwc_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  bilinear_nhwc_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(in, out);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -295,83 +295,59 @@ int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bi
 // FFM: feat = feat*att + feat (in place); att is a (B,1,1,C) map (reference models/common.py:228-229)
 // ------------------------------------------------------------------------------------------------
 __global__ void channel_scale_kernel(TensorView feat, TensorView att) {
-  const int nv = feat.C / 8;
-  const long total = (long)feat.B * feat.H * feat.W * nv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nv);
-    long p = i / nv;
-    const int x = (int)(p % feat.W);
-    p /= feat.W;
-    const int y = (int)(p % feat.H);
-    const int b = (int)(p / feat.H);
-    uint4* ptr = reinterpret_cast<uint4*>(vptr(feat, b, y, x)) + v;
-    uint4 q = *ptr;
-    __half* h = reinterpret_cast<__half*>(&q);
+  const RowIdx r = row_index(feat.W, feat.C / 8);
+  if (!r.ok) return;
+  uint4* ptr = reinterpret_cast<uint4*>(vptr(feat, r.b, r.y, r.x)) + r.v;
+  uint4 q = *ptr;
+  __half* h = reinterpret_cast<__half*>(&q);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float a = att.dtype == MYOLO_F32 ? vptr_f(att, b, 0, 0)[v * 8 + k] : __half2float(vptr(att, b, 0, 0)[v * 8 + k]);
-      const float f = __half2float(h[k]);
-      h[k] = __float2half_rn(fmaf(f, a, f));
-    }
-    *ptr = q;
+  for (int k = 0; k < 8; ++k) {
+    const float a = att.dtype == MYOLO_F32 ? vptr_f(att, r.b, 0, 0)[r.v * 8 + k] : __half2float(vptr(att, r.b, 0, 0)[r.v * 8 + k]);
+    const float f = __half2float(h[k]);
+    h[k] = __float2half_rn(fmaf(f, a, f));
   }
+  *ptr = q;
 }
 int launch_channel_scale(const TensorView& feat, const TensorView& att, cudaStream_t s) {
   MYOLO_REQUIRE(feat.dtype == MYOLO_F16 && feat.C % 8 == 0 && feat.ctot % 8 == 0 && att.C == feat.C && att.H == 1 && att.W == 1,
                 "channel_scale: bad views");
-  channel_scale_kernel<<<grid_for((long)feat.B * feat.H * feat.W * (feat.C / 8), 256), 256, 0, s>>>(feat, att);
+  channel_scale_kernel<<<row_grid(feat, feat.C / 8), 256, 0, s>>>(feat, att);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void add_kernel(TensorView a, TensorView bb, TensorView out) {
-  const int nv = out.C / 8;
-  const long total = (long)out.B * out.H * out.W * nv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nv);
-    long p = i / nv;
-    const int x = (int)(p % out.W);
-    p /= out.W;
-    const int y = (int)(p % out.H);
-    const int b = (int)(p / out.H);
-    const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(a, b, y, x)) + v);
-    const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(bb, b, y, x)) + v);
-    const __half2* ha = reinterpret_cast<const __half2*>(&qa);
-    const __half2* hb = reinterpret_cast<const __half2*>(&qb);
-    uint4 o;
-    __half2* ho = reinterpret_cast<__half2*>(&o);
+  const RowIdx r = row_index(out.W, out.C / 8);
+  if (!r.ok) return;
+  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(a, r.b, r.y, r.x)) + r.v);
+  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(bb, r.b, r.y, r.x)) + r.v);
+  const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+  const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+  uint4 o;
+  __half2* ho = reinterpret_cast<__half2*>(&o);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
-      ho[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
-    }
-    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = o;
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
+    ho[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
   }
+  reinterpret_cast<uint4*>(vptr(out, r.b, r.y, r.x))[r.v] = o;
 }
 int launch_add(const TensorView& a, const TensorView& b, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(a.C == out.C && b.C == out.C && out.C % 8 == 0 && a.H == out.H && b.H == out.H && a.W == out.W && b.W == out.W,
                 "add: bad views");
-  add_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(a, b, out);
+  add_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(a, b, out);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void broadcast_kernel(TensorView in, TensorView out) {
-  const int nv = out.C / 8;
-  const long total = (long)out.B * out.H * out.W * nv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int v = (int)(i % nv);
-    long p = i / nv;
-    const int x = (int)(p % out.W);
-    p /= out.W;
-    const int y = (int)(p % out.H);
-    const int b = (int)(p / out.H);
-    reinterpret_cast<uint4*>(vptr(out, b, y, x))[v] = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, 0, 0)) + v);
-  }
+  const RowIdx r = row_index(out.W, out.C / 8);
+  if (!r.ok) return;
+  reinterpret_cast<uint4*>(vptr(out, r.b, r.y, r.x))[r.v] = __ldg(reinterpret_cast<const uint4*>(vptr(in, r.b, 0, 0)) + r.v);
 }
 int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(in.C == out.C && in.H == 1 && in.W == 1 && in.dtype == MYOLO_F16 && out.C % 8 == 0, "broadcast: bad views");
-  broadcast_kernel<<<grid_for((long)out.B * out.H * out.W * (out.C / 8), 256), 256, 0, s>>>(in, out);
+  broadcast_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(in, out);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -382,34 +358,29 @@ int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s
 // ------------------------------------------------------------------------------------------------
 __global__ void detect_decode_kernel(TensorView in, int na, int no, float stride, const float* __restrict__ anchors, float* raw,
                                      float* z, int z_off, int z_rows) {
-  // one thread per output element: (b, a, y, x, o) with o fastest -> reads, raw writes and z writes are all coalesced
-  const long total = (long)in.B * na * in.H * in.W * no;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int o = (int)(i % no);
-    long p = i / no;
-    const int x = (int)(p % in.W);
-    p /= in.W;
-    const int y = (int)(p % in.H);
-    p /= in.H;
-    const int a = (int)(p % na);
-    const int b = (int)(p / na);
-    const float v = vptr_f(in, b, y, x)[a * no + o];
-    if (raw) raw[i] = v;
-    float sg = 1.0f / (1.0f + expf(-v));
-    if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
-    else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
-    else if (o == 2 || o == 3) {
-      const float t = sg * 2.0f;
-      sg = t * t * anchors[a * 2 + (o - 2)];
-    }
-    z[((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no + o] = sg;
+  // grid = (chunks of W*no, H, B*na); o fastest -> reads, raw writes and z writes are all contiguous per warp
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = i / no, o = i - x * no;
+  if (x >= in.W) return;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / na, a = blockIdx.z - b * na;
+  const float v = vptr_f(in, b, y, x)[a * no + o];
+  const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
+  if (raw) raw[row * no + o] = v;
+  float sg = 1.0f / (1.0f + expf(-v));
+  if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
+  else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
+  else if (o == 2 || o == 3) {
+    const float t = sg * 2.0f;
+    sg = t * t * anchors[a * 2 + (o - 2)];
   }
+  z[((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no + o] = sg;
 }
 int launch_detect_decode(const TensorView& in, int na, int no, float stride, const float* d_anchors, float* raw, float* z,
                          int z_row_offset, int z_rows_total, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.C >= na * no, "detect_decode: bad view");
-  detect_decode_kernel<<<grid_for((long)in.B * na * in.H * in.W * no, 256), 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z,
-                                                                                   z_row_offset, z_rows_total);
+  detect_decode_kernel<<<dim3(ceil_div(in.W * no, 256), in.H, in.B * na), 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset,
+                                                                                     z_rows_total);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -475,15 +446,30 @@ __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int nc
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int bi[4] = {0, 0, 0, 0};
   const bool full = (x0 + 3 < W) && (W % 4 == 0);
+  // up-scaling by >= 4: the 4 outputs of a thread touch at most 3 neighbouring source columns -> 6 shared loads per class
+  const int base = lx[0].i0;
+  const bool narrow = (lx[3].i1 - base) <= 2;
+  const int b1 = min(base + 1, ncol - 1), b2 = min(base + 2, ncol - 1);
   for (int c = 0; c < ncls; ++c) {
     const float* r0 = s0 + c * pitch;
     const float* r1 = s1 + c * pitch;
     float v[4];
+    if (narrow) {
+      const float a0 = r0[base], a1 = r0[b1], a2 = r0[b2], c0v = r1[base], c1v = r1[b1], c2v = r1[b2];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
-      if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
+      for (int j = 0; j < 4; ++j) {
+        const int o0 = lx[j].i0 - base, o1 = lx[j].i1 - base;
+        const float ta = o0 == 0 ? a0 : (o0 == 1 ? a1 : a2), tb = o1 == 0 ? a0 : (o1 == 1 ? a1 : a2);
+        const float tc = o0 == 0 ? c0v : (o0 == 1 ? c1v : c2v), td = o1 == 0 ? c0v : (o1 == 1 ? c1v : c2v);
+        v[j] = bilerp(ta, tb, tc, td, ly, lx[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
     }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
     if (seg) {
       TOut* o = seg + (((size_t)b * ncls + c) * H + y) * W + x0;
       if (full) Pack4<TOut>::store(o, v[0], v[1], v[2], v[3]);

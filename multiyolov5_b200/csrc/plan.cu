@@ -536,7 +536,32 @@ extern "C" int myolo_conv_bn_silu(const void* x, int B, int H, int W, int ci, co
       rc = conv_simt_launch(c, s);
     } else {
       rc = conv_tc_prepare(c, sms);
+      const char* tl = getenv("MYOLO_CONV_TIMELINE");
+      long long* dbg = nullptr;
+      if (!rc && tl && tl[0] == '1') {
+        cudaMalloc(&dbg, 64 * 16 * sizeof(long long));
+        cudaMemset(dbg, 0, 64 * 16 * sizeof(long long));
+        c.p.dbg = dbg;
+        conv_tc_launch(c, s);   // warm (tensor maps, L2)
+        cudaStreamSynchronize(s);
+        cudaMemset(dbg, 0, 64 * 16 * sizeof(long long));
+      }
       if (!rc) rc = conv_tc_launch(c, s);
+      if (dbg) {
+        cudaStreamSynchronize(s);
+        std::vector<long long> h(64 * 16);
+        cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+        const long long t0 = h[0];
+        printf("# conv timeline CTA0: grid %d tiles %d BN %d kc %d kstages %d S %d ws %d n_stg %d smem %d\n", c.grid, c.p.total_tiles, c.p.BN, c.p.kc,
+               c.p.n_kstages, c.p.num_stages, c.p.ws_mode, c.p.n_stg, c.smem);
+        printf("# it: P_begin P_issued | M_begin M_tempty M_full0 M_commit | E_begin E_tfull E_stgready E_done E_store   (cycles since first stamp)\n");
+        for (int it = 0; it < 64 && h[it * 16] != 0; ++it) {
+          printf("%2d:", it);
+          for (int k = 0; k <= 10; ++k) printf(" %7lld", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+          printf("\n");
+        }
+        cudaFree(dbg);
+      }
     }
   }
   cudaError_t e = cudaStreamSynchronize(s);
