@@ -9,6 +9,8 @@ struct ConvTcParams {
   int tw, th;            // output tile = tw x th pixels, tw*th == 128 (UMMA M)
   int tiles_x, tiles_y;  // per image
   int n_tiles_n, total_tiles;
+  int G;                 // M tiles per accumulator round (G*BN <= 128 TMEM columns); G > 1 only when n_tiles_n == 1
+  int total_rounds;
   int BN;                // UMMA N (multiple of 16, <= 128)
   int Co;                // real output channels
   int kc;                // channels per K chunk: 16 / 32 / 64  (swizzle 32B / 64B / 128B)
@@ -18,19 +20,27 @@ struct ConvTcParams {
   int tap_map[9], tap_dx[9], tap_dy[9];
   int act;
   int num_stages;
-  int out_mode;          // 0: fp16 NHWC slice via TMA store, 1: fp32 NHWC direct stores
-  int ow;                // output sub-box width in channels (16/32/64)
-  int n_sub;             // sub-boxes per N tile
-  int log2_tw, log2_ow;
+  int a_stage_bytes, b_stage_bytes;
+  int out_mode;          // 0: fp16 NHWC slice via per-warp TMA stores, 1: fp32 NHWC direct stores
+  int log2_tw;
   int ws_mode;           // weights-stationary: the whole [BN x K] weight tile stays resident in shared memory
   int b_res_bytes;       // bytes of the resident weight region (ws_mode)
-  int n_stg;             // TMA-store staging buffers (1 or 2)
+  // epilogue: 8 warps = 4 TMEM lane quarters x 2 "halves"; a half takes every other tile (G >= 2) or half of the columns (G == 1)
+  int ep_cols;           // columns handled by one warp per tile
+  int ep_split_cols;     // 1: halves split the columns, 0: halves split the tiles (or half 1 idles when the chunk count is odd)
+  int ow, log2_ow;       // per-warp TMA-store sub-box width in channels (16/32/64)
+  int n_sub;             // sub-boxes per warp per tile
+  int n_stg;             // staging buffers per warp (1 or 2)
+  int rows_w, rows_h;    // the 32 tile rows of a warp as an rows_w x rows_h pixel rectangle (store box)
+  // strip mode (3x3 stride 1, th == 1): one TMA strip of tw + 2*dil pixels per (ky, channel block) serves the three kx taps
+  int strip;             // 0 off; 1: shifted descriptors with base_offset 0; 2: base_offset = (addr >> 7) & 7
+  int dil;
   const float* bias;
   const __half* residual;  // nullable; base of the residual slice (image 0, pixel 0, channel 0 of the slice)
   int res_ctot;
   float* out_f32;
   int out_f32_ctot;
-  long long* dbg;        // optional timeline buffer [64 tiles][16] of clock64 stamps for CTA 0 (MYOLO_CONV_TIMELINE=1), else null
+  long long* dbg;        // optional clock64 timeline buffer (MYOLO_CONV_TIMELINE=1), else null
 };
 
 struct ConvOp {

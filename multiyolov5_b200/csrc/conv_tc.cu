@@ -6,12 +6,16 @@
 //   same rectangle shifted by (dx,dy): one 4-D TMA box load {kc channels, tw, th, 1} with hardware zero fill at the
 //   image border (that is the conv padding).  Stride-2 convs use four "parity" tensor maps (even/odd rows x cols)
 //   so that the stride-2 gather is again a dense box.  No im2col buffer ever exists in HBM.
-// * K loop  = taps x (Ci/kc) chunks, grouped 64 K-elements per pipeline stage; both operands are K-major with the
-//   32/64/128-byte TMA swizzle that the UMMA shared-memory descriptor names.
-// * warp roles (192 threads): warp0 = TMA producer (1 thread), warp1 = MMA issuer (1 thread; the warp owns TMEM
-//   alloc/dealloc), warps 2..5 = epilogue (TMEM -> regs -> bias/SiLU/residual -> fp16 -> swizzled smem -> TMA store
-//   into the channel slice of the consumer's concat buffer).  Two TMEM accumulator stages overlap epilogue and MMA.
-// * persistent: grid = min(#tiles, #SMs), static round-robin tile schedule.
+// * strip mode (3x3, stride 1, full-row tiles): ONE strip of tw+2*dil pixels per (filter row, channel block) feeds the
+//   three kx taps through row-shifted UMMA descriptors -> 3x less L2->SM traffic than nine tap boxes.
+// * K loop  = taps x (Ci/kc) chunks, 64 K-elements per pipeline stage; operands are K-major with the 32/64/128-byte
+//   TMA swizzle named in the UMMA shared-memory descriptor.  Small weight tiles stay resident in smem (weights-stationary).
+// * warp roles (320 threads): warp0 = TMA producer (1 thread), warp1 = MMA issuer (1 thread; the warp owns TMEM
+//   alloc/dealloc), warps 2..9 = epilogue.  An accumulator "round" holds G M-tiles (G*BN <= 128 TMEM columns, two rounds
+//   double-buffered).  Every epilogue warp is autonomous: it owns 32 TMEM lanes (= 32 pixels), converts its share of the
+//   round (TMEM -> regs -> bias/SiLU/residual -> fp16 -> its private swizzled staging) and issues its OWN TMA store into the
+//   channel slice of the consumer's concat buffer - no CTA-wide barrier anywhere in the steady state.
+// * persistent grid, two CTAs per SM, programmatic dependent launch (prologue overlaps the previous kernel's tail).
 //
 // Reference semantics: Conv.fuseforward (reference models/common.py:45-46) with BN folded as in
 // utils/torch_utils.py:182-202; Bottleneck shortcut add (models/common.py:105).
@@ -21,17 +25,21 @@ namespace myolo {
 
 static constexpr int kTileM = 128;
 static constexpr int kKStage = 64;        // K elements per pipeline stage
-static constexpr int kABytesStage = kTileM * kKStage * 2;  // 16 KB
-static constexpr int kEpiWarps = 8;       // two warps per TMEM lane quarter, each takes every other 16-column chunk
-static constexpr int kEpiThreads = kEpiWarps * 32;
-static constexpr int kNumThreads = 64 + kEpiThreads;
-static constexpr int kTmemCols = 256;     // 2 accumulator stages x 128 columns
+static constexpr int kEpiWarps = 8;
+static constexpr int kNumThreads = 64 + kEpiWarps * 32;
+static constexpr int kTmemCols = 256;     // 2 accumulator rounds x 128 columns
 static constexpr int kAccStride = 128;
 static constexpr int kMaxWsBytes = 40 * 1024;
 static constexpr int kSmemPerCta = 112 * 1024;   // two CTAs per SM: their epilogues / TMA latencies overlap
-static constexpr int kTileRing = 16;
+static constexpr int kTileRing = 32;
 
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
+#ifdef MYOLO_TIMELINE
+#define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(slot) do { } while (0)
+#endif
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc, uint32_t base_offset) {
   // K-major canonical layout, rows of kc*2 bytes, 8-row groups (PTX ISA "matrix descriptor", sm_100 version=1)
   const uint32_t sw_bytes = kc * 2;
   const uint64_t layout = sw_bytes == 128 ? 2ull : (sw_bytes == 64 ? 4ull : 6ull);
@@ -41,6 +49,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc) {
   d |= (uint64_t)1 << 16;                    // leading byte offset (ignored for swizzled K-major), bits [16,30)
   d |= sbo << 32;                            // stride byte offset, bits [32,46)
   d |= (uint64_t)1 << 46;                    // descriptor version (Blackwell)
+  d |= (uint64_t)(base_offset & 7) << 49;    // matrix base offset (start not aligned to the swizzle repeat)
   d |= layout << 61;                         // swizzle mode
   return d;
 }
@@ -50,8 +59,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-
-#define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
 
 struct TileCoord { int b, y0, x0, n0; };
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile, int tiles_per_img) {
@@ -75,23 +82,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_stages;
-  const int b_bytes_stage = p.ws_mode ? 0 : ((p.BN * kKStage * 2 + 1023) & ~1023);  // stage stride keeps the 1024-byte atom alignment
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem_a + S * kABytesStage;                 // per-stage B, or the resident weight tile (ws_mode)
-  uint8_t* smem_o = smem_b + (p.ws_mode ? p.b_res_bytes : S * b_bytes_stage);
-  const int sub_bytes = kTileM * p.ow * 2;
-  const int stg_bytes = p.n_sub * sub_bytes;                   // one staging buffer; two are allocated (double buffered)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + p.n_stg * stg_bytes);
+  uint8_t* smem_b = smem_a + S * p.a_stage_bytes;                 // per-stage B ring, or the resident weight tile (ws_mode)
+  uint8_t* smem_o = smem_b + (p.ws_mode ? p.b_res_bytes : S * p.b_stage_bytes);
+  const int sub_bytes = 32 * p.ow * 2;                            // one warp sub-box: 32 rows x ow channels
+  const int stg_warp_bytes = p.n_sub * sub_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + kEpiWarps * p.n_stg * stg_warp_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
   uint64_t* bres_bar = bars + 2 * S + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
-  int4* tile_ring = reinterpret_cast<int4*>(bars + 2 * S + 6);   // {b, y0, x0, n0} per tile iteration, written by the producer
+  int4* tile_ring = reinterpret_cast<int4*>(bars + 2 * S + 6);    // {b, y0, x0, n0} per tile, written by the producer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int b_sub_bytes = p.BN * p.kc * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -115,47 +122,65 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const bool ws_preload = p.ws_mode != 0;
-  if (ws_preload && warp == 0 && lane == 0) {
+  if (p.ws_mode && warp == 0 && lane == 0) {
     // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
-    mbar_arrive_expect_tx(bres_bar, p.n_chunks * (p.BN * p.kc * 2));
-    for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * (p.BN * p.kc * 2), &tmB, bres_bar, q * p.kc, 0);
+    mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
+    for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
   }
   // ... and wait here until every predecessor grid has completed and flushed (activations / residual come from them)
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int a_sub_bytes = kTileM * p.kc * 2;
-  const int b_sub_bytes = p.BN * p.kc * 2;
+  const int row_bytes = p.kc * 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
     int stage = 0;
     uint32_t phase = 0;
-    const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const TileCoord t = decode_tile(p, tile, tiles_per_img);
-      // the epilogue reads this slot only after tfull of the same tile, i.e. long after this write (released by the mbarrier chain)
-      tile_ring[it & (kTileRing - 1)] = make_int4(t.b, t.y0, t.x0, t.n0);
-      DBG_STAMP(0);
-      int tap = 0, cb = 0, q = 0;
-      for (int ks = 0; ks < p.n_kstages; ++ks) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-        mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
-        uint8_t* sa = smem_a + stage * kABytesStage;
-        uint8_t* sb = smem_b + stage * b_bytes_stage;
-        for (int j = 0; j < nch; ++j, ++q) {
-          const int mi = p.tap_map[tap];
-          const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-          tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.b);
-          if (!p.ws_mode) tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t.n0);
-          if (++cb == p.cblocks) { cb = 0; ++tap; }
+    for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
+      for (int g = 0; g < p.G; ++g) {
+        const int tile = round * p.G + g;
+        if (tile >= p.total_tiles) break;
+        const TileCoord t = decode_tile(p, tile, tiles_per_img);
+        // the epilogue reads this slot only after tfull of the same round, i.e. long after this write (mbarrier chain)
+        tile_ring[it & (kTileRing - 1)] = make_int4(t.b, t.y0, t.x0, t.n0);
+        DBG_STAMP(0);
+        if (p.strip) {
+          for (int ky = 0; ky < 3; ++ky)
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2 * p.dil) * row_bytes + (p.ws_mode ? 0 : 3 * b_sub_bytes));
+              tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - p.dil, t.y0 + (ky - 1) * p.dil, t.b);
+              if (!p.ws_mode)
+                for (int kx = 0; kx < 3; ++kx)
+                  tma_load_2d(smem_b + stage * p.b_stage_bytes + kx * b_sub_bytes, &tmB, &full_bar[stage],
+                              ((ky * 3 + kx) * p.cblocks + cb) * p.kc, t.n0);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          int tap = 0, cb = 0, q = 0;
+          const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
+          for (int ks = 0; ks < p.n_kstages; ++ks) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+            mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
+            uint8_t* sa = smem_a + stage * p.a_stage_bytes;
+            uint8_t* sb = smem_b + stage * p.b_stage_bytes;
+            for (int j = 0; j < nch; ++j, ++q) {
+              const int mi = p.tap_map[tap];
+              const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+              tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.b);
+              if (!p.ws_mode) tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t.n0);
+              if (++cb == p.cblocks) { cb = 0; ++tap; }
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
         }
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        DBG_STAMP(1);
+        ++it;
       }
-      DBG_STAMP(1);
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (single thread) =====================
@@ -171,181 +196,193 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int kmma = p.kc / 16;
     if (p.ws_mode) mbar_wait(bres_bar, 0);
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
       DBG_STAMP(2);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       DBG_STAMP(3);
-      const uint32_t tmem_d = tmem_base + as * kAccStride;
-      int q = 0;
-      for (int ks = 0; ks < p.n_kstages; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        tcgen05_fence_after();
-        if (ks == 0) DBG_STAMP(4);
-        const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-        const uint32_t sa = smem_u32(smem_a + stage * kABytesStage);
-        const uint32_t sb = p.ws_mode ? smem_u32(smem_b) + q * b_sub_bytes : smem_u32(smem_b + stage * b_bytes_stage);
-        for (int j = 0; j < nch; ++j, ++q) {
-          const uint64_t da = make_smem_desc(sa + j * a_sub_bytes, p.kc);
-          const uint64_t db = make_smem_desc(sb + j * b_sub_bytes, p.kc);
-          for (int k = 0; k < kmma; ++k) {
-            // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
-            umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((ks | j | k) != 0));
+      for (int g = 0; g < p.G; ++g) {
+        if (round * p.G + g >= p.total_tiles) break;
+        const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
+        if (p.strip) {
+          uint32_t first = 0;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint32_t a_addr = sa + kx * p.dil * row_bytes;   // same strip, shifted by kx*dil pixels
+                const uint32_t b_addr = p.ws_mode ? smem_u32(smem_b) + ((ky * 3 + kx) * p.cblocks + cb) * b_sub_bytes
+                                                  : smem_u32(smem_b + stage * p.b_stage_bytes) + kx * b_sub_bytes;
+                const uint64_t da = make_smem_desc(a_addr, p.kc, p.strip == 2 ? (a_addr >> 7) : 0u);
+                const uint64_t db = make_smem_desc(b_addr, p.kc, 0u);
+                for (int k = 0; k < kmma; ++k) {
+                  umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+                  first = 1;
+                }
+              }
+              umma_commit(&empty_bar[stage]);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          int q = 0;
+          for (int ks = 0; ks < p.n_kstages; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            if (ks == 0) DBG_STAMP(4);
+            const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+            const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
+            const uint32_t sb = p.ws_mode ? smem_u32(smem_b) + q * b_sub_bytes : smem_u32(smem_b + stage * p.b_stage_bytes);
+            for (int j = 0; j < nch; ++j, ++q) {
+              const uint64_t da = make_smem_desc(sa + j * a_sub_bytes, p.kc, 0u);
+              const uint64_t db = make_smem_desc(sb + j * b_sub_bytes, p.kc, 0u);
+              for (int k = 0; k < kmma; ++k) {
+                // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+                umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((ks | j | k) != 0));
+              }
+            }
+            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+            if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
-      umma_commit(&tfull_bar[as]);       // accumulator complete -> epilogue
+      umma_commit(&tfull_bar[as]);       // all accumulators of the round complete -> epilogue
       DBG_STAMP(5);
       if (++as == 2) { as = 0; aphase ^= 1; }
+      ++it;
     }
   } else if (warp >= 2) {
-    // ===================== epilogue: 8 warps; warp w reads TMEM lanes 32*(w%4).., chunks c = half, half+2, ... =====================
-    const int quarter = warp & 3;
+    // ===================== epilogue: 8 autonomous warps =====================
+    const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
-    const int row = quarter * 32 + lane;   // tile row == pixel index inside the tw x th rectangle
-    const int et = threadIdx.x - 64;       // 0..255
+    const int row = quarter * 32 + lane;           // tile row == pixel index inside the tw x th rectangle
     const int ry = row >> p.log2_tw, rx = row & (p.tw - 1);
-    const int nchunk16 = p.BN >> 4;
-    const int units_log2 = p.log2_ow - 3;  // 16-byte units per staging row: 8 / 4 / 2
-    const int sw = units_log2 == 3 ? (row & 7) : (units_log2 == 2 ? ((row >> 1) & 3) : ((row >> 2) & 1));
-    const uint32_t stg_row0 = smem_u32(smem_o) + row * (p.ow * 2);
+    const int wy = (quarter * 32) >> p.log2_tw, wx = (quarter * 32) & (p.tw - 1);   // origin of this warp's 32-row rectangle
+    const int units_log2 = p.log2_ow - 3;          // 16-byte units per staging row: 8 / 4 / 2
+    const int sw = units_log2 == 3 ? (lane & 7) : (units_log2 == 2 ? ((lane >> 1) & 3) : ((lane >> 2) & 1));
+    const uint32_t stg0 = smem_u32(smem_o) + (warp - 2) * p.n_stg * stg_warp_bytes + lane * (p.ow * 2);
+    const int nchunks_w = p.ep_cols >> 4;
+    const int c_lo = p.ep_split_cols ? half * nchunks_w : 0;
+    const int g_first = p.ep_split_cols ? 0 : half;
+    const int g_step = p.ep_split_cols ? 1 : 2;
+    const bool idle_half = (!p.ep_split_cols && p.G == 1 && half == 1);
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;
+    int ring_base = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      TileCoord t;
-      if (p.residual != nullptr) {
-        t = decode_tile(p, tile, tiles_per_img);   // needed before the wait (residual prefetch); only 7 of ~80 layers
-      }
-      int py = 0, px = 0;
-      bool pix_ok = false;
-      size_t pix = 0;
-      // residual rows do not depend on the accumulator: fetch them before waiting for the MMA
-      uint4 rres[4][2];
-      if (p.residual != nullptr) {
-        py = t.y0 + ry; px = t.x0 + rx;
-        pix_ok = (py < p.Ho) && (px < p.Wo);
-        pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = half + 2 * i;
-          if (c < nchunk16 && pix_ok) {
-            const __half* rp = p.residual + pix * p.res_ctot + t.n0 + c * 16;
-            rres[i][0] = (t.n0 + c * 16 < p.Co) ? __ldg(reinterpret_cast<const uint4*>(rp)) : make_uint4(0, 0, 0, 0);
-            rres[i][1] = (t.n0 + c * 16 + 8 < p.Co) ? __ldg(reinterpret_cast<const uint4*>(rp + 8)) : make_uint4(0, 0, 0, 0);
-          } else {
-            rres[i][0] = rres[i][1] = make_uint4(0, 0, 0, 0);
-          }
-        }
-      }
-      if (et == 0) DBG_STAMP(6);
+    for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
+      const int n_valid = min(p.G, p.total_tiles - round * p.G);
+      if (warp == 2 && lane == 0) DBG_STAMP(6);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
-      if (et == 0) DBG_STAMP(7);
-      if (p.residual == nullptr) {
-        const int4 ti = tile_ring[it & (kTileRing - 1)];
-        t.b = ti.x; t.y0 = ti.y; t.x0 = ti.z; t.n0 = ti.w;
-        if (p.out_mode != 0) {
-          py = t.y0 + ry; px = t.x0 + rx;
-          pix_ok = (py < p.Ho) && (px < p.Wo);
-          pix = ((size_t)t.b * p.Ho + py) * p.Wo + px;
-        }
-      }
-      if (p.out_mode == 0) {
-        // the staging buffer about to be overwritten was handed to the TMA store engine n_stg tiles ago: it must have been read
-        if (et == 0) {
-          if (p.n_stg == 2) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        named_bar_sync(1, kEpiThreads);
-      }
-      if (et == 0) DBG_STAMP(8);
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride;
-      const uint32_t stg_row = stg_row0 + sbuf * stg_bytes;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = half + 2 * i;
-        if (c < nchunk16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(taddr + c * 16, v);
-          const int nb = t.n0 + c * 16;
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
-          const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
-          tmem_ld_wait();
-          float f[16];
-          f[0] = __uint_as_float(v[0]) + b0.x;   f[1] = __uint_as_float(v[1]) + b0.y;
-          f[2] = __uint_as_float(v[2]) + b0.z;   f[3] = __uint_as_float(v[3]) + b0.w;
-          f[4] = __uint_as_float(v[4]) + b1.x;   f[5] = __uint_as_float(v[5]) + b1.y;
-          f[6] = __uint_as_float(v[6]) + b1.z;   f[7] = __uint_as_float(v[7]) + b1.w;
-          f[8] = __uint_as_float(v[8]) + b2.x;   f[9] = __uint_as_float(v[9]) + b2.y;
-          f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
-          f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y;
-          f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
-          if (p.act == MYOLO_ACT_SILU) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
-          } else if (p.act == MYOLO_ACT_SIGMOID) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
+      if (warp == 2 && lane == 0) DBG_STAMP(7);
+      if (!idle_half) {
+        for (int g = g_first; g < n_valid; g += g_step) {
+          const int4 ti = tile_ring[(ring_base + g) & (kTileRing - 1)];
+          const int tb = ti.x, ty0 = ti.y, tx0 = ti.z, tn0 = ti.w;
+          const int py = ty0 + ry, px = tx0 + rx;
+          const bool pix_ok = (py < p.Ho) && (px < p.Wo);
+          const size_t pix = ((size_t)tb * p.Ho + py) * p.Wo + px;
+          if (p.out_mode == 0) {
+            // my staging buffer was handed to the TMA engine n_stg stores ago: it must have been read by now
+            if (lane == 0) {
+              if (p.n_stg == 2) tma_store_wait_read<1>();
+              else tma_store_wait_read<0>();
+            }
+            __syncwarp();
           }
-          if (p.residual != nullptr) {
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride + g * p.BN;
+          const uint32_t stg = stg0 + sbuf * stg_warp_bytes;
+          for (int ci = 0; ci < nchunks_w; ++ci) {
+            const int c = c_lo + ci;
+            const int nb = tn0 + c * 16;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(taddr + c * 16, v);
+            uint4 rr0 = make_uint4(0, 0, 0, 0), rr1 = make_uint4(0, 0, 0, 0);
+            if (p.residual != nullptr && pix_ok) {
+              const __half* rp = p.residual + pix * p.res_ctot + nb;
+              if (nb < p.Co) rr0 = __ldg(reinterpret_cast<const uint4*>(rp));
+              if (nb + 8 < p.Co) rr1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+            }
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
+            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
+            tmem_ld_wait();
+            float f[16];
+            f[0] = __uint_as_float(v[0]) + b0.x;   f[1] = __uint_as_float(v[1]) + b0.y;
+            f[2] = __uint_as_float(v[2]) + b0.z;   f[3] = __uint_as_float(v[3]) + b0.w;
+            f[4] = __uint_as_float(v[4]) + b1.x;   f[5] = __uint_as_float(v[5]) + b1.y;
+            f[6] = __uint_as_float(v[6]) + b1.z;   f[7] = __uint_as_float(v[7]) + b1.w;
+            f[8] = __uint_as_float(v[8]) + b2.x;   f[9] = __uint_as_float(v[9]) + b2.y;
+            f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
+            f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y;
+            f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
+            if (p.act == MYOLO_ACT_SILU) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const __half2* r2 = reinterpret_cast<const __half2*>(&rres[i][h]);
+              for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
+            } else if (p.act == MYOLO_ACT_SIGMOID) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
+            }
+            if (p.residual != nullptr) {
+              const __half2* r0 = reinterpret_cast<const __half2*>(&rr0);
+              const __half2* r1 = reinterpret_cast<const __half2*>(&rr1);
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float2 rf = __half22float2(r2[e]);
-                f[h * 8 + 2 * e] += rf.x;
-                f[h * 8 + 2 * e + 1] += rf.y;
+                const float2 fa = __half22float2(r0[e]), fb = __half22float2(r1[e]);
+                f[2 * e] += fa.x;     f[2 * e + 1] += fa.y;
+                f[8 + 2 * e] += fb.x; f[8 + 2 * e + 1] += fb.y;
+              }
+            }
+            if (p.out_mode == 0) {
+              const int ch = ci << 4;
+              const int sub = ch >> p.log2_ow;
+              const int u0 = (ch & (p.ow - 1)) >> 3;
+              const uint32_t srow = stg + sub * sub_bytes;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                uint4 o;
+                __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(f[h * 8 + 2 * e], f[h * 8 + 2 * e + 1]);
+                sts128(srow + (((u0 + h) ^ sw) << 4), o);
+              }
+            } else if (pix_ok) {
+              float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (nb + 4 * e < p.out_f32_ctot)
+                  *reinterpret_cast<float4*>(op + 4 * e) = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
               }
             }
           }
           if (p.out_mode == 0) {
-            const int ch = c << 4;
-            const int sub = ch >> p.log2_ow;
-            const int u0 = (ch & (p.ow - 1)) >> 3;
-            const uint32_t srow = stg_row + sub * sub_bytes;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              uint4 o;
-              __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(f[h * 8 + 2 * e], f[h * 8 + 2 * e + 1]);
-              sts128(srow + (((u0 + h) ^ sw) << 4), o);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int nbase = tn0 + c_lo * 16;
+              for (int s = 0; s < p.n_sub; ++s) {
+                if (nbase + s * p.ow < p.Co)
+                  tma_store_4d(&tmO, smem_o + (warp - 2) * p.n_stg * stg_warp_bytes + sbuf * stg_warp_bytes + s * sub_bytes,
+                               nbase + s * p.ow, tx0 + wx, ty0 + wy, tb);
+              }
+              tma_store_commit();
             }
-          } else if (pix_ok) {
-            float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (nb + 4 * e < p.out_f32_ctot)
-                *reinterpret_cast<float4*>(op + 4 * e) = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
-            }
+            if (p.n_stg == 2) sbuf ^= 1;
           }
         }
       }
-      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp (one arrival per warp)
+      // all TMEM reads of this warp for the round are complete (every tcgen05.ld was waited on): release the accumulators
       tcgen05_fence_before();
       __syncwarp();
-      if (et == 0) DBG_STAMP(9);
+      if (warp == 2 && lane == 0) DBG_STAMP(9);
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
-      if (p.out_mode == 0) {
-        fence_proxy_async_smem();
-        named_bar_sync(1, kEpiThreads);
-        if (et == 0) {
-          for (int s = 0; s < p.n_sub; ++s) {
-            if (t.n0 + s * p.ow < p.Co) tma_store_4d(&tmO, smem_o + sbuf * stg_bytes + s * sub_bytes, t.n0 + s * p.ow, t.x0, t.y0, t.b);
-          }
-          tma_store_commit();
-          DBG_STAMP(10);
-        }
-        if (p.n_stg == 2) sbuf ^= 1;
-      }
       if (++as == 2) { as = 0; aphase ^= 1; }
+      ring_base += n_valid;
+      ++it;
     }
-    if (p.out_mode == 0 && et == 0) tma_store_wait_all();
+    if (p.out_mode == 0 && lane == 0) tma_store_wait_all();
   }
 
   tcgen05_fence_before();
@@ -441,19 +478,20 @@ bool conv_tc_eligible(const ConvOp& op) {
 int conv_tc_prepare(ConvOp& op, int num_sms) {
   ConvTcParams& p = op.p;
   memset(&p, 0, sizeof(p));
+  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
   const int Ho = op.out.H, Wo = op.out.W;
   p.B = op.in.B;
   p.Ho = Ho;
   p.Wo = Wo;
   choose_tile(Wo, Ho, &p.tw, &p.th);
+  p.log2_tw = ilog2(p.tw);
   p.tiles_x = ceil_div(Wo, p.tw);
   p.tiles_y = ceil_div(Ho, p.th);
   p.Co = op.Co;
-  // N tile: whole Co if it fits in 128, else 128 (Co_pad was sized as a multiple of BN by the planner)
+  // N tile: whole Co if it fits in 128, else the largest multiple of 16 <= 128 dividing Co16 (Co_pad sized by the caller)
   const int co16 = (int)align_up(op.Co, 16);
   p.BN = co16 <= 128 ? co16 : 128;
   if (co16 > 128 && co16 % 128 != 0) {
-    // e.g. Co = 192, 384: use the largest multiple of 16 <= 128 that divides co16
     for (int bn = 128; bn >= 16; bn -= 16)
       if (co16 % bn == 0) { p.BN = bn; break; }
   }
@@ -467,15 +505,14 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   p.chunks_per_stage = kKStage / p.kc;
   p.n_kstages = ceil_div(p.n_chunks, p.chunks_per_stage);
   p.act = op.act;
+  p.dil = op.dil;
   p.bias = op.bias;
   p.residual = op.has_res ? reinterpret_cast<const __half*>(op.res.base) : nullptr;
   p.res_ctot = op.has_res ? op.res.ctot : 0;
   p.out_mode = op.out.dtype == MYOLO_F16 ? 0 : 1;
   p.out_f32 = p.out_mode ? reinterpret_cast<float*>(op.out.base) : nullptr;
   p.out_f32_ctot = p.out_mode ? op.out.ctot : 0;
-  // sub-box width must divide BN: a wider last sub-box would spill garbage into the next N tile's channels
-  p.ow = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
-  p.n_sub = p.out_mode == 0 ? ceil_div(p.BN, p.ow) : 0;
+  p.dbg = nullptr;
   for (int t = 0; t < p.taps; ++t) {
     const int ky = op.k == 3 ? t / 3 : 1, kx = op.k == 3 ? t % 3 : 1;
     if (op.stride == 1) {
@@ -489,16 +526,47 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
       p.tap_dx[t] = (kx == 0) ? -1 : 0;
     }
   }
-  auto ilog2 = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
-  p.log2_tw = ilog2(p.tw);
+  const int max_ctas = 2 * num_sms;
+  // strip mode: 3x3 stride-1 conv on full-row tiles; row-shifted descriptors need the 128-byte swizzle atom (kc == 64)
+  static int strip_env = -1;
+  if (strip_env < 0) {
+    const char* e = getenv("MYOLO_STRIP");
+    strip_env = e ? atoi(e) : 0;
+  }
+  p.strip = (strip_env > 0 && op.k == 3 && op.stride == 1 && p.th == 1 && p.kc == 64 && p.tw + 2 * op.dil <= 256) ? strip_env : 0;
+  // accumulator rounds: G tiles share one TMEM stage when the layer is big enough to keep every CTA busy
+  p.G = 1;
+  if (p.n_tiles_n == 1) {
+    for (int g = 4; g >= 2; g >>= 1)
+      if (g * p.BN <= kAccStride && p.total_tiles / g >= 2 * max_ctas) { p.G = g; break; }
+  }
+  p.total_rounds = ceil_div(p.total_tiles, p.G);
+  // epilogue work split between the two warps of a TMEM lane quarter
+  const int nchunk16 = p.BN / 16;
+  if (p.G >= 2) { p.ep_split_cols = 0; p.ep_cols = p.BN; }
+  else if (nchunk16 % 2 == 0) { p.ep_split_cols = 1; p.ep_cols = p.BN / 2; }
+  else { p.ep_split_cols = 0; p.ep_cols = p.BN; }
+  p.ow = p.ep_cols % 64 == 0 ? 64 : (p.ep_cols % 32 == 0 ? 32 : 16);
   p.log2_ow = ilog2(p.ow);
+  p.n_sub = p.out_mode == 0 ? p.ep_cols / p.ow : 0;
+  p.rows_w = p.tw < 32 ? p.tw : 32;
+  p.rows_h = 32 / p.rows_w;
   // weights-stationary mode: one N tile and the whole [BN x K] weight tile fits next to the A ring
   const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
   p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= kMaxWsBytes) ? 1 : 0;
   p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
-  // shared memory budget: aim for two co-resident CTAs per SM (<= 112 KB each); fall back to one big CTA otherwise
-  const int stage_bytes = kABytesStage + (p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024));
-  const int stg1 = p.n_sub * kTileM * p.ow * 2;
+  // stage geometry
+  if (p.strip) {
+    p.a_stage_bytes = (int)align_up((p.tw + 2 * op.dil) * p.kc * 2, 1024);
+    p.b_stage_bytes = p.ws_mode ? 0 : (int)align_up(3 * p.BN * p.kc * 2, 1024);
+    p.n_kstages = 3 * p.cblocks;
+  } else {
+    p.a_stage_bytes = kTileM * kKStage * 2;
+    p.b_stage_bytes = p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024);
+  }
+  // shared memory budget: two co-resident CTAs per SM (<= 112 KB each); fall back to one big CTA otherwise
+  const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
+  const int stg1 = kEpiWarps * p.n_sub * 32 * p.ow * 2;     // one staging buffer for each of the 8 warps
   const int misc = 2048 /*barriers + tile ring*/ + 1024 /*alignment slack*/;
   int ctas_per_sm = 2;
   p.n_stg = p.out_mode == 0 ? 2 : 0;
@@ -516,8 +584,8 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");
   p.num_stages = S;
   op.smem = S * stage_bytes + p.b_res_bytes + p.n_stg * stg1 + misc;
-  const int max_ctas = num_sms * ctas_per_sm;
-  op.grid = p.total_tiles < max_ctas ? p.total_tiles : max_ctas;
+  const int cta_cap = num_sms * ctas_per_sm;
+  op.grid = p.total_rounds < cta_cap ? p.total_rounds : cta_cap;
 
   // ---- tensor maps ----
   const int esz = 2;
@@ -526,7 +594,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   if (op.stride == 1) {
     uint64_t dims[4] = {(uint64_t)in.C, (uint64_t)in.W, (uint64_t)in.H, (uint64_t)in.B};
     uint64_t str[3] = {(uint64_t)in.ctot * esz, (uint64_t)in.W * in.ctot * esz, (uint64_t)in.H * in.W * in.ctot * esz};
-    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    uint32_t box[4] = {(uint32_t)p.kc, (uint32_t)(p.strip ? p.tw + 2 * op.dil : p.tw), (uint32_t)p.th, 1};
     int rc = encode_map(&op.tmA[0], 4, in.base, dims, str, box, sw);
     if (rc) return rc;
     op.tmA[1] = op.tmA[2] = op.tmA[3] = op.tmA[0];
@@ -554,13 +622,12 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     const TensorView& o = op.out;
     uint64_t dims[4] = {(uint64_t)o.C, (uint64_t)o.W, (uint64_t)o.H, (uint64_t)o.B};
     uint64_t str[3] = {(uint64_t)o.ctot * esz, (uint64_t)o.W * o.ctot * esz, (uint64_t)o.H * o.W * o.ctot * esz};
-    uint32_t box[4] = {(uint32_t)p.ow, (uint32_t)p.tw, (uint32_t)p.th, 1};
+    uint32_t box[4] = {(uint32_t)p.ow, (uint32_t)p.rows_w, (uint32_t)p.rows_h, 1};
     int rc = encode_map(&op.tmO, 4, o.base, dims, str, box, p.ow * 2);
     if (rc) return rc;
   } else {
     op.tmO = op.tmB;
   }
-  p.dbg = nullptr;
   static bool attr_set = false;
   if (!attr_set) {
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

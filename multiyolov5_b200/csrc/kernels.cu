@@ -446,30 +446,15 @@ __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int nc
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int bi[4] = {0, 0, 0, 0};
   const bool full = (x0 + 3 < W) && (W % 4 == 0);
-  // up-scaling by >= 4: the 4 outputs of a thread touch at most 3 neighbouring source columns -> 6 shared loads per class
-  const int base = lx[0].i0;
-  const bool narrow = (lx[3].i1 - base) <= 2;
-  const int b1 = min(base + 1, ncol - 1), b2 = min(base + 2, ncol - 1);
   for (int c = 0; c < ncls; ++c) {
     const float* r0 = s0 + c * pitch;
     const float* r1 = s1 + c * pitch;
     float v[4];
-    if (narrow) {
-      const float a0 = r0[base], a1 = r0[b1], a2 = r0[b2], c0v = r1[base], c1v = r1[b1], c2v = r1[b2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o0 = lx[j].i0 - base, o1 = lx[j].i1 - base;
-        const float ta = o0 == 0 ? a0 : (o0 == 1 ? a1 : a2), tb = o1 == 0 ? a0 : (o1 == 1 ? a1 : a2);
-        const float tc = o0 == 0 ? c0v : (o0 == 1 ? c1v : c2v), td = o1 == 0 ? c0v : (o1 == 1 ? c1v : c2v);
-        v[j] = bilerp(ta, tb, tc, td, ly, lx[j]);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+      v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
       if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
+    }
     if (seg) {
       TOut* o = seg + (((size_t)b * ncls + c) * H + y) * W + x0;
       if (full) Pack4<TOut>::store(o, v[0], v[1], v[2], v[3]);

@@ -28,6 +28,12 @@ SHAPES = [
     (1, 32, 32, 48, 96, 3, 1, 1, False),      # kc=16 with Ci=48, Co=96
     (1, 16, 32, 192, 192, 1, 1, 1, False),    # Co=192 -> BN=96 x 2
     (3, 8, 16, 64, 64, 1, 1, 1, False),       # exactly one tile per image
+    (2, 16, 128, 64, 64, 3, 1, 1, False),     # full-row tiles (tw=128): strip mode when MYOLO_STRIP is set
+    (1, 12, 128, 64, 64, 3, 1, 2, True),      # strip + dilation 2 + residual
+    (1, 8, 128, 64, 64, 3, 1, 3, False),      # strip + dilation 3
+    (1, 8, 256, 256, 128, 3, 1, 1, False),    # strip, 4 channel blocks, W=256 (2 tiles per row), streamed weights
+    (16, 64, 256, 32, 32, 1, 1, 1, False),    # many tiles, BN=32 -> 4 tiles per accumulator round
+    (8, 64, 128, 64, 64, 1, 1, 1, True),      # 2 tiles per round + residual
 ]
 
 
