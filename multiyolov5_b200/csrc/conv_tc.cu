@@ -527,13 +527,13 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     }
   }
   const int max_ctas = 2 * num_sms;
-  // strip mode: 3x3 stride-1 conv on full-row tiles; row-shifted descriptors need the 128-byte swizzle atom (kc == 64)
+  // strip mode: 3x3 stride-1 conv on full-row tiles (any swizzle width: rows are shifted by whole pixels)
   static int strip_env = -1;
   if (strip_env < 0) {
     const char* e = getenv("MYOLO_STRIP");
-    strip_env = e ? atoi(e) : 0;
+    strip_env = e ? atoi(e) : 1;   // 1: shifted start addresses (the UMMA swizzle is a function of the absolute smem address - verified on B200)
   }
-  p.strip = (strip_env > 0 && op.k == 3 && op.stride == 1 && p.th == 1 && p.kc == 64 && p.tw + 2 * op.dil <= 256) ? strip_env : 0;
+  p.strip = (strip_env > 0 && op.k == 3 && op.stride == 1 && p.th == 1 && p.tw + 2 * op.dil <= 256) ? strip_env : 0;
   // accumulator rounds: G tiles share one TMEM stage when the layer is big enough to keep every CTA busy
   p.G = 1;
   if (p.n_tiles_n == 1) {

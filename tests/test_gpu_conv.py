@@ -32,6 +32,9 @@ SHAPES = [
     (1, 12, 128, 64, 64, 3, 1, 2, True),      # strip + dilation 2 + residual
     (1, 8, 128, 64, 64, 3, 1, 3, False),      # strip + dilation 3
     (1, 8, 256, 256, 128, 3, 1, 1, False),    # strip, 4 channel blocks, W=256 (2 tiles per row), streamed weights
+    (2, 16, 256, 32, 32, 3, 1, 1, True),      # strip with 64-byte rows (kc=32) + residual (L2 bottleneck class)
+    (2, 16, 512, 16, 32, 3, 1, 1, False),     # strip with 32-byte rows (kc=16): Focus conv class
+    (1, 8, 128, 48, 96, 3, 1, 2, False),      # strip, kc=16 x 3 channel blocks, dilation 2
     (16, 64, 256, 32, 32, 1, 1, 1, False),    # many tiles, BN=32 -> 4 tiles per accumulator round
     (8, 64, 128, 64, 64, 1, 1, 1, True),      # 2 tiles per round + residual
 ]
