@@ -177,7 +177,18 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-__device__ __forceinline__ float silu_f(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+// SiLU with ONE transcendental (MUFU.EX2) per element: the reciprocal of 1+e^-v runs on the FMA pipe (integer seed + 3 Newton
+// steps, ~4e-8 relative) so the conv epilogues are not bound by the 16-lane/clk SFU (two MUFU ops per output would be).
+__device__ __forceinline__ float silu_f(float v) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  const float d = 1.0f + fminf(e, 1e30f);
+  float r = __int_as_float(0x7EF311C7 - __float_as_int(d));
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  r = r * fmaf(-d, r, 2.0f);
+  return v * r;
+}
 __device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   return act == MYOLO_ACT_SILU ? silu_f(v) : (act == MYOLO_ACT_SIGMOID ? sigmoid_f(v) : v);

@@ -34,6 +34,8 @@ struct ConvTcParams {
   int rows_w, rows_h;    // the 32 tile rows of a warp as an rows_w x rows_h pixel rectangle (store box)
   // strip mode (3x3 stride 1, th == 1): one TMA strip of tw + 2*dil pixels per (ky, channel block) serves the three kx taps
   int strip;             // 0 off; 1: shifted descriptors with base_offset 0; 2: base_offset = (addr >> 7) & 7
+  int vround;            // strip + weights-stationary + dil 1: the G tiles of a round are vertically adjacent rows sharing G+2 strips
+  int rounds_per_img;
   int dil;
   const float* bias;
   const __half* residual;  // nullable; base of the residual slice (image 0, pixel 0, channel 0 of the slice)

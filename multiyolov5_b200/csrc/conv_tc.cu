@@ -140,6 +140,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     uint32_t phase = 0;
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
+      if (p.vround) {
+        // G vertically adjacent full-row tiles: rows y0 .. y0+n_valid-1 need input rows y0-1 .. y0+n_valid -> n_valid+2 strips
+        const int b = round / p.rounds_per_img;
+        const int r = round - b * p.rounds_per_img;
+        const int tyg = r / p.tiles_x;
+        const int x0 = (r - tyg * p.tiles_x) * p.tw, y0 = tyg * p.G;
+        const int n_valid = min(p.G, p.Ho - y0);
+        for (int g = 0; g < n_valid; ++g) tile_ring[(it + g) & (kTileRing - 1)] = make_int4(b, y0 + g, x0, 0);
+        it += n_valid;
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int s = 0; s < n_valid + 2; ++s) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2) * row_bytes);
+            tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, x0 - 1, y0 - 1 + s, b);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        continue;
+      }
       for (int g = 0; g < p.G; ++g) {
         const int tile = round * p.G + g;
         if (tile >= p.total_tiles) break;
@@ -201,6 +219,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       DBG_STAMP(3);
+      if (p.vround) {
+        const int r = round % p.rounds_per_img;
+        const int n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
+        for (int cb = 0; cb < p.cblocks; ++cb)
+          for (int s = 0; s < n_valid + 2; ++s) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
+            // strip s (input row y0-1+s) is filter row ky = s-g of output row g
+            for (int g = max(0, s - 2); g <= min(n_valid - 1, s); ++g) {
+              const int ky = s - g;
+              const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
+              for (int kx = 0; kx < 3; ++kx) {
+                const uint64_t da = make_smem_desc(sa + kx * row_bytes, p.kc, 0u);
+                const uint64_t db = make_smem_desc(smem_u32(smem_b) + ((ky * 3 + kx) * p.cblocks + cb) * b_sub_bytes, p.kc, 0u);
+                for (int k = 0; k < kmma; ++k)
+                  umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((cb | ky | kx | k) != 0));
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+      } else
       for (int g = 0; g < p.G; ++g) {
         if (round * p.G + g >= p.total_tiles) break;
         const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
@@ -273,7 +314,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int ring_base = 0;
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
-      const int n_valid = min(p.G, p.total_tiles - round * p.G);
+      int n_valid;
+      if (p.vround) {
+        const int r = round % p.rounds_per_img;
+        n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
+      } else {
+        n_valid = min(p.G, p.total_tiles - round * p.G);
+      }
       if (warp == 2 && lane == 0) DBG_STAMP(6);
       mbar_wait(&tfull_bar[as], aphase);
       tcgen05_fence_after();
@@ -541,6 +588,26 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
       if (g * p.BN <= kAccStride && p.total_tiles / g >= 2 * max_ctas) { p.G = g; break; }
   }
   p.total_rounds = ceil_div(p.total_tiles, p.G);
+  // weights-stationary mode: one N tile and the whole [BN x K] weight tile fits next to the A ring
+  static int ws_kb = -1;
+  if (ws_kb < 0) {
+    const char* e = getenv("MYOLO_WS_KB");
+    ws_kb = e ? atoi(e) : kMaxWsBytes / 1024;
+  }
+  const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
+  p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= ws_kb * 1024) ? 1 : 0;
+  p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
+  // vertical rounds: the G tiles of a round are G consecutive image rows, so G+2 strips feed 3*G (row, filter-row) pairs
+  static int vr_env = -1;
+  if (vr_env < 0) {
+    const char* e = getenv("MYOLO_VROUND");
+    vr_env = e ? atoi(e) : 1;
+  }
+  p.vround = (vr_env && p.strip && p.ws_mode && op.dil == 1 && p.G >= 2) ? 1 : 0;
+  if (p.vround) {
+    p.rounds_per_img = p.tiles_x * ceil_div(Ho, p.G);
+    p.total_rounds = p.B * p.rounds_per_img;
+  }
   // epilogue work split between the two warps of a TMEM lane quarter
   const int nchunk16 = p.BN / 16;
   if (p.G >= 2) { p.ep_split_cols = 0; p.ep_cols = p.BN; }
@@ -551,10 +618,6 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   p.n_sub = p.out_mode == 0 ? p.ep_cols / p.ow : 0;
   p.rows_w = p.tw < 32 ? p.tw : 32;
   p.rows_h = 32 / p.rows_w;
-  // weights-stationary mode: one N tile and the whole [BN x K] weight tile fits next to the A ring
-  const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
-  p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= kMaxWsBytes) ? 1 : 0;
-  p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
   // stage geometry
   if (p.strip) {
     p.a_stage_bytes = (int)align_up((p.tw + 2 * op.dil) * p.kc * 2, 1024);

@@ -35,6 +35,9 @@ SHAPES = [
     (2, 16, 256, 32, 32, 3, 1, 1, True),      # strip with 64-byte rows (kc=32) + residual (L2 bottleneck class)
     (2, 16, 512, 16, 32, 3, 1, 1, False),     # strip with 32-byte rows (kc=16): Focus conv class
     (1, 8, 128, 48, 96, 3, 1, 2, False),      # strip, kc=16 x 3 channel blocks, dilation 2
+    (16, 64, 256, 32, 32, 3, 1, 1, True),     # vertical rounds: 2 rows share 4 strips (weights-stationary) + residual
+    (16, 128, 256, 16, 32, 3, 1, 1, False),   # vertical rounds: 4 rows share 6 strips, 32-byte rows (Focus conv at scale)
+    (8, 37, 512, 32, 32, 3, 1, 1, False),     # vertical rounds with a ragged last row group (Ho = 37)
     (16, 64, 256, 32, 32, 1, 1, 1, False),    # many tiles, BN=32 -> 4 tiles per accumulator round
     (8, 64, 128, 64, 64, 1, 1, 1, True),      # 2 tiles per round + residual
 ]
