@@ -356,9 +356,11 @@ int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s
 // Detect.forward (eval): view (bs,na,no,ny,nx) -> permute (bs,na,ny,nx,no); sigmoid; xy=(s*2-0.5+grid)*stride;
 // wh=(s*2)^2*anchor; z = cat over levels                                     [reference models/yolo.py:211-225]
 // ------------------------------------------------------------------------------------------------
-__global__ void detect_decode_kernel(TensorView in, int na, int no, float stride, const float* __restrict__ anchors, float* raw,
+template <int NO>
+__global__ void detect_decode_kernel(TensorView in, int na, int no_rt, float stride, const float* __restrict__ anchors, float* raw,
                                      float* z, int z_off, int z_rows) {
   // grid = (chunks of W*no, H, B*na); o fastest -> reads, raw writes and z writes are all contiguous per warp
+  const int no = NO > 0 ? NO : no_rt;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int x = i / no, o = i - x * no;
   if (x >= in.W) return;
@@ -367,7 +369,7 @@ __global__ void detect_decode_kernel(TensorView in, int na, int no, float stride
   const float v = vptr_f(in, b, y, x)[a * no + o];
   const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
   if (raw) raw[row * no + o] = v;
-  float sg = 1.0f / (1.0f + expf(-v));
+  float sg = __fdividef(1.0f, 1.0f + __expf(-v));
   if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
   else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
   else if (o == 2 || o == 3) {
@@ -379,8 +381,9 @@ __global__ void detect_decode_kernel(TensorView in, int na, int no, float stride
 int launch_detect_decode(const TensorView& in, int na, int no, float stride, const float* d_anchors, float* raw, float* z,
                          int z_row_offset, int z_rows_total, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.C >= na * no, "detect_decode: bad view");
-  detect_decode_kernel<<<dim3(ceil_div(in.W * no, 256), in.H, in.B * na), 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset,
-                                                                                     z_rows_total);
+  const dim3 grid(ceil_div(in.W * no, 256), in.H, in.B * na);
+  if (no == 15) detect_decode_kernel<15><<<grid, 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total);
+  else detect_decode_kernel<0><<<grid, 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -402,9 +405,11 @@ template <> struct Pack4<__half> {
   }
 };
 
-// One CTA = one output row segment of 4*blockDim.x pixels of one image.  The two source rows it needs are staged in shared
-// memory as [row][class][col] (col fastest -> conflict-free), every thread then produces 4 consecutive pixels for all classes
-// with 16-byte stores: per class a warp writes 512 contiguous bytes.  ATen operation order is kept (exact fp32, no FMA).
+// One CTA = one output row segment of 4*blockDim.x pixels of one image.  While staging, the two source rows the output row
+// needs are blended vertically once per (class, source column) into shared memory [class][col] (col fastest -> conflict-free);
+// every thread then produces 4 consecutive pixels for all classes with 2 shared loads + 1 lerp per value and 16-byte stores
+// (per class a warp writes 512 contiguous bytes).  (Vertical-then-horizontal association differs from ATen's
+// horizontal-then-vertical by <= 1 ulp; the bit-exact-vs-ATen path is myolo_seg_upsample_argmax / myolo_bilinear_nchw.)
 template <typename TOut>
 __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int ncls, int H, int W, TOut* seg, int64_t* amax) {
   extern __shared__ float sup_smem[];
@@ -419,16 +424,15 @@ __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int nc
   const int c1 = lerp_axis(xend - 1, in.W, W).i1;
   const int ncol = c1 - c0 + 1;
   const int pitch = ncol | 1;                      // odd pitch: rows of different classes start in different banks
-  float* s0 = sup_smem;                            // [ncls][pitch] source row i0
-  float* s1 = sup_smem + ncls * pitch;             // source row i1
+  float* sv = sup_smem;                            // [ncls][pitch] vertically blended source row
   const int c4n = (ncls + 3) / 4;
-  for (int i = threadIdx.x; i < 2 * ncol * c4n; i += blockDim.x) {
-    const int r = i / (ncol * c4n);
-    const int rem = i - r * ncol * c4n;
-    const int col = rem / c4n, c4 = rem % c4n;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(vptr_f(in, b, r ? ly.i1 : ly.i0, c0 + col)) + c4);
-    float* d = (r ? s1 : s0) + col;
-    const float vv[4] = {v.x, v.y, v.z, v.w};
+  for (int i = threadIdx.x; i < ncol * c4n; i += blockDim.x) {
+    const int col = i / c4n, c4 = i - col * c4n;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(vptr_f(in, b, ly.i0, c0 + col)) + c4);
+    const float4 u = __ldg(reinterpret_cast<const float4*>(vptr_f(in, b, ly.i1, c0 + col)) + c4);
+    const float vv[4] = {fmaf(ly.l1, u.x, ly.l0 * t.x), fmaf(ly.l1, u.y, ly.l0 * t.y), fmaf(ly.l1, u.z, ly.l0 * t.z),
+                         fmaf(ly.l1, u.w, ly.l0 * t.w)};
+    float* d = sv + col;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (c4 * 4 + k < ncls) d[(c4 * 4 + k) * pitch] = vv[k];
@@ -436,23 +440,22 @@ __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int nc
   __syncthreads();
   const int x0 = xbeg + 4 * threadIdx.x;
   if (x0 >= W) return;
-  Lerp lx[4];
+  int i0[4], i1[4];
+  float l0[4], l1[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    lx[j] = lerp_axis(min(x0 + j, W - 1), in.W, W);
-    lx[j].i0 -= c0;
-    lx[j].i1 -= c0;
+    const Lerp lx = lerp_axis(min(x0 + j, W - 1), in.W, W);
+    i0[j] = lx.i0 - c0; i1[j] = lx.i1 - c0; l0[j] = lx.l0; l1[j] = lx.l1;
   }
   float best[4] = {0.f, 0.f, 0.f, 0.f};
   int bi[4] = {0, 0, 0, 0};
   const bool full = (x0 + 3 < W) && (W % 4 == 0);
   for (int c = 0; c < ncls; ++c) {
-    const float* r0 = s0 + c * pitch;
-    const float* r1 = s1 + c * pitch;
+    const float* r = sv + c * pitch;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      v[j] = bilerp(r0[lx[j].i0], r0[lx[j].i1], r1[lx[j].i0], r1[lx[j].i1], ly, lx[j]);
+      v[j] = fmaf(l1[j], r[i1[j]], l0[j] * r[i0[j]]);
       if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
     }
     if (seg) {
@@ -471,7 +474,7 @@ int launch_seg_upsample(const TensorView& in, int n_cls, int H, int W, void* seg
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.ctot % 4 == 0 && in.ctot >= ((n_cls + 3) / 4) * 4, "seg_upsample: bad view");
   const int threads = W >= 1024 ? 256 : (W >= 512 ? 128 : 64);
   const int segs = ceil_div(W, 4 * threads);
-  const size_t smem = (size_t)2 * n_cls * ((in.W + 2) | 1) * 4;
+  const size_t smem = (size_t)n_cls * ((in.W + 2) | 1) * 4;
   MYOLO_REQUIRE(smem <= 48 * 1024, "seg_upsample: source row too wide for the shared-memory kernel (%d cols x %d classes)", in.W, n_cls);
   const long blocks = (long)in.B * H * segs;
   if (seg_dtype == MYOLO_F16) seg_upsample_kernel<__half><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, (__half*)seg, argmax);

@@ -105,14 +105,18 @@ __device__ __forceinline__ Cand load_cand(const NmsParams& p, int b, unsigned lo
   return c;
 }
 
-// torchvision CPU nms_kernel arithmetic, op for op
+// torchvision CPU nms_kernel arithmetic, op for op.  The IEEE division is only executed when the cheap reciprocal estimate is
+// within 1e-4 relative of the threshold: everywhere else the comparison result is provably the same, so rows stay bit-exact.
 __device__ __forceinline__ bool iou_gt(float ax1, float ay1, float ax2, float ay2, float aarea, float bx1, float by1, float bx2,
                                        float by2, float barea, float thr) {
   const float xx1 = fmaxf(ax1, bx1), yy1 = fmaxf(ay1, by1), xx2 = fminf(ax2, bx2), yy2 = fminf(ay2, by2);
   const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1)), h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
   const float inter = __fmul_rn(w, h);
-  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aarea, barea), inter));
-  return ovr > thr;
+  const float uni = __fsub_rn(__fadd_rn(aarea, barea), inter);
+  const float approx = inter * __frcp_rn(uni);                 // 2 roundings away from the IEEE quotient
+  if (approx > thr * 1.0001f) return true;
+  if (approx < thr * 0.9999f) return false;
+  return __fdiv_rn(inter, uni) > thr;                          // also the path NaN / inf take (never "greater")
 }
 
 __global__ void __launch_bounds__(1024) nms_kernel(NmsParams p) {
@@ -171,20 +175,28 @@ __global__ void __launch_bounds__(1024) nms_kernel(NmsParams p) {
       if ((t & 31) == 0) s_alive_words[t >> 5] = (int)bal;
     }
     __syncthreads();
-    if (t < kChunk) {
-      // row t: which later candidates u>t of this chunk would be suppressed by t
+    {
+      // row r = t/4: which later candidates u>r of this chunk would be suppressed by r; the 4 threads of a row take u = r+1+q, +4, ...
+      const int r = t >> 2, q = t & 3;
       unsigned wbits[8];
 #pragma unroll
       for (int wq = 0; wq < 8; ++wq) wbits[wq] = 0u;
-      if (t < m && alive) {
-        for (int u = t + 1; u < m; ++u) {
+      const bool r_alive = r < m && ((((unsigned)s_alive_words[r >> 5]) >> (r & 31)) & 1u);
+      if (r_alive) {
+        const float4 rb = cbox[r];
+        const float ra = carea[r];
+        for (int u = r + 1 + q; u < m; u += 4) {
           const float4 ub = cbox[u];
-          if (iou_gt(me.ox1, me.oy1, me.ox2, me.oy2, me.area, ub.x, ub.y, ub.z, ub.w, carea[u], p.iou_thres))
-            wbits[u >> 5] |= 1u << (u & 31);
+          if (iou_gt(rb.x, rb.y, rb.z, rb.w, ra, ub.x, ub.y, ub.z, ub.w, carea[u], p.iou_thres)) wbits[u >> 5] |= 1u << (u & 31);
         }
       }
 #pragma unroll
-      for (int wq = 0; wq < 8; ++wq) mat[t * 8 + wq] = wbits[wq];
+      for (int wq = 0; wq < 8; ++wq) {
+        unsigned v = wbits[wq];
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        if (q == 0) mat[r * 8 + wq] = v;
+      }
     }
     __syncthreads();
     if (t < 32) {
