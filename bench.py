@@ -212,14 +212,14 @@ def main():
         return det, cnt, cls
 
     def timed(fn, steps, sampler=None, finalize=None):
-        for i in range(warmup):
+        if sampler:
+            sampler.start()     # samples cover warm-up + timed region (identical load)
+        for i in range(warmup + (40 if sampler else 0)):
             fn(i)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        if sampler:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = None
         e0.record()
@@ -287,7 +287,14 @@ def main():
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
         ach = flops / (conv_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+        traffic = None
+        try:   # dram__bytes_read+write per conv_tc launch from the committed `ncu --set full` capture of the same step (profiles/)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tj.get("cfg") == tag and tj.get("batch") == B:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "kernel": "conv_tc_kernel (all fused Conv+BN+SiLU launches of one forward)", "launches": n_conv, "avg_launch_ms": conv_ms / n_conv,
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
                 "conv_share_of_forward": conv_ms / float(per_op.sum())}

@@ -43,8 +43,18 @@ def full(rep, out):
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none (one row per captured launch, stream order)\n\n")
         f.write("| # | " + " | ".join(idx) + " |\n|---|" + "---:|" * len(idx) + "\n")
+        tot_rd = tot_wr = 0.0
+        nrows = 0
         for n, r in enumerate(rows[2:]):
             f.write(f"| {n} | " + " | ".join(r[i] for i in idx.values()) + " |\n")
+            try:
+                tot_rd += float(r[idx["dram_rd_MB"]]); tot_wr += float(r[idx["dram_wr_MB"]]); nrows += 1
+            except Exception:
+                pass
+    if nrows:
+        import json
+        json.dump({"cfg": "s_psp", "batch": 16, "launches": nrows, "dram_bytes_per_launch": (tot_rd + tot_wr) * 1e6 / nrows,
+                   "dram_read_MB_total": tot_rd, "dram_write_MB_total": tot_wr, "source": rep}, open("profiles/ncu_traffic.json", "w"))
 
 
 if __name__ == "__main__":
