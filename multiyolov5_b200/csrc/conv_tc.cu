@@ -54,6 +54,12 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc, uint3
   return d;
 }
 
+// The MMA issuer is ONE thread: every instruction it executes sits on the critical path of the tensor pipe.  Descriptors are
+// therefore split into a kernel-constant high word and a low word that is a plain 32-bit add away from a per-stage base.
+__device__ __forceinline__ uint32_t desc_hi(int kc) { return (uint32_t)(make_smem_desc(0u, kc, 0u) >> 32); }
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_join(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -212,6 +218,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int as = 0;
     uint32_t aphase = 0;
     const int kmma = p.kc / 16;
+    const uint32_t dhi = desc_hi(p.kc);
+    const uint32_t lb_res = desc_lo(smem_u32(smem_b));
+    const int bsub16 = b_sub_bytes >> 4, asub16 = a_sub_bytes >> 4, row16 = row_bytes >> 4;
     if (p.ws_mode) mbar_wait(bres_bar, 0);
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
@@ -226,16 +235,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int s = 0; s < n_valid + 2; ++s) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
+            const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
             // strip s (input row y0-1+s) is filter row ky = s-g of output row g
             for (int g = max(0, s - 2); g <= min(n_valid - 1, s); ++g) {
               const int ky = s - g;
               const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
+              uint32_t lb = lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16);
+#pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
-                const uint64_t da = make_smem_desc(sa + kx * row_bytes, p.kc, 0u);
-                const uint64_t db = make_smem_desc(smem_u32(smem_b) + ((ky * 3 + kx) * p.cblocks + cb) * b_sub_bytes, p.kc, 0u);
+                const uint32_t lak = la + kx * row16;
                 for (int k = 0; k < kmma; ++k)
-                  umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((cb | ky | kx | k) != 0));
+                  umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((cb | ky | kx | k) != 0));
+                lb += (uint32_t)(p.cblocks * bsub16);
               }
             }
             umma_commit(&empty_bar[stage]);
@@ -251,17 +262,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int cb = 0; cb < p.cblocks; ++cb) {
               mbar_wait(&full_bar[stage], phase);
               tcgen05_fence_after();
-              const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
+              const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
+              uint32_t lb = p.ws_mode ? lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16)
+                                      : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
+              const uint32_t lb_step = p.ws_mode ? (uint32_t)(p.cblocks * bsub16) : (uint32_t)bsub16;
+#pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
-                const uint32_t a_addr = sa + kx * p.dil * row_bytes;   // same strip, shifted by kx*dil pixels
-                const uint32_t b_addr = p.ws_mode ? smem_u32(smem_b) + ((ky * 3 + kx) * p.cblocks + cb) * b_sub_bytes
-                                                  : smem_u32(smem_b + stage * p.b_stage_bytes) + kx * b_sub_bytes;
-                const uint64_t da = make_smem_desc(a_addr, p.kc, p.strip == 2 ? (a_addr >> 7) : 0u);
-                const uint64_t db = make_smem_desc(b_addr, p.kc, 0u);
+                const uint32_t lak = la + kx * p.dil * row16;          // same strip, shifted by kx*dil pixels
                 for (int k = 0; k < kmma; ++k) {
-                  umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, first);
+                  umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, first);
                   first = 1;
                 }
+                lb += lb_step;
               }
               umma_commit(&empty_bar[stage]);
               if (++stage == S) { stage = 0; phase ^= 1; }
@@ -273,15 +285,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             tcgen05_fence_after();
             if (ks == 0) DBG_STAMP(4);
             const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-            const uint32_t sa = smem_u32(smem_a + stage * p.a_stage_bytes);
-            const uint32_t sb = p.ws_mode ? smem_u32(smem_b) + q * b_sub_bytes : smem_u32(smem_b + stage * p.b_stage_bytes);
+            uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
+            uint32_t lb = p.ws_mode ? lb_res + (uint32_t)(q * bsub16) : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
             for (int j = 0; j < nch; ++j, ++q) {
-              const uint64_t da = make_smem_desc(sa + j * a_sub_bytes, p.kc, 0u);
-              const uint64_t db = make_smem_desc(sb + j * b_sub_bytes, p.kc, 0u);
               for (int k = 0; k < kmma; ++k) {
                 // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
-                umma_f16_ss(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((ks | j | k) != 0));
+                umma_f16_ss(tmem_d, desc_join(la + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((ks | j | k) != 0));
               }
+              la += asub16;
+              lb += bsub16;
             }
             umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
             if (++stage == S) { stage = 0; phase ^= 1; }
@@ -541,6 +553,16 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   if (co16 > 128 && co16 % 128 != 0) {
     for (int bn = 128; bn >= 16; bn -= 16)
       if (co16 % bn == 0) { p.BN = bn; break; }
+  }
+  // small grids (P4/P5 layers): trade N-tile width for CTA count until every SM has work (A is re-read from L2, which is cheap here)
+  static int split_env = -1;
+  if (split_env < 0) {
+    const char* e = getenv("MYOLO_NSPLIT");
+    split_env = e ? atoi(e) : 1;
+  }
+  if (split_env) {
+    const int m_tiles = p.B * p.tiles_x * p.tiles_y;
+    while (p.BN >= 64 && p.BN % 32 == 0 && m_tiles * ceil_div(co16, p.BN) < 2 * num_sms) p.BN /= 2;
   }
   p.n_tiles_n = ceil_div(co16, p.BN);
   MYOLO_REQUIRE(op.Co_pad >= p.n_tiles_n * p.BN, "conv_tc: Co_pad %d < %d", op.Co_pad, p.n_tiles_n * p.BN);

@@ -90,6 +90,25 @@ def test_forward_tensor_core_sizes(tag, hw):
     assert torch.equal(out[2], seg.argmax(1))
 
 
+@pytest.mark.parametrize("tag", list(NETS))
+def test_forward_full_resolution_all_heads(tag):
+    """BASELINE.json resolution (512x1024): every head / model size on the tensor-core path incl. strip mode, vertical rounds,
+    dilation 6/9 (Lab ASPP), the BiSe global branch and C3SPP (Base)."""
+    model, cfg, sd = build(tag)
+    x = synth.synth_image(1, 512, 1024, seed=7).cuda()
+    (z, raw), seg = model(x)
+    torch.cuda.synchronize()
+    q = restate.model_forward(cfg, sd, x.cpu(), quantised=True)
+    ea = dict(seg=relmax(seg.cpu().numpy(), q["seg"].numpy()), raw0=relmax(raw[0].cpu().numpy(), q["raw"][0].numpy()),
+              raw2=relmax(raw[2].cpu().numpy(), q["raw"][2].numpy()), z=relmax(z.cpu().numpy(), q["z"].numpy()))
+    print(f"\n[{tag} 512x1024] vs fp16-emulation oracle {ea}")
+    assert z.shape == (1, 32256, 15) and seg.shape == (1, 19, 512, 1024)
+    assert max(ea["seg"], ea["raw0"], ea["raw2"]) <= 6e-3 and ea["z"] <= 3e-2, ea
+    # second call replays the captured CUDA graph: must reproduce the eager first call bit for bit
+    (z2, raw2), seg2 = model(x)
+    assert torch.equal(z, z2) and torch.equal(seg, seg2)
+
+
 def test_simt_and_tensor_core_paths_agree(monkeypatch):
     model, cfg, sd = build("s_psp")
     x = synth.synth_image(1, 256, 512, seed=4).cuda()
