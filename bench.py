@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--cfg", default="s_psp", choices=list(CFGS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fp32-logits", action="store_true", help="keep fp32 I/O (fp32 seg logits) instead of the reference's half() mode")
     ap.add_argument("--profile-ops", action="store_true", help="print the per-op device-time table to stderr")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -149,13 +150,15 @@ def main():
     model = Model(yml)
     model.load_state_dict(sd)
     model.cuda().eval()
+    if not args.fp32_logits:
+        model.half()      # the reference's CUDA configuration (detect.py:96-103): fp16 parameters/IO -> seg logits come back as fp16
     eng = model.engine()
 
     # inputs: rotate over NROT different batches so that a step's input is never L2 resident from the previous step
     NROT = 4
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     xs_u8 = [torch.randint(0, 256, (B, 3, H, W), dtype=torch.uint8, device="cuda", generator=gen) for _ in range(NROT)]
-    xs_f32 = [x.float() / 255.0 for x in xs_u8]
+    xs_f32 = [(x.float() / 255.0) if args.fp32_logits else (x.float() / 255.0).half() for x in xs_u8]
     host_u8 = [x.cpu().pin_memory() for x in xs_u8]
 
     # NMS (16 CTAs, latency bound) and the seg argmax (HBM bound) are independent consumers of the forward: run them concurrently
@@ -307,7 +310,7 @@ def main():
         line = {"metric": "images/sec @1024x512 (det+seg fwd)", "value": imgs / (ms_total * 1e-3), "unit": "images/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f16 storage / f32 accumulate", "data": "synthetic",
-                "config": {"workload": f"{yml} inference, batch {B}x3x{H}x{W} per GPU: Model.forward (z, raw, fp32 seg logits) + NMS(0.25,0.45) + "
+                "config": {"workload": f"{yml} inference, batch {B}x3x{H}x{W} per GPU: Model.forward (z, raw, {'fp32' if args.fp32_logits else 'fp16'} seg logits) + NMS(0.25,0.45) + "
                                        "seg upsample/argmax", "global_batch": B * world, "parallelism": f"replicas x{world} (no collective)",
                            "l2": f"inputs rotate over {NROT} batches ({NROT * B * 3 * H * W * 4 / 1e6:.0f} MB > 126 MB L2); activations are rewritten every step",
                            "nms_candidates_kept_per_img": n_cand},

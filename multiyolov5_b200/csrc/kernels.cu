@@ -150,10 +150,40 @@ __global__ void spp_pool_kernel(TensorView in, TensorView out, int n_cascade) {
     __syncthreads();
   }
 }
+// large maps (the Base head pools the 1/8-resolution map): plain 5x5 stride-1 max from global memory, one launch per cascade level
+__global__ void maxpool5_nhwc_kernel(TensorView in, TensorView out) {
+  const RowIdx r = row_index(out.W, out.C / 8);
+  if (!r.ok) return;
+  uint4 m = __ldg(reinterpret_cast<const uint4*>(vptr(in, r.b, r.y, r.x)) + r.v);
+#pragma unroll
+  for (int dy = -2; dy <= 2; ++dy) {
+    const int yy = r.y + dy;
+    if (yy < 0 || yy >= in.H) continue;
+#pragma unroll
+    for (int dx = -2; dx <= 2; ++dx) {
+      const int xx = r.x + dx;
+      if (xx < 0 || xx >= in.W || (dx == 0 && dy == 0)) continue;
+      m = hmax8(m, __ldg(reinterpret_cast<const uint4*>(vptr(in, r.b, yy, xx)) + r.v));
+    }
+  }
+  reinterpret_cast<uint4*>(vptr(out, r.b, r.y, r.x))[r.v] = m;
+}
+
 int launch_spp_pool(const TensorView& in, const TensorView& out5, int n_cascade, cudaStream_t s) {
   MYOLO_REQUIRE(in.C % 8 == 0 && in.ctot % 8 == 0 && out5.ctot % 8 == 0 && in.H == out5.H && in.W == out5.W, "spp_pool: bad views");
   const size_t smem = (size_t)in.H * in.W * 16 * 2;
-  MYOLO_REQUIRE(smem <= 200 * 1024, "spp_pool: map %dx%d too large for the shared-memory kernel", in.H, in.W);
+  if (smem > 200 * 1024) {
+    TensorView src = in;
+    for (int st = 0; st < n_cascade; ++st) {
+      TensorView dst = out5;
+      dst.C = in.C;
+      dst.base = reinterpret_cast<__half*>(out5.base) + (size_t)st * in.C;
+      maxpool5_nhwc_kernel<<<row_grid(dst, dst.C / 8), 256, 0, s>>>(src, dst);
+      MYOLO_LAUNCH_CHECK();
+      src = dst;
+    }
+    return 0;
+  }
   static bool attr = false;
   if (!attr) {
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -529,6 +559,37 @@ __global__ void argmax_nchw_f32x4_kernel(const float* __restrict__ src, int B, i
   }
 }
 
+// fp16 logits (the reference's CUDA path runs model.half(), detect.py:96-103): 8 pixels per thread, one 16-byte load per class plane
+template <typename TOut>
+__global__ void argmax_nchw_f16x8_kernel(const __half* __restrict__ src, int B, int C, long HW, TOut* out) {
+  const long n8 = (long)B * HW / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n8; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i * 8;
+    const long b = pix / HW, off = pix - b * HW;
+    const __half* p = src + b * C * HW + off;
+    float best[8];
+    int bi[8];
+    {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+      const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { best[k] = __half2float(h[k]); bi[k] = 0; }
+    }
+#pragma unroll 6
+    for (int c = 1; c < C; ++c) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + (size_t)c * HW));
+      const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float f = __half2float(h[k]);
+        if (f > best[k]) { best[k] = f; bi[k] = c; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[pix + k] = (TOut)bi[k];
+  }
+}
+
 __global__ void bilinear_nchw_kernel(const float* __restrict__ src, int B, int C, int h, int w, int H, int W, float* dst) {
   const long total = (long)B * C * H * W;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -572,6 +633,13 @@ extern "C" int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, i
     const int g4 = grid_for((long)B * H * W / 4, 256, 148 * 32);
     if (out_dtype == MYOLO_I64) argmax_nchw_f32x4_kernel<int64_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (int64_t*)out);
     else argmax_nchw_f32x4_kernel<uint8_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (uint8_t*)out);
+    MYOLO_LAUNCH_CHECK();
+    return 0;
+  }
+  if (dtype == MYOLO_F16 && H == h && W == w && ((long)H * W) % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) {
+    const int g8 = grid_for((long)B * H * W / 8, 256, 148 * 32);
+    if (out_dtype == MYOLO_I64) argmax_nchw_f16x8_kernel<int64_t><<<g8, 256, 0, s>>>((const __half*)logits, B, C, (long)H * W, (int64_t*)out);
+    else argmax_nchw_f16x8_kernel<uint8_t><<<g8, 256, 0, s>>>((const __half*)logits, B, C, (long)H * W, (uint8_t*)out);
     MYOLO_LAUNCH_CHECK();
     return 0;
   }

@@ -96,7 +96,9 @@ class Engine:
         raws = []
         for i, v in enumerate([o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]):
             raws.append(torch.empty((B, det.na, v.h, v.w, det.no), dtype=torch.float32, device=dev) if want_raw else None)
-        seg_dt = torch.float16 if x.dtype == torch.float16 else torch.float32
+        # like the reference: fp16 in (or model.half(), detect.py:96-103) -> fp16 seg logits; otherwise fp32
+        half_model = next(self.model.parameters()).dtype == torch.float16
+        seg_dt = torch.float16 if (x.dtype == torch.float16 or half_model) else torch.float32
         seg = torch.empty((B, seg_head.c_out, H, W), dtype=seg_dt, device=dev) if (want_seg and not seg_argmax) else None
         amax = torch.empty((B, H, W), dtype=torch.int64, device=dev) if seg_argmax else None
         raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])

@@ -109,6 +109,24 @@ def test_forward_full_resolution_all_heads(tag):
     assert torch.equal(z, z2) and torch.equal(seg, seg2)
 
 
+def test_half_mode_like_reference_cuda_path():
+    """detect.py:96-103: model.half() + img.half() -> fp16 seg logits; class ids must agree with the fp32-IO run except at near-ties."""
+    model, cfg, sd = build("s_psp")
+    x = synth.synth_image(2, 256, 512, seed=9).cuda()
+    (z32, _), seg32 = model(x)
+    mh, _, _ = build("s_psp")
+    mh.half()
+    (z16, _), seg16 = mh(x.half())
+    torch.cuda.synchronize()
+    assert seg16.dtype == torch.float16 and seg32.dtype == torch.float32
+    assert relmax(seg16.float().cpu().numpy(), seg32.cpu().numpy()) < 4e-3
+    assert relmax(z16.cpu().numpy(), z32.cpu().numpy()) < 2e-2
+    from multiyolov5_b200.utils.general import seg_argmax
+    a16, a32 = seg_argmax(seg16), seg_argmax(seg32)
+    assert torch.equal(a16, seg16.float().argmax(1))            # fp16 fast path is an exact argmax of what it is given
+    assert (a16 != a32).float().mean().item() < 2e-3
+
+
 def test_simt_and_tensor_core_paths_agree(monkeypatch):
     model, cfg, sd = build("s_psp")
     x = synth.synth_image(1, 256, 512, seed=4).cuda()
