@@ -59,6 +59,7 @@ extern "C" {
 #define MYOLO_OP_DETECT_DECODE 10 /* Detect.forward view/permute/sigmoid/decode, models/yolo.py:211-225 */
 #define MYOLO_OP_SEG_UPSAMPLE 11 /* final x8 bilinear of the seg head -> NCHW logits, models/yolo.py:163 */
 #define MYOLO_OP_BROADCAST 12    /* F.interpolate(nearest) of a 1x1 map (RFB2 global branch), models/common.py:509 */
+#define MYOLO_OP_FOCUS_CONV 13   /* whole layer 0 fused: Focus slicing + Conv3x3+BN+SiLU from the NCHW image, models/common.py:542-551 */
 
 /* conv op flags */
 #define MYOLO_CONV_FORCE_SIMT 1 /* run on the generic CUDA-core kernel (tiny M / odd shapes / debugging) */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmyolo_sm100a.so")
 F16, F32, U8, I64 = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_SIGMOID = 0, 1, 2
 (OP_INPUT_FOCUS, OP_CONV, OP_UPSAMPLE_NEAREST, OP_SPP_POOL, OP_BILINEAR, OP_REGION_SUM, OP_REGION_COMBINE, OP_CHANNEL_SCALE,
- OP_ADD, OP_DETECT_DECODE, OP_SEG_UPSAMPLE, OP_BROADCAST) = range(1, 13)
+ OP_ADD, OP_DETECT_DECODE, OP_SEG_UPSAMPLE, OP_BROADCAST, OP_FOCUS_CONV) = range(1, 14)
 CONV_FORCE_SIMT = 1
 
 EXPORTS = [

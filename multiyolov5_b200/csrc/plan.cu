@@ -260,6 +260,14 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
     case MYOLO_OP_INPUT_FOCUS:
       if ((rc = resolve_view(pl, op.out, &out))) return rc;
       return launch_input_focus(x, x_dtype, pl->B, pl->H, pl->W, out, s);
+    case MYOLO_OP_FOCUS_CONV: {
+      if ((rc = resolve_view(pl, op.out, &out))) return rc;
+      MYOLO_REQUIRE(op.weight_slot >= 0 && op.weight_slot < (int)pl->slots.size() && pl->slots[op.weight_slot].set,
+                    "op %d: focus_conv weights not set", i);
+      const WeightSlot& ws = pl->slots[op.weight_slot];
+      MYOLO_REQUIRE(ws.k == 3 && ws.ci == 12 && ws.ci_pad == 16, "op %d: focus_conv expects a 3x3 conv over 12 channels", i);
+      return launch_focus_conv(x, x_dtype, pl->B, pl->H, pl->W, ws.w, ws.bias, ws.co, out, s);
+    }
     case MYOLO_OP_CONV:
       if (!pl->conv_ready[i] && (rc = prepare_conv(pl, i))) return rc;
       return pl->convs[i].use_tc ? conv_tc_launch(pl->convs[i], s) : conv_simt_launch(pl->convs[i], s);
@@ -309,7 +317,7 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
 // dependency analysis + multi-lane graph capture
 // ------------------------------------------------------------------------------------------------
 static bool is_external_op(int kind) {
-  return kind == MYOLO_OP_INPUT_FOCUS || kind == MYOLO_OP_DETECT_DECODE || kind == MYOLO_OP_SEG_UPSAMPLE;
+  return kind == MYOLO_OP_INPUT_FOCUS || kind == MYOLO_OP_FOCUS_CONV || kind == MYOLO_OP_DETECT_DECODE || kind == MYOLO_OP_SEG_UPSAMPLE;
 }
 
 struct Access { int buf, c_lo, c_hi; int64_t lo, hi; bool write; };
@@ -448,7 +456,7 @@ extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, fl
   }
   int n_ext = 0;
   for (size_t i = 0; i < pl->ops.size(); ++i)     // ops reading the caller's input: before the graph
-    if (pl->ops[i].kind == MYOLO_OP_INPUT_FOCUS) {
+    if (pl->ops[i].kind == MYOLO_OP_INPUT_FOCUS || pl->ops[i].kind == MYOLO_OP_FOCUS_CONV) {
       int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
       if (rc) return rc;
       ++n_ext;

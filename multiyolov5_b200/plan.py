@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_SIGMOID, ACT_SILU, F16, F32, OP_ADD, OP_BILINEAR, OP_BROADCAST, OP_CHANNEL_SCALE, OP_CONV,
-                   OP_DETECT_DECODE, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
+                   OP_DETECT_DECODE, OP_FOCUS_CONV, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
                    OP_UPSAMPLE_NEAREST)
 from .models import common as cm
 
@@ -227,7 +227,17 @@ class PlanBuilder:
         return self.Conv(m.cv3, cat, dst)
 
     def Focus(self, m: cm.Focus, dst=None) -> V:
-        assert m.conv.conv.in_channels == 12
+        conv = m.conv.conv
+        assert conv.in_channels == 12
+        import os
+        if (conv.kernel_size == (3, 3) and conv.out_channels in (32, 48) and isinstance(m.conv.act, nn.SiLU)
+                and os.environ.get("MYOLO_NO_FOCUS_FUSION") != "1"):
+            # whole layer in one kernel straight from the NCHW image (csrc/focus_conv.cu)
+            dst = dst or self.new_buf(self.H // 2, self.W // 2, conv.out_channels)
+            slot = len(self.slots)
+            self.slots.append(WeightSlot(conv, m.conv.bn, "focus"))
+            self.emit(OpRec(OP_FOCUS_CONV, None, None, dst, 3, 1, 1, ACT_SILU, 0, slot))
+            return dst
         s2d = self.new_buf(self.H // 2, self.W // 2, 16)
         self.emit(OpRec(OP_INPUT_FOCUS, None, None, s2d))
         return self.Conv(m.conv, s2d, dst)

@@ -60,7 +60,8 @@ def test_planner_invariants(tag, B, H, W):
     assert pb.workspace_bytes < sum(b.nbytes(B) for b in used)
     # every conv reads exactly the (16-padded) input channels it was packed for; outputs land in slices (no concat copies)
     kinds = [o.kind for o in pb.ops]
-    assert kinds.count(_lib.OP_INPUT_FOCUS) == 1 and kinds.count(_lib.OP_DETECT_DECODE) == 3 and kinds.count(_lib.OP_SEG_UPSAMPLE) == 1
+    assert kinds.count(_lib.OP_INPUT_FOCUS) + kinds.count(_lib.OP_FOCUS_CONV) == 1   # layer 0: fused Focus+conv (or s2d + conv)
+    assert kinds.count(_lib.OP_DETECT_DECODE) == 3 and kinds.count(_lib.OP_SEG_UPSAMPLE) == 1
     for o in pb.ops:
         if o.kind == _lib.OP_CONV:
             c = pb.slots[o.slot].conv
