@@ -231,8 +231,9 @@ class PlanBuilder:
         assert conv.in_channels == 12
         import os
         if (conv.kernel_size == (3, 3) and conv.out_channels in (32, 48) and isinstance(m.conv.act, nn.SiLU)
-                and os.environ.get("MYOLO_NO_FOCUS_FUSION") != "1"):
-            # whole layer in one kernel straight from the NCHW image (csrc/focus_conv.cu)
+                and os.environ.get("MYOLO_FOCUS_FUSION") == "1"):
+            # opt-in: whole layer in one kernel straight from the NCHW image (csrc/focus_conv.cu).  Measured on B200 it is still
+            # slower (190 us) than space-to-depth kernel + tcgen05 conv (26 + 108 us), so the two-kernel path stays the default.
             dst = dst or self.new_buf(self.H // 2, self.W // 2, conv.out_channels)
             slot = len(self.slots)
             self.slots.append(WeightSlot(conv, m.conv.bn, "focus"))

@@ -115,11 +115,12 @@ def test_fused_layer0_matches_unfused_path(tag, dtype, monkeypatch):
     model, cfg, sd = build(tag)
     x8 = torch.randint(0, 256, (2, 3, 128, 256), dtype=torch.uint8, generator=torch.Generator().manual_seed(3)).cuda()
     x = x8 if dtype == torch.uint8 else (x8.float() / 255.0).to(dtype)
+    monkeypatch.setenv("MYOLO_FOCUS_FUSION", "1")
     eng = model.engine()
     eng.noalias = True          # keep layer 0's buffer readable after the forward
     model(x)
     y_fused = eng.read_view(eng.last_plan.pb.layer_views[0]).clone()
-    monkeypatch.setenv("MYOLO_NO_FOCUS_FUSION", "1")
+    monkeypatch.setenv("MYOLO_FOCUS_FUSION", "0")
     model2, _, _ = build(tag)
     model2.engine().noalias = True
     model2(x)
