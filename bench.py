@@ -141,7 +141,18 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created: keep stdout clean for the ONE JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from multiyolov5_b200.models.yolo import Model
     from multiyolov5_b200.utils.general import non_max_suppression, seg_argmax
     tag = args.cfg
