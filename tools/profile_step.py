@@ -17,7 +17,8 @@ yml, cfg, sd = bench.make_weights(tag)
 model = Model(yml)
 model.load_state_dict(sd)
 model.cuda().eval()
-x = torch.rand(B, 3, bench.H, bench.W, device="cuda")
+model.half()          # same configuration as bench.py's default (the reference's CUDA path: detect.py:96-103)
+x = torch.rand(B, 3, bench.H, bench.W, device="cuda").half()
 
 
 def step():

@@ -8,25 +8,41 @@ import sys
 
 
 def launches(path, out):
+    """launch list with gpu__time_duration (+ optional dram bytes) per launch; writes the markdown summary and, when dram metrics are
+    present, profiles/ncu_traffic.json (dram bytes per conv_tc launch, read by bench.py for roofline.traffic)."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 5]
     hdr = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
     H, data = rows[hdr], rows[hdr + 1:]
-    ki, vi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Unit")
-    agg, tot = collections.OrderedDict(), 0.0
-    per = []
+    ii, ki, mi, vi, ui = H.index("ID"), H.index("Kernel Name"), H.index("Metric Name"), H.index("Metric Value"), H.index("Metric Unit")
+    per = collections.OrderedDict()
     for r in data:
-        t = float(r[vi].replace(",", ""))
-        t = t / 1000 if r[ui] == "ns" else (t * 1000 if r[ui] == "ms" else t)
-        k = r[ki].split("(")[0].replace("void ", "").replace("myolo::", "")
-        a = agg.setdefault(k, [0, 0.0]); a[0] += 1; a[1] += t; tot += t
-        per.append((k, t))
+        d = per.setdefault(r[ii], {"k": r[ki].split("(")[0].replace("void ", "").replace("myolo::", "")})
+        v = float(r[vi].replace(",", ""))
+        if r[mi].startswith("gpu__time_duration"):
+            d["us"] = v / 1000 if r[ui] in ("ns", "nsecond") else (v * 1000 if r[ui] in ("ms", "msecond") else v)
+        elif r[mi].startswith("dram__bytes_read"):
+            d["rd"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1)
+        elif r[mi].startswith("dram__bytes_write"):
+            d["wr"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1)
+    agg, tot = collections.OrderedDict(), 0.0
+    for d in per.values():
+        a = agg.setdefault(d["k"], [0, 0.0, 0.0]); a[0] += 1; a[1] += d.get("us", 0.0); a[2] += d.get("rd", 0.0) + d.get("wr", 0.0)
+        tot += d.get("us", 0.0)
+    has_dram = any("rd" in d for d in per.values())
     with open(out, "w") as f:
-        f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised): {len(data)} launches, {tot:.1f} us\n\n")
-        f.write("| kernel | launches | total us | share |\n|---|---:|---:|---:|\n")
-        for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            f.write(f"| {k} | {n} | {t:.1f} | {100 * t / tot:.1f}% |\n")
+        f.write(f"# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised): {len(per)} launches, {tot:.1f} us\n\n")
+        f.write("| kernel | launches | total us | share |" + (" dram MB (rd+wr) |" if has_dram else "") + "\n|---|---:|---:|---:|" + ("---:|" if has_dram else "") + "\n")
+        for k, (n, t, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"| {k} | {n} | {t:.1f} | {100 * t / tot:.1f}% |" + (f" {by / 1e6:.1f} |" if has_dram else "") + "\n")
         f.write("\nper-launch durations in stream order (us):\n\n")
-        f.write(" ".join(f"{k[:12]}:{t:.1f}" for k, t in per) + "\n")
+        f.write(" ".join(f"{d['k'][:12]}:{d.get('us', 0):.1f}" for d in per.values()) + "\n")
+    if has_dram:
+        import json
+        conv = [d for d in per.values() if d["k"].startswith("conv_tc")]
+        json.dump({"cfg": "s_psp", "batch": 16, "launches": len(conv),
+                   "dram_bytes_per_launch": sum(d.get("rd", 0) + d.get("wr", 0) for d in conv) / max(1, len(conv)),
+                   "dram_read_MB_total": sum(d.get("rd", 0) for d in conv) / 1e6, "dram_write_MB_total": sum(d.get("wr", 0) for d in conv) / 1e6,
+                   "source": path}, open("profiles/ncu_traffic.json", "w"))
 
 
 def full(rep, out):
@@ -51,10 +67,6 @@ def full(rep, out):
                 tot_rd += float(r[idx["dram_rd_MB"]]); tot_wr += float(r[idx["dram_wr_MB"]]); nrows += 1
             except Exception:
                 pass
-    if nrows:
-        import json
-        json.dump({"cfg": "s_psp", "batch": 16, "launches": nrows, "dram_bytes_per_launch": (tot_rd + tot_wr) * 1e6 / nrows,
-                   "dram_read_MB_total": tot_rd, "dram_write_MB_total": tot_wr, "source": rep}, open("profiles/ncu_traffic.json", "w"))
 
 
 if __name__ == "__main__":
