@@ -59,6 +59,9 @@ extern "C" {
 #define MYOLO_OP_DETECT_DECODE 10 /* Detect.forward view/permute/sigmoid/decode, models/yolo.py:211-225 */
 #define MYOLO_OP_SEG_UPSAMPLE 11 /* final x8 bilinear of the seg head -> NCHW logits, models/yolo.py:163 */
 #define MYOLO_OP_BROADCAST 12    /* F.interpolate(nearest) of a 1x1 map (RFB2 global branch), models/common.py:509 */
+#define MYOLO_OP_BN_ACT 14       /* train mode: batch-statistics BatchNorm + activation (+ residual) on a raw conv output; aux[0] = bn slot */
+#define MYOLO_OP_ACT 15          /* train mode: standalone activation (FFM attention SiLU / Sigmoid) so the pre-activation is kept */
+#define MYOLO_OP_CHANNEL_SCALE_OOP 16 /* train mode: out = in * (1 + in2) out of place (in is needed by the backward pass) */
 #define MYOLO_OP_FOCUS_CONV 13   /* whole layer 0 fused: Focus slicing + Conv3x3+BN+SiLU from the NCHW image, models/common.py:542-551 */
 
 /* conv op flags */
@@ -119,6 +122,19 @@ int64_t myolo_plan_last_launch_count(const myolo_plan* plan);
 /* per-op device time of the next forward (CUDA events around every op; host array of n_ops floats, ms) */
 int myolo_plan_profile(myolo_plan* plan, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
                        int64_t* seg_argmax, float* host_ms_per_op, void* stream);
+
+/* ---- training: plans built with train-mode ops; no buffer aliasing; no CUDA graph ---- */
+/* BatchNorm parameters of bn_slot: device fp32 pointers owned by the caller (updated in place by its optimiser); running stats are
+ * updated by the forward with `momentum` (reference utils/torch_utils.py:150-152: eps 1e-3, momentum 0.03); d_gamma/d_beta nullable */
+int myolo_plan_set_bn(myolo_plan* plan, int bn_slot, int channels, float* gamma, float* beta, float* running_mean, float* running_var,
+                      float* d_gamma, float* d_beta, float momentum, float eps);
+/* where the conv parameter gradients are accumulated (fp32, PyTorch layout [Co][Ci][k][k]; d_bias nullable) */
+int myolo_plan_set_conv_grad(myolo_plan* plan, int weight_slot, float* d_weight, float* d_bias);
+/* train-mode forward: raw[i] (B,na,ny,nx,no) fp32 and seg (B,n_segcls,H,W) fp32, like Model.forward in training (models/yolo.py:225,316) */
+int myolo_plan_train_forward(myolo_plan* plan, const void* x, int x_dtype, float* const* raw, float* seg, void* stream);
+/* backward of the last train forward: grad_raw[i] / grad_seg are dL/d(raw[i]) / dL/d(seg) (fp32, nullable); parameter gradients are
+ * ACCUMULATED into the registered pointers (the reference accumulates the det and the seg pass, train.py:371,392) */
+int myolo_plan_backward(myolo_plan* plan, const float* const* grad_raw, const float* grad_seg, void* stream);
 
 /* ---- post-process ---- */
 /* utils.general.non_max_suppression (reference utils/general.py:421-509).  pred: (B,A,no) fp32.

@@ -12,14 +12,14 @@ LIB_PATH = os.path.join(_HERE, "libmyolo_sm100a.so")
 F16, F32, U8, I64 = 0, 1, 2, 3
 ACT_NONE, ACT_SILU, ACT_SIGMOID = 0, 1, 2
 (OP_INPUT_FOCUS, OP_CONV, OP_UPSAMPLE_NEAREST, OP_SPP_POOL, OP_BILINEAR, OP_REGION_SUM, OP_REGION_COMBINE, OP_CHANNEL_SCALE,
- OP_ADD, OP_DETECT_DECODE, OP_SEG_UPSAMPLE, OP_BROADCAST, OP_FOCUS_CONV) = range(1, 14)
+ OP_ADD, OP_DETECT_DECODE, OP_SEG_UPSAMPLE, OP_BROADCAST, OP_FOCUS_CONV, OP_BN_ACT, OP_ACT, OP_CHANNEL_SCALE_OOP) = range(1, 17)
 CONV_FORCE_SIMT = 1
 
 EXPORTS = [
     "myolo_abi_version", "myolo_last_error", "myolo_device_info", "myolo_plan_create", "myolo_plan_destroy",
     "myolo_plan_set_conv_weights", "myolo_plan_forward", "myolo_plan_read_view", "myolo_plan_last_launch_count",
     "myolo_plan_profile", "myolo_nms_workspace_bytes", "myolo_nms", "myolo_seg_upsample_argmax", "myolo_bilinear_nchw",
-    "myolo_conv_bn_silu",
+    "myolo_conv_bn_silu", "myolo_plan_set_bn", "myolo_plan_set_conv_grad", "myolo_plan_train_forward", "myolo_plan_backward",
 ]
 
 
@@ -67,6 +67,10 @@ def lib():
     L.myolo_plan_last_launch_count.argtypes = [vp]
     L.myolo_plan_last_launch_count.restype = i64
     L.myolo_plan_profile.argtypes = [vp, vp, i32, vp, C.POINTER(vp), vp, i32, vp, C.POINTER(f32), vp]
+    L.myolo_plan_set_bn.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp, vp, f32, f32]
+    L.myolo_plan_set_conv_grad.argtypes = [vp, i32, vp, vp]
+    L.myolo_plan_train_forward.argtypes = [vp, vp, i32, C.POINTER(vp), vp, vp]
+    L.myolo_plan_backward.argtypes = [vp, C.POINTER(vp), vp, vp]
     L.myolo_nms_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.myolo_nms_workspace_bytes.restype = i64
     L.myolo_nms.argtypes = [vp, i32, i32, i32, f32, f32, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, i64, vp]

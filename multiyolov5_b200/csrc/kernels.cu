@@ -399,6 +399,7 @@ __global__ void detect_decode_kernel(TensorView in, int na, int no_rt, float str
   const float v = vptr_f(in, b, y, x)[a * no + o];
   const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
   if (raw) raw[row * no + o] = v;
+  if (!z) return;     // train mode: only the raw, permuted head outputs (reference models/yolo.py:225 `return x if self.training`)
   float sg = __fdividef(1.0f, 1.0f + __expf(-v));
   if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
   else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;

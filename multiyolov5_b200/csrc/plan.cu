@@ -3,11 +3,13 @@
 // liveness-packed NHWC buffers; this file resolves views, owns packed weights / tensor maps and replays the list on a stream.
 #include <stdarg.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
 #include "conv.h"
 #include "kernels.h"
+#include "train.h"
 
 namespace myolo {
 
@@ -48,6 +50,12 @@ struct WeightSlot {
   float* bias = nullptr;
   int co = 0, ci = 0, k = 0, co_pad = 0, ci_pad = 0;
   bool set = false;
+  // training
+  const float* w_master = nullptr;   // caller's fp32 parameter (device)
+  float* d_w = nullptr;              // caller's .grad (accumulated)
+  float* d_bias = nullptr;
+  __half* w_dgrad = nullptr;         // flipped / transposed fp16 pack for the data gradient
+  float* zero_bias = nullptr;
 };
 
 }  // namespace myolo
@@ -77,6 +85,17 @@ struct myolo_plan {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int n_graph_ops = 0;
+  // training state
+  std::vector<BnParams> bns;
+  std::vector<float*> bn_stats;       // per op: mean / invstd of the last forward (2*C floats) + 2*C scratch
+  unsigned char* gws = nullptr;       // gradient workspace, same layout as ws
+  __half* tmp16 = nullptr;            // fp16 copy of an fp32 head gradient / zero-stuffed stride-2 gradient
+  size_t tmp16_bytes = 0;
+  float* spp_scratch = nullptr;
+  size_t spp_scratch_bytes = 0;
+  std::vector<ConvOp> dconvs;         // data-gradient convs (parallel to ops)
+  std::vector<int> dconv_ready;
+  bool train_fwd_done = false;
 };
 
 static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
@@ -175,6 +194,14 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   for (auto e : pl->op_ev) cudaEventDestroy(e);
   if (pl->ev_start) cudaEventDestroy(pl->ev_start);
   for (auto st : pl->lanes) cudaStreamDestroy(st);
+  for (auto& sl : pl->slots) {
+    if (sl.w_dgrad) cudaFree(sl.w_dgrad);
+    if (sl.zero_bias) cudaFree(sl.zero_bias);
+  }
+  for (auto p : pl->bn_stats) if (p) cudaFree(p);
+  if (pl->gws) cudaFree(pl->gws);
+  if (pl->tmp16) cudaFree(pl->tmp16);
+  if (pl->spp_scratch) cudaFree(pl->spp_scratch);
   delete pl;
 }
 
@@ -211,6 +238,7 @@ extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float
   s.co_pad = co_pad;
   s.ci_pad = ci_pad;
   s.set = true;
+  s.w_master = w;
   return pack_conv_weights(w, co, ci, k, gamma, beta, mean, var, eps, bias, s.w, s.bias, co_pad, ci_pad, (cudaStream_t)stream);
 }
 
@@ -296,10 +324,27 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
     case MYOLO_OP_BROADCAST:
       if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
       return launch_broadcast(in, out, s);
+    case MYOLO_OP_BN_ACT: {
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      const bool has_res = op.in2.buf >= 0;
+      if (has_res && (rc = resolve_view(pl, op.in2, &in2))) return rc;
+      MYOLO_REQUIRE(op.aux[0] >= 0 && op.aux[0] < (int)pl->bns.size() && pl->bns[op.aux[0]].set, "op %d: BN slot %d not set", i, op.aux[0]);
+      const BnParams& bn = pl->bns[op.aux[0]];
+      if ((int)pl->bn_stats.size() <= i) pl->bn_stats.resize(pl->ops.size(), nullptr);
+      if (!pl->bn_stats[i]) MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], 4 * (size_t)bn.C * sizeof(float)));
+      if ((rc = launch_bn_stats(in, bn, pl->bn_stats[i], pl->bn_stats[i] + 2 * bn.C, s))) return rc;
+      return launch_bn_act_fwd(in, has_res ? &in2 : nullptr, out, bn, pl->bn_stats[i], op.act, s);
+    }
+    case MYOLO_OP_ACT:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_act_fwd(in, out, op.act, s);
+    case MYOLO_OP_CHANNEL_SCALE_OOP:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.in2, &in2)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      return launch_channel_scale_oop(in, in2, out, s);
     case MYOLO_OP_DETECT_DECODE: {
       if ((rc = resolve_view(pl, op.in, &in))) return rc;
       const int level = op.aux[0];
-      MYOLO_REQUIRE(z != nullptr, "detect_decode: z output pointer is null");
+      MYOLO_REQUIRE(z != nullptr || raw != nullptr, "detect_decode: no output pointer");
       return launch_detect_decode(in, op.aux[1], op.aux[2], op.faux[0], reinterpret_cast<const float*>(pl->d_extra + op.aux[5]),
                                   raw ? raw[level] : nullptr, z, op.aux[3], op.aux[4], s);
     }
@@ -499,6 +544,220 @@ extern "C" int myolo_plan_read_view(myolo_plan* pl, myolo_view view, float* dst,
   int rc = resolve_view(pl, view, &v);
   if (rc) return rc;
   return launch_read_view(v, dst, (cudaStream_t)stream);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// training: forward with batch-statistics BN, backward over the op list in reverse
+// ------------------------------------------------------------------------------------------------
+extern "C" int myolo_plan_set_bn(myolo_plan* pl, int bn_slot, int channels, float* gamma, float* beta, float* running_mean,
+                                 float* running_var, float* d_gamma, float* d_beta, float momentum, float eps) {
+  MYOLO_REQUIRE(pl && bn_slot >= 0 && gamma && beta && channels > 0, "set_bn: bad arguments");
+  if ((int)pl->bns.size() <= bn_slot) pl->bns.resize(bn_slot + 1);
+  BnParams& b = pl->bns[bn_slot];
+  b.gamma = gamma; b.beta = beta; b.running_mean = running_mean; b.running_var = running_var;
+  b.d_gamma = d_gamma; b.d_beta = d_beta; b.momentum = momentum; b.eps = eps; b.C = channels; b.set = true;
+  return 0;
+}
+
+extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weight, float* d_bias) {
+  MYOLO_REQUIRE(pl && slot >= 0 && slot < (int)pl->slots.size(), "set_conv_grad: bad slot %d", slot);
+  pl->slots[slot].d_w = d_weight;
+  pl->slots[slot].d_bias = d_bias;
+  return 0;
+}
+
+extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream) {
+  MYOLO_REQUIRE(pl && x, "train_forward: null plan / input");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t l0 = g_launch_count;
+  for (size_t i = 0; i < pl->ops.size(); ++i) {
+    int rc = run_op(pl, (int)i, x, x_dtype, nullptr, raw, seg, MYOLO_F32, nullptr, s);
+    if (rc) return rc;
+  }
+  pl->last_launches = g_launch_count - l0;
+  pl->train_fwd_done = true;
+  return 0;
+}
+
+static int grad_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
+  int rc = resolve_view(pl, v, out);
+  if (rc) return rc;
+  out->base = pl->gws + (reinterpret_cast<unsigned char*>(out->base) - pl->ws);   // same layout in the gradient workspace
+  return 0;
+}
+
+static int ensure_tmp16(myolo_plan* pl, size_t bytes) {
+  if (pl->tmp16_bytes >= bytes) return 0;
+  if (pl->tmp16) cudaFree(pl->tmp16);
+  pl->tmp16 = nullptr;
+  MYOLO_CHECK_CUDA(cudaMalloc(&pl->tmp16, bytes));
+  pl->tmp16_bytes = bytes;
+  for (auto& r : pl->dconv_ready) r = 0;   // tensor maps point into tmp16
+  return 0;
+}
+
+// backward of one conv op: dY = grad(out); grad(in) += conv^T(dY, W); dW += ...; dbias += ...
+static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s) {
+  const myolo_op& op = pl->ops[i];
+  WeightSlot& sl = pl->slots[op.weight_slot];
+  MYOLO_REQUIRE(sl.set && sl.w_master && sl.d_w, "op %d: conv slot %d has no master weights / gradient pointer", i, op.weight_slot);
+  TensorView xin, gout, gin;
+  int rc;
+  if ((rc = resolve_view(pl, op.in, &xin)) || (rc = grad_view(pl, op.out, &gout)) || (rc = grad_view(pl, op.in, &gin))) return rc;
+  const long npix_out = (long)gout.B * gout.H * gout.W;
+  // tiny maps / fp32 inputs: generic kernels on the fp32 master weights
+  if (xin.dtype == MYOLO_F32 || npix_out <= 1024 || gout.H * gout.W < 128) {
+    TensorView gy = gout;
+    gy.C = sl.co;
+    return launch_conv_small_bwd(xin, gy, need_dgrad ? &gin : nullptr, sl.w_master, sl.d_w, sl.d_bias, sl.co, sl.ci, op.k, op.stride, op.dil, s);
+  }
+  // dY in fp16 (cast fp32 head gradients; zero-stuff for stride 2)
+  const int cpad = (int)align_up(sl.co, 16);
+  TensorView dy16 = gout;
+  size_t need = 0;
+  if (gout.dtype == MYOLO_F32) need = (size_t)npix_out * cpad * 2;
+  const bool s2 = op.stride == 2;
+  size_t stuffed_off = align_up((int64_t)need, 256);
+  if (s2) need = stuffed_off + (size_t)gout.B * (2 * gout.H) * (2 * gout.W) * cpad * 2;
+  if (need && (rc = ensure_tmp16(pl, need))) return rc;
+  if (gout.dtype == MYOLO_F32) {
+    dy16 = TensorView{pl->tmp16, gout.B, gout.H, gout.W, cpad, cpad, MYOLO_F16};
+    if ((rc = launch_cast_f32_to_f16(gout, dy16, s))) return rc;
+  } else {
+    MYOLO_REQUIRE(gout.C == sl.co && sl.co % 16 == 0, "op %d: fp16 conv gradient needs Co %% 16 == 0 (Co=%d)", i, sl.co);
+  }
+  // weight / bias gradients
+  if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, sl.d_bias, s))) return rc;
+  if (!need_dgrad) return 0;
+  // data gradient = stride-1 conv of (zero-stuffed) dY with flipped / transposed weights, accumulated into grad(in)
+  const int ci_out_pad = (int)align_up(sl.ci, 16);
+  const int n_pad = ((ci_out_pad <= 128) ? ci_out_pad : [&] { for (int bn = 128; bn >= 16; bn -= 16) if (ci_out_pad % bn == 0) return ci_out_pad; return ci_out_pad; }());
+  if (!sl.w_dgrad) {
+    MYOLO_CHECK_CUDA(cudaMalloc(&sl.w_dgrad, (size_t)n_pad * op.k * op.k * cpad * 2));
+    MYOLO_CHECK_CUDA(cudaMalloc(&sl.zero_bias, (size_t)n_pad * 4));
+  }
+  if ((rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, op.k, sl.w_dgrad, sl.zero_bias, n_pad, cpad, s))) return rc;
+  TensorView din = dy16;
+  if (s2) {
+    din = TensorView{reinterpret_cast<unsigned char*>(pl->tmp16) + stuffed_off, gout.B, 2 * gout.H, 2 * gout.W, cpad, cpad, MYOLO_F16};
+    TensorView src = dy16;
+    src.C = cpad;
+    if (gout.dtype != MYOLO_F32) { src = gout; }
+    MYOLO_REQUIRE(src.C == cpad, "op %d: stride-2 gradient channel padding mismatch", i);
+    if ((rc = launch_zero_stuff2(src, din, s))) return rc;
+  }
+  if (pl->dconvs.size() != pl->ops.size()) { pl->dconvs.resize(pl->ops.size()); pl->dconv_ready.assign(pl->ops.size(), 0); }
+  ConvOp& c = pl->dconvs[i];
+  if (!pl->dconv_ready[i]) {
+    c = ConvOp();
+    c.in = din;
+    c.in.C = cpad;
+    c.out = gin;
+    c.out.C = sl.ci;
+    c.has_res = true;
+    c.res = c.out;
+    c.k = op.k;
+    c.stride = 1;
+    c.dil = op.dil;
+    c.act = MYOLO_ACT_NONE;
+    c.w = sl.w_dgrad;
+    c.bias = sl.zero_bias;
+    c.Ci_pad = cpad;
+    c.Co_pad = n_pad;
+    c.Co = sl.ci;
+    MYOLO_REQUIRE(din.H == gin.H && din.W == gin.W, "op %d: data-gradient geometry %dx%d vs %dx%d", i, din.H, din.W, gin.H, gin.W);
+    c.use_tc = !pl->force_simt && conv_tc_eligible(c);
+    if (c.use_tc && (rc = conv_tc_prepare(c, pl->num_sms))) return rc;
+    pl->dconv_ready[i] = 1;
+  }
+  return c.use_tc ? conv_tc_launch(c, s) : conv_simt_launch(c, s);
+}
+
+extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream) {
+  MYOLO_REQUIRE(pl && pl->train_fwd_done, "backward: call myolo_plan_train_forward first");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
+  const int n = (int)pl->ops.size();
+  // which buffers are produced by the input conversion (no data gradient needed into them)
+  std::vector<char> is_input_buf(pl->bufs.size(), 0);
+  for (const auto& op : pl->ops)
+    if (op.kind == MYOLO_OP_INPUT_FOCUS && op.out.buf >= 0) is_input_buf[op.out.buf] = 1;
+  int rc = 0;
+  for (int i = n - 1; i >= 0 && !rc; --i) {
+    const myolo_op& op = pl->ops[i];
+    TensorView a, b, c, d;
+    switch (op.kind) {
+      case MYOLO_OP_INPUT_FOCUS:
+        break;
+      case MYOLO_OP_SEG_UPSAMPLE:
+        if (!grad_seg) break;
+        if ((rc = grad_view(pl, op.in, &a))) break;
+        rc = launch_seg_upsample_bwd(grad_seg, op.aux[0], pl->H, pl->W, a, s);
+        break;
+      case MYOLO_OP_DETECT_DECODE:
+        if (!grad_raw || !grad_raw[op.aux[0]]) break;
+        if ((rc = grad_view(pl, op.in, &a))) break;
+        rc = launch_detect_raw_bwd(grad_raw[op.aux[0]], op.aux[1], op.aux[2], a, s);
+        break;
+      case MYOLO_OP_CONV:
+        rc = conv_backward(pl, i, !is_input_buf[op.in.buf], s);
+        break;
+      case MYOLO_OP_BN_ACT: {
+        const bool has_res = op.in2.buf >= 0;
+        if ((rc = resolve_view(pl, op.in, &a)) || (rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
+        if (has_res && (rc = grad_view(pl, op.in2, &d))) break;
+        const BnParams& bn = pl->bns[op.aux[0]];
+        rc = launch_bn_act_bwd(a, b, c, has_res ? &d : nullptr, bn, pl->bn_stats[i], op.act, pl->bn_stats[i] + 2 * bn.C, s);
+        break;
+      }
+      case MYOLO_OP_ACT:
+        if ((rc = resolve_view(pl, op.in, &a)) || (rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
+        rc = launch_act_bwd(a, b, c, op.act, s);
+        break;
+      case MYOLO_OP_CHANNEL_SCALE_OOP: {
+        TensorView f, av, gout, gf, ga;
+        if ((rc = resolve_view(pl, op.in, &f)) || (rc = resolve_view(pl, op.in2, &av)) || (rc = grad_view(pl, op.out, &gout)) ||
+            (rc = grad_view(pl, op.in, &gf)) || (rc = grad_view(pl, op.in2, &ga)))
+          break;
+        rc = launch_channel_scale_bwd(f, av, gout, gf, ga, s);
+        break;
+      }
+      case MYOLO_OP_UPSAMPLE_NEAREST:
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
+        rc = launch_nearest2x_bwd(a, b, s);
+        break;
+      case MYOLO_OP_BILINEAR:
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
+        rc = launch_bilinear_bwd(a, b, s);
+        break;
+      case MYOLO_OP_SPP_POOL: {
+        if ((rc = resolve_view(pl, op.in, &a)) || (rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
+        const size_t need = (size_t)a.B * a.H * a.W * a.C * sizeof(float);
+        if (pl->spp_scratch_bytes < need) {
+          if (pl->spp_scratch) cudaFree(pl->spp_scratch);
+          pl->spp_scratch = nullptr;
+          if (cudaMalloc(&pl->spp_scratch, need) != cudaSuccess) { set_error("backward: spp scratch allocation failed"); rc = MYOLO_E_CUDA; break; }
+          pl->spp_scratch_bytes = need;
+        }
+        rc = launch_spp_bwd(a, b, c, pl->spp_scratch, s);
+        break;
+      }
+      case MYOLO_OP_REGION_COMBINE:
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
+        rc = launch_region_combine_bwd(a, b, op.aux[2], pl->d_extra + op.aux[0], op.aux[1], s);
+        break;
+      case MYOLO_OP_REGION_SUM:
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
+        rc = launch_region_bwd(a, b, pl->d_extra + op.aux[0], op.aux[1], pl->d_extra + op.aux[2], op.aux[3], s);
+        break;
+      default:
+        set_error("backward: op %d of kind %d has no backward (training supports the PSP-head graphs)", i, op.kind);
+        rc = MYOLO_E_INVALID;
+    }
+  }
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,751 @@
+// Training-mode kernels (see train.h).  Correct-first implementations: the data gradients of all convolutions reuse the tcgen05
+// implicit-GEMM kernel (a conv of dY with flipped/transposed weights); weight gradients run on legacy mma.sync with split-K
+// atomics; everything else is plain coalesced CUDA.  Reference semantics: torch.autograd through models/common.py / models/yolo.py
+// in train mode (BatchNorm with batch statistics, eps 1e-3, momentum 0.03: reference utils/torch_utils.py:150-152).
+#include <algorithm>
+
+#include "train.h"
+
+namespace myolo {
+
+static inline int grid_for_t(long items, int block, int max_blocks = 148 * 32) {
+  long b = (items + block - 1) / block;
+  if (b > max_blocks) b = max_blocks;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+__device__ __forceinline__ __half* tv(const TensorView& v, int b, int y, int x) {
+  return reinterpret_cast<__half*>(v.base) + (((size_t)b * v.H + y) * v.W + x) * v.ctot;
+}
+__device__ __forceinline__ float* tvf(const TensorView& v, int b, int y, int x) {
+  return reinterpret_cast<float*>(v.base) + (((size_t)b * v.H + y) * v.W + x) * v.ctot;
+}
+__device__ __forceinline__ float ldv(const TensorView& v, int b, int y, int x, int c) {
+  return v.dtype == MYOLO_F32 ? tvf(v, b, y, x)[c] : __half2float(tv(v, b, y, x)[c]);
+}
+__device__ __forceinline__ void stv(const TensorView& v, int b, int y, int x, int c, float f) {
+  if (v.dtype == MYOLO_F32) tvf(v, b, y, x)[c] = f;
+  else tv(v, b, y, x)[c] = __float2half_rn(f);
+}
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == MYOLO_ACT_SILU) return z / (1.0f + __expf(-z));
+  if (act == MYOLO_ACT_SIGMOID) return 1.0f / (1.0f + __expf(-z));
+  return z;
+}
+__device__ __forceinline__ float act_grad(float z, int act) {   // d act(z) / dz
+  if (act == MYOLO_ACT_SILU) {
+    const float s = 1.0f / (1.0f + __expf(-z));
+    return s * (1.0f + z * (1.0f - s));
+  }
+  if (act == MYOLO_ACT_SIGMOID) {
+    const float s = 1.0f / (1.0f + __expf(-z));
+    return s * (1.0f - s);
+  }
+  return 1.0f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions over all pixels of an NHWC view:  out[k][c] = sum_p f_k(p, c)
+//   grid.x = channel groups of 32, grid.y = pixel slabs; each block reduces its slab and atomically adds 1 or 2 sums per channel
+// ------------------------------------------------------------------------------------------------
+template <int MODE>   // 0: (sum u, sum u^2)   1: (sum dz, sum dz*xhat) for BN backward   2: (sum dy) column sum (bias gradient)
+__global__ void chan_reduce_kernel(TensorView a, TensorView bview, const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, int act, float* out, long npix, int C) {
+  __shared__ float sh[2][8][32];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int lane_p = threadIdx.x >> 5;                      // 8 pixel lanes
+  const long per = (npix + gridDim.y - 1) / gridDim.y;
+  const long p0 = (long)blockIdx.y * per, p1 = min(npix, p0 + per);
+  float s0 = 0.f, s1 = 0.f;
+  if (c < C) {
+    float mean = 0.f, istd = 0.f, g = 0.f, bt = 0.f;
+    if (MODE == 1) { mean = stats[c]; istd = stats[C + c]; g = gamma[c]; bt = beta[c]; }
+    for (long p = p0 + lane_p; p < p1; p += 8) {
+      const size_t off = (size_t)p * a.ctot + c;
+      if (MODE == 0) {
+        const float u = __half2float(reinterpret_cast<const __half*>(a.base)[off]);
+        s0 += u; s1 += u * u;
+      } else if (MODE == 1) {
+        const float xh = (__half2float(reinterpret_cast<const __half*>(a.base)[off]) - mean) * istd;
+        const float dy = __half2float(reinterpret_cast<const __half*>(bview.base)[(size_t)p * bview.ctot + c]);
+        const float dz = dy * act_grad(g * xh + bt, act);
+        s0 += dz; s1 += dz * xh;
+      } else {
+        s0 += a.dtype == MYOLO_F32 ? reinterpret_cast<const float*>(a.base)[off] : __half2float(reinterpret_cast<const __half*>(a.base)[off]);
+      }
+    }
+  }
+  sh[0][lane_p][threadIdx.x & 31] = s0;
+  sh[1][lane_p][threadIdx.x & 31] = s1;
+  __syncthreads();
+  if (lane_p == 0 && c < C) {
+    for (int l = 1; l < 8; ++l) { s0 += sh[0][l][threadIdx.x & 31]; s1 += sh[1][l][threadIdx.x & 31]; }
+    atomicAdd(out + c, s0);
+    if (MODE != 2) atomicAdd(out + C + c, s1);
+  }
+}
+
+__global__ void bn_finalize_kernel(float* sums, float* stats, BnParams bn, long npix) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= bn.C) return;
+  const float n = (float)npix;
+  const float mean = sums[c] / n;
+  const float var = fmaxf(sums[bn.C + c] / n - mean * mean, 0.f);           // biased variance normalises (F.batch_norm, training=True)
+  stats[c] = mean;
+  stats[bn.C + c] = rsqrtf(var + bn.eps);
+  if (bn.running_mean) {                                                       // running stats: unbiased variance, momentum 0.03
+    bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * mean;
+    bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * var * (n / fmaxf(n - 1.f, 1.f));
+  }
+}
+
+int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s) {
+  MYOLO_REQUIRE(u.dtype == MYOLO_F16 && bn.set && bn.C == u.C, "bn_stats: bad view / BN parameters not set");
+  const long npix = (long)u.B * u.H * u.W;
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)u.C * sizeof(float), s));
+  dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
+  chan_reduce_kernel<0><<<g, 256, 0, s>>>(u, u, nullptr, nullptr, nullptr, 0, scratch, npix, u.C);
+  MYOLO_LAUNCH_CHECK();
+  bn_finalize_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, stats, bn, npix);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void bn_act_fwd_kernel(TensorView u, TensorView res, bool has_res, TensorView y, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, const float* __restrict__ stats, int act) {
+  const long total = (long)u.B * u.H * u.W * (u.C / 8);
+  const int nv = u.C / 8, C = u.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const long p = i / nv;
+    const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(u.base) + (size_t)p * u.ctot + v * 8);
+    const __half* h = reinterpret_cast<const __half*>(&q);
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (has_res) r = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(res.base) + (size_t)p * res.ctot + v * 8);
+    const __half* hr = reinterpret_cast<const __half*>(&r);
+    uint4 o;
+    __half* ho = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = v * 8 + k;
+      const float z = gamma[c] * (__half2float(h[k]) - stats[c]) * stats[C + c] + beta[c];
+      float val = act_fwd(z, act);
+      if (has_res) val += __half2float(hr[k]);
+      ho[k] = __float2half_rn(val);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(y.base) + (size_t)p * y.ctot + v * 8) = o;
+  }
+}
+int launch_bn_act_fwd(const TensorView& u, const TensorView* res, const TensorView& y, const BnParams& bn, const float* stats, int act,
+                      cudaStream_t s) {
+  MYOLO_REQUIRE(u.C % 8 == 0 && u.C == y.C && u.ctot % 8 == 0 && y.ctot % 8 == 0 && (!res || (res->C == u.C && res->ctot % 8 == 0)),
+                "bn_act_fwd: bad views");
+  bn_act_fwd_kernel<<<grid_for_t((long)u.B * u.H * u.W * (u.C / 8), 256), 256, 0, s>>>(u, res ? *res : u, res != nullptr, y, bn.gamma, bn.beta,
+                                                                                     stats, act);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ stats, const float* __restrict__ sums, int act, float inv_n) {
+  const long total = (long)u.B * u.H * u.W * (u.C / 8);
+  const int nv = u.C / 8, C = u.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const long p = i / nv;
+    const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(u.base) + (size_t)p * u.ctot + v * 8);
+    const uint4 g = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(dy.base) + (size_t)p * dy.ctot + v * 8);
+    const __half* h = reinterpret_cast<const __half*>(&q);
+    const __half* hg = reinterpret_cast<const __half*>(&g);
+    uint4 o;
+    __half* ho = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = v * 8 + k;
+      const float xh = (__half2float(h[k]) - stats[c]) * stats[C + c];
+      const float dz = __half2float(hg[k]) * act_grad(gamma[c] * xh + beta[c], act);
+      ho[k] = __float2half_rn(gamma[c] * stats[C + c] * (dz - sums[c] * inv_n - xh * sums[C + c] * inv_n));
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(du.base) + (size_t)p * du.ctot + v * 8) = o;
+  }
+}
+__global__ void bn_param_grad_kernel(const float* sums, BnParams bn) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= bn.C) return;
+  if (bn.d_beta) bn.d_beta[c] += sums[c];
+  if (bn.d_gamma) bn.d_gamma[c] += sums[bn.C + c];
+}
+__global__ void add_acc_kernel(TensorView dst, TensorView src) {   // dst += src (fp16 NHWC)
+  const long total = (long)dst.B * dst.H * dst.W * (dst.C / 8);
+  const int nv = dst.C / 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    const long p = i / nv;
+    uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(dst.base) + (size_t)p * dst.ctot + v * 8);
+    uint4 a = *dp;
+    const uint4 b = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src.base) + (size_t)p * src.ctot + v * 8);
+    __half2* ha = reinterpret_cast<__half2*>(&a);
+    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = __half22float2(ha[k]), fb = __half22float2(hb[k]);
+      ha[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+    }
+    *dp = a;
+  }
+}
+int launch_bn_act_bwd(const TensorView& u, const TensorView& dy, const TensorView& du, const TensorView* d_res, const BnParams& bn,
+                      const float* stats, int act, float* scratch, cudaStream_t s) {
+  MYOLO_REQUIRE(u.C % 8 == 0 && dy.C == u.C && du.C == u.C && dy.ctot % 8 == 0 && du.ctot % 8 == 0, "bn_act_bwd: bad views");
+  const long npix = (long)u.B * u.H * u.W;
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)u.C * sizeof(float), s));
+  dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
+  chan_reduce_kernel<1><<<g, 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C);
+  MYOLO_LAUNCH_CHECK();
+  bn_act_bwd_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(u, dy, du, bn.gamma, bn.beta, stats, scratch, act, 1.0f / (float)npix);
+  MYOLO_LAUNCH_CHECK();
+  bn_param_grad_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, bn);
+  MYOLO_LAUNCH_CHECK();
+  if (d_res) {
+    add_acc_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(*d_res, dy);
+    MYOLO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small elementwise ops (generic dtype through ldv/stv: used on tiny maps or fp32 head buffers)
+// ------------------------------------------------------------------------------------------------
+__global__ void act_fwd_kernel(TensorView x, TensorView y, int act) {
+  const long total = (long)x.B * x.H * x.W * x.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % x.C);
+    long p = i / x.C;
+    const int xx = (int)(p % x.W); p /= x.W;
+    const int yy = (int)(p % x.H);
+    const int b = (int)(p / x.H);
+    stv(y, b, yy, xx, c, act_fwd(ldv(x, b, yy, xx, c), act));
+  }
+}
+int launch_act_fwd(const TensorView& x, const TensorView& y, int act, cudaStream_t s) {
+  act_fwd_kernel<<<grid_for_t((long)x.B * x.H * x.W * x.C, 256), 256, 0, s>>>(x, y, act);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void act_bwd_kernel(TensorView x, TensorView dy, TensorView dx, int act) {
+  const long total = (long)x.B * x.H * x.W * x.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % x.C);
+    long p = i / x.C;
+    const int xx = (int)(p % x.W); p /= x.W;
+    const int yy = (int)(p % x.H);
+    const int b = (int)(p / x.H);
+    stv(dx, b, yy, xx, c, ldv(dx, b, yy, xx, c) + ldv(dy, b, yy, xx, c) * act_grad(ldv(x, b, yy, xx, c), act));
+  }
+}
+int launch_act_bwd(const TensorView& x, const TensorView& dy, const TensorView& dx, int act, cudaStream_t s) {
+  act_bwd_kernel<<<grid_for_t((long)x.B * x.H * x.W * x.C, 256), 256, 0, s>>>(x, dy, dx, act);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void channel_scale_oop_kernel(TensorView f, TensorView a, TensorView out) {
+  const long total = (long)f.B * f.H * f.W * f.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % f.C);
+    long p = i / f.C;
+    const int x = (int)(p % f.W); p /= f.W;
+    const int y = (int)(p % f.H);
+    const int b = (int)(p / f.H);
+    const float fv = ldv(f, b, y, x, c);
+    stv(out, b, y, x, c, fmaf(fv, ldv(a, b, 0, 0, c), fv));
+  }
+}
+int launch_channel_scale_oop(const TensorView& f, const TensorView& a, const TensorView& out, cudaStream_t s) {
+  MYOLO_REQUIRE(a.H == 1 && a.W == 1 && a.C >= f.C && out.C == f.C, "channel_scale_oop: bad views");
+  channel_scale_oop_kernel<<<grid_for_t((long)f.B * f.H * f.W * f.C, 256), 256, 0, s>>>(f, a, out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+// df += dout*(1+a);  da[b,c] += sum_p dout*f    (one block per (b, 32-channel group))
+__global__ void channel_scale_bwd_kernel(TensorView f, TensorView a, TensorView dout, TensorView df, TensorView da) {
+  __shared__ float sh[8][32];
+  const int cg = blockIdx.x % ((f.C + 31) / 32), b = blockIdx.x / ((f.C + 31) / 32);
+  const int c = cg * 32 + (threadIdx.x & 31), lp = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (c < f.C) {
+    const float sc = 1.0f + ldv(a, b, 0, 0, c);
+    for (int p = lp; p < f.H * f.W; p += 8) {
+      const int y = p / f.W, x = p % f.W;
+      const float g = ldv(dout, b, y, x, c);
+      acc += g * ldv(f, b, y, x, c);
+      stv(df, b, y, x, c, ldv(df, b, y, x, c) + g * sc);
+    }
+  }
+  sh[lp][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (lp == 0 && c < f.C) {
+    for (int l = 1; l < 8; ++l) acc += sh[l][threadIdx.x & 31];
+    stv(da, b, 0, 0, c, ldv(da, b, 0, 0, c) + acc);
+  }
+}
+int launch_channel_scale_bwd(const TensorView& f, const TensorView& a, const TensorView& dout, const TensorView& df, const TensorView& da,
+                             cudaStream_t s) {
+  channel_scale_bwd_kernel<<<f.B * ceil_div(f.C, 32), 256, 0, s>>>(f, a, dout, df, da);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void nearest2x_bwd_kernel(TensorView dout, TensorView din) {
+  const long total = (long)din.B * din.H * din.W * din.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % din.C);
+    long p = i / din.C;
+    const int x = (int)(p % din.W); p /= din.W;
+    const int y = (int)(p % din.H);
+    const int b = (int)(p / din.H);
+    const float g = ldv(dout, b, 2 * y, 2 * x, c) + ldv(dout, b, 2 * y, 2 * x + 1, c) + ldv(dout, b, 2 * y + 1, 2 * x, c) +
+                    ldv(dout, b, 2 * y + 1, 2 * x + 1, c);
+    stv(din, b, y, x, c, ldv(din, b, y, x, c) + g);
+  }
+}
+int launch_nearest2x_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s) {
+  MYOLO_REQUIRE(dout.H == 2 * din.H && dout.W == 2 * din.W && dout.C == din.C, "nearest2x_bwd: bad views");
+  nearest2x_bwd_kernel<<<grid_for_t((long)din.B * din.H * din.W * din.C, 256), 256, 0, s>>>(dout, din);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// adjoint of bilinear(align_corners=True): every source pixel gathers from the destination pixels that read it
+__device__ __forceinline__ void lerp_src(int dst, int n_in, int n_out, int* i0, int* i1, float* l0, float* l1) {
+  const float scale = n_out > 1 ? (float)(n_in - 1) / (float)(n_out - 1) : 0.f;
+  const float src = scale * (float)dst;
+  *i0 = min((int)src, n_in - 1);
+  *i1 = *i0 + (*i0 < n_in - 1 ? 1 : 0);
+  *l1 = src - (float)*i0;
+  *l0 = 1.0f - *l1;
+}
+__device__ __forceinline__ void dst_range(int src_i, int n_in, int n_out, int* lo, int* hi) {
+  // destination indices d whose i0 or i1 can equal src_i: src(d) in (src_i-1, src_i+1)
+  if (n_out <= 1 || n_in <= 1) { *lo = 0; *hi = n_out - 1; return; }
+  const float inv = (float)(n_out - 1) / (float)(n_in - 1);
+  *lo = max(0, (int)floorf((src_i - 1) * inv) - 1);
+  *hi = min(n_out - 1, (int)ceilf((src_i + 1) * inv) + 1);
+}
+__global__ void bilinear_bwd_kernel(TensorView dout, TensorView din) {
+  const long total = (long)din.B * din.H * din.W * din.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % din.C);
+    long p = i / din.C;
+    const int x = (int)(p % din.W); p /= din.W;
+    const int y = (int)(p % din.H);
+    const int b = (int)(p / din.H);
+    int ylo, yhi, xlo, xhi;
+    dst_range(y, din.H, dout.H, &ylo, &yhi);
+    dst_range(x, din.W, dout.W, &xlo, &xhi);
+    float acc = 0.f;
+    for (int dy = ylo; dy <= yhi; ++dy) {
+      int a0, a1; float w0, w1;
+      lerp_src(dy, din.H, dout.H, &a0, &a1, &w0, &w1);
+      const float wy = (a0 == y ? w0 : 0.f) + (a1 == y ? w1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int dx = xlo; dx <= xhi; ++dx) {
+        int b0, b1; float v0, v1;
+        lerp_src(dx, din.W, dout.W, &b0, &b1, &v0, &v1);
+        const float wx = (b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f);
+        if (wx != 0.f) acc += wy * wx * ldv(dout, b, dy, dx, c);
+      }
+    }
+    stv(din, b, y, x, c, ldv(din, b, y, x, c) + acc);
+  }
+}
+int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s) {
+  MYOLO_REQUIRE(dout.C == din.C, "bilinear_bwd: bad views");
+  bilinear_bwd_kernel<<<grid_for_t((long)din.B * din.H * din.W * din.C, 128), 128, 0, s>>>(dout, din);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// SPP: the three pools are max pools of the SAME input x with windows 5/9/13 (cascade == direct); each output routes its gradient
+// to the first maximum of its window in row-major scan order (ATen max_pool2d backward).  fp32 scratch accumulates, then dx += scratch.
+__global__ void spp_bwd_scatter_kernel(TensorView x, TensorView dout3, float* scratch) {
+  const long total = (long)x.B * x.H * x.W * x.C * 3;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % x.C);
+    long p = i / x.C;
+    const int k3 = (int)(p % 3); p /= 3;
+    const int xx = (int)(p % x.W); p /= x.W;
+    const int yy = (int)(p % x.H);
+    const int b = (int)(p / x.H);
+    const float g = __half2float(tv(dout3, b, yy, xx)[k3 * x.C + c]);
+    if (g == 0.f) continue;
+    const int r = 2 + 2 * k3;   // radius 2 / 4 / 6
+    float best = -INFINITY;
+    int by = yy, bx = xx;
+    for (int y2 = max(0, yy - r); y2 <= min(x.H - 1, yy + r); ++y2)
+      for (int x2 = max(0, xx - r); x2 <= min(x.W - 1, xx + r); ++x2) {
+        const float v = __half2float(tv(x, b, y2, x2)[c]);
+        if (v > best) { best = v; by = y2; bx = x2; }
+      }
+    atomicAdd(scratch + (((size_t)b * x.H + by) * x.W + bx) * x.C + c, g);
+  }
+}
+__global__ void add_scratch_kernel(TensorView dx, const float* scratch) {
+  const long total = (long)dx.B * dx.H * dx.W * dx.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dx.C);
+    const long p = i / dx.C;
+    __half* d = reinterpret_cast<__half*>(dx.base) + (size_t)p * dx.ctot + c;
+    *d = __float2half_rn(__half2float(*d) + scratch[i]);
+  }
+}
+int launch_spp_bwd(const TensorView& x, const TensorView& dout3, const TensorView& dx, float* scratch, cudaStream_t s) {
+  const long n = (long)x.B * x.H * x.W * x.C;
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (size_t)n * sizeof(float), s));
+  spp_bwd_scatter_kernel<<<grid_for_t(n * 3, 128), 128, 0, s>>>(x, dout3, scratch);
+  MYOLO_LAUNCH_CHECK();
+  add_scratch_kernel<<<grid_for_t(n, 256), 256, 0, s>>>(dx, scratch);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// adaptive pools: forward atoms = sum over cell, bins = sum(atoms)/count.
+__global__ void region_combine_bwd_kernel(TensorView dbins, TensorView datoms, const int* __restrict__ bins, int nbins) {
+  const long total = (long)dbins.B * nbins * dbins.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dbins.C);
+    const int bin = (int)((i / dbins.C) % nbins);
+    const int b = (int)(i / ((long)dbins.C * nbins));
+    const int* bd = bins + bin * 5;
+    const float g = ldv(dbins, b, bin / dbins.W, bin % dbins.W, c) / (float)bd[4];
+    for (int ay = bd[0]; ay < bd[1]; ++ay)
+      for (int ax = bd[2]; ax < bd[3]; ++ax) atomicAdd(tvf(datoms, b, ay, ax) + c, g);   // bins of one level are disjoint, levels are separate launches
+  }
+}
+int launch_region_combine_bwd(const TensorView& dbins, const TensorView& datoms, int atoms_nx, const int* d_bins, int nbins, cudaStream_t s) {
+  MYOLO_REQUIRE(datoms.dtype == MYOLO_F32, "region_combine_bwd: atoms gradient must be fp32");
+  region_combine_bwd_kernel<<<grid_for_t((long)dbins.B * nbins * dbins.C, 256), 256, 0, s>>>(dbins, datoms, d_bins, nbins);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void region_bwd_kernel(TensorView datoms, TensorView dx, const int* __restrict__ yb, int ny, const int* __restrict__ xb, int nx) {
+  const long total = (long)dx.B * dx.H * dx.W * dx.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dx.C);
+    long p = i / dx.C;
+    const int x = (int)(p % dx.W); p /= dx.W;
+    const int y = (int)(p % dx.H);
+    const int b = (int)(p / dx.H);
+    int ay = 0, ax = 0;
+    while (ay + 1 < ny && y >= yb[ay + 1]) ++ay;
+    while (ax + 1 < nx && x >= xb[ax + 1]) ++ax;
+    stv(dx, b, y, x, c, ldv(dx, b, y, x, c) + tvf(datoms, b, ay, ax)[c]);
+  }
+}
+int launch_region_bwd(const TensorView& datoms, const TensorView& dx, const int* d_yb, int ny, const int* d_xb, int nx, cudaStream_t s) {
+  region_bwd_kernel<<<grid_for_t((long)dx.B * dx.H * dx.W * dx.C, 256), 256, 0, s>>>(datoms, dx, d_yb, ny, d_xb, nx);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void seg_upsample_bwd_kernel(const float* __restrict__ dseg, int ncls, int H, int W, TensorView dlo) {
+  const long total = (long)dlo.B * dlo.H * dlo.W * ncls;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ncls);
+    long p = i / ncls;
+    const int x = (int)(p % dlo.W); p /= dlo.W;
+    const int y = (int)(p % dlo.H);
+    const int b = (int)(p / dlo.H);
+    int ylo, yhi, xlo, xhi;
+    dst_range(y, dlo.H, H, &ylo, &yhi);
+    dst_range(x, dlo.W, W, &xlo, &xhi);
+    const float* plane = dseg + ((size_t)b * ncls + c) * H * W;
+    float acc = 0.f;
+    for (int dy = ylo; dy <= yhi; ++dy) {
+      int a0, a1; float w0, w1;
+      lerp_src(dy, dlo.H, H, &a0, &a1, &w0, &w1);
+      const float wy = (a0 == y ? w0 : 0.f) + (a1 == y ? w1 : 0.f);
+      if (wy == 0.f) continue;
+      for (int dx = xlo; dx <= xhi; ++dx) {
+        int b0, b1; float v0, v1;
+        lerp_src(dx, dlo.W, W, &b0, &b1, &v0, &v1);
+        const float wx = (b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f);
+        if (wx != 0.f) acc += wy * wx * plane[(size_t)dy * W + dx];
+      }
+    }
+    tvf(dlo, b, y, x)[c] += acc;
+  }
+}
+int launch_seg_upsample_bwd(const float* dseg, int n_cls, int H, int W, const TensorView& dlo, cudaStream_t s) {
+  MYOLO_REQUIRE(dlo.dtype == MYOLO_F32, "seg_upsample_bwd: low-res logits gradient must be fp32");
+  seg_upsample_bwd_kernel<<<grid_for_t((long)dlo.B * dlo.H * dlo.W * n_cls, 128), 128, 0, s>>>(dseg, n_cls, H, W, dlo);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void detect_raw_bwd_kernel(const float* __restrict__ draw, int na, int no, TensorView dconv) {
+  const long total = (long)dconv.B * na * dconv.H * dconv.W * no;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % no);
+    long p = i / no;
+    const int x = (int)(p % dconv.W); p /= dconv.W;
+    const int y = (int)(p % dconv.H); p /= dconv.H;
+    const int a = (int)(p % na);
+    const int b = (int)(p / na);
+    tvf(dconv, b, y, x)[a * no + o] += draw[i];
+  }
+}
+int launch_detect_raw_bwd(const float* draw, int na, int no, const TensorView& dconv, cudaStream_t s) {
+  MYOLO_REQUIRE(dconv.dtype == MYOLO_F32 && dconv.ctot >= na * no, "detect_raw_bwd: bad view");
+  detect_raw_bwd_kernel<<<grid_for_t((long)dconv.B * na * dconv.H * dconv.W * no, 256), 256, 0, s>>>(draw, na, no, dconv);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void cast_kernel(TensorView src, TensorView dst, int acc) {
+  const int C = min(src.C, dst.C);
+  const long total = (long)dst.B * dst.H * dst.W * dst.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dst.C);
+    long p = i / dst.C;
+    const int x = (int)(p % dst.W); p /= dst.W;
+    const int y = (int)(p % dst.H);
+    const int b = (int)(p / dst.H);
+    const float v = c < C ? ldv(src, b, y, x, c) : 0.f;
+    stv(dst, b, y, x, c, acc ? ldv(dst, b, y, x, c) + v : v);
+  }
+}
+int launch_cast_f32_to_f16(const TensorView& src, const TensorView& dst, cudaStream_t s) {
+  cast_kernel<<<grid_for_t((long)dst.B * dst.H * dst.W * dst.C, 256), 256, 0, s>>>(src, dst, 0);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+int launch_cast_f16_to_f32_acc(const TensorView& src, const TensorView& dst, cudaStream_t s) {
+  cast_kernel<<<grid_for_t((long)dst.B * dst.H * dst.W * dst.C, 256), 256, 0, s>>>(src, dst, 1);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void zero_stuff2_kernel(TensorView src, TensorView dst) {
+  const int nv = dst.C / 8;
+  const long total = (long)dst.B * dst.H * dst.W * nv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nv);
+    long p = i / nv;
+    const int x = (int)(p % dst.W); p /= dst.W;
+    const int y = (int)(p % dst.H);
+    const int b = (int)(p / dst.H);
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (!(x & 1) && !(y & 1)) val = reinterpret_cast<const uint4*>(tv(src, b, y >> 1, x >> 1))[v];
+    reinterpret_cast<uint4*>(tv(dst, b, y, x))[v] = val;
+  }
+}
+int launch_zero_stuff2(const TensorView& src, const TensorView& dst, cudaStream_t s) {
+  MYOLO_REQUIRE(dst.H == 2 * src.H && dst.W == 2 * src.W && dst.C == src.C && dst.C % 8 == 0 && src.ctot % 8 == 0 && dst.ctot % 8 == 0,
+                "zero_stuff2: bad views");
+  zero_stuff2_kernel<<<grid_for_t((long)dst.B * dst.H * dst.W * (dst.C / 8), 256), 256, 0, s>>>(src, dst);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// dgrad weights: W'[ci][tap'][co] = W[co][ci][k*k-1-tap']   (fp16, [Ci_pad_out][k*k][Co_pad_in]); zero bias of length Ci_pad_out
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, int co, int ci, int k, __half* wp, float* zb, int ci_pad_out, int co_pad_in) {
+  const int taps = k * k;
+  const long total = (long)ci_pad_out * taps * co_pad_in;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % co_pad_in);
+    const int t = (int)((i / co_pad_in) % taps);
+    const int c = (int)(i / ((long)co_pad_in * taps));
+    float v = 0.f;
+    if (c < ci && o < co) v = w[((size_t)o * ci + c) * taps + (taps - 1 - t)];
+    wp[i] = __float2half_rn(v);
+  }
+  for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ci_pad_out; c += gridDim.x * blockDim.x) zb[c] = 0.f;
+}
+int pack_dgrad_weights(const float* w, int co, int ci, int k, __half* wp, float* zero_bias, int ci_pad_out, int co_pad_in, cudaStream_t s) {
+  pack_dgrad_kernel<<<grid_for_t((long)ci_pad_out * k * k * co_pad_in, 256, 4096), 256, 0, s>>>(w, co, ci, k, wp, zero_bias, ci_pad_out, co_pad_in);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient: dW[co][ci][tap] += sum over output pixels p of dY[p][co] * X[in(p, tap)][ci]
+// one CTA = 64 co x 64 ci x one tap x one slab of pixels; mma.sync.m16n8k16 with ldmatrix.trans from [pixel][channel] smem tiles
+// ------------------------------------------------------------------------------------------------
+static constexpr int kWgPitch = 72;   // halves per smem row (64 + 8 pad): conflict-free 8x8 ldmatrix
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(128) conv_wgrad_kernel(TensorView x, TensorView dy, int k, int stride, int dil, float* dW, int co, int ci,
+                                                         int splits) {
+  __shared__ __align__(16) __half s_dy[32 * kWgPitch];
+  __shared__ __align__(16) __half s_x[32 * kWgPitch];
+  const int taps = k * k;
+  const int co0 = blockIdx.x * 64;
+  const int ci_tiles = (ci + 63) / 64;
+  const int ci0 = (blockIdx.y % ci_tiles) * 64, tap = blockIdx.y / ci_tiles;
+  const int ky = tap / k, kx = tap % k, pad = dil * (k / 2);
+  const long npix = (long)dy.B * dy.H * dy.W;
+  const long chunks = (npix + 31) / 32;
+  const long c_begin = chunks * blockIdx.z / splits, c_end = chunks * (blockIdx.z + 1) / splits;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;   // warp tile origin inside the 64 x 64 CTA tile
+  float acc[2][4][4];
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[a][b][e] = 0.f;
+  const uint32_t sdy = smem_u32(s_dy), sx = smem_u32(s_x);
+  for (long ch = c_begin; ch < c_end; ++ch) {
+    // stage 32 pixels: 8 x 16-byte units per row, 2 units per thread per matrix
+    for (int u = threadIdx.x; u < 32 * 8; u += 128) {
+      const int r = u >> 3, v = u & 7;
+      const long p = ch * 32 + r;
+      uint4 qd = make_uint4(0, 0, 0, 0), qx = make_uint4(0, 0, 0, 0);
+      if (p < npix) {
+        const int ox = (int)(p % dy.W);
+        const int oy = (int)((p / dy.W) % dy.H);
+        const int b = (int)(p / ((long)dy.W * dy.H));
+        if (co0 + v * 8 < co) qd = *reinterpret_cast<const uint4*>(tv(dy, b, oy, ox) + co0 + v * 8);
+        const int iy = oy * stride - pad + ky * dil, ix = ox * stride - pad + kx * dil;
+        if (iy >= 0 && iy < x.H && ix >= 0 && ix < x.W && ci0 + v * 8 < ci) qx = *reinterpret_cast<const uint4*>(tv(x, b, iy, ix) + ci0 + v * 8);
+      }
+      *reinterpret_cast<uint4*>(s_dy + r * kWgPitch + v * 8) = qd;
+      *reinterpret_cast<uint4*>(s_x + r * kWgPitch + v * 8) = qx;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k0 = 0; k0 < 32; k0 += 16) {
+      uint32_t af[2][4], bf[4][2];
+      // A(m = co, k = pixel) from s_dy[k][m] via .trans: matrices (k0,m0) (k0,m0+8) (k0+8,m0) (k0+8,m0+8)
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const int m0 = wm + mt * 16;
+        const int row = k0 + (lane & 7) + ((lane >> 4) << 3), col = m0 + (((lane >> 3) & 1) << 3);
+        ldsm_x4_trans(sdy + (row * kWgPitch + col) * 2, af[mt][0], af[mt][1], af[mt][2], af[mt][3]);
+      }
+      // B(k = pixel, n = ci) from s_x[k][n] via .trans: matrices (k0,n0) (k0+8,n0) (k0,n0+8) (k0+8,n0+8)
+#pragma unroll
+      for (int nt2 = 0; nt2 < 2; ++nt2) {
+        const int n0 = wn + nt2 * 16;
+        const int row = k0 + (lane & 7) + (((lane >> 3) & 1) << 3), col = n0 + ((lane >> 4) << 3);
+        ldsm_x4_trans(sx + (row * kWgPitch + col) * 2, bf[2 * nt2][0], bf[2 * nt2][1], bf[2 * nt2 + 1][0], bf[2 * nt2 + 1][1]);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(acc[mt][nt], af[mt][0], af[mt][1], af[mt][2], af[mt][3], bf[nt][0], bf[nt][1]);
+    }
+    __syncthreads();
+  }
+  // C fragment: rows g, g+8; cols 2t, 2t+1
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int o = co0 + wm + mt * 16 + g + ((e >> 1) << 3);
+        const int c = ci0 + wn + nt * 8 + 2 * t + (e & 1);
+        if (o < co && c < ci) atomicAdd(dW + ((size_t)o * ci + c) * taps + tap, acc[mt][nt][e]);
+      }
+}
+
+int launch_conv_wgrad(const TensorView& x, const TensorView& dy, int k, int stride, int dil, float* dW, int co, int ci, float* dbias,
+                      cudaStream_t s) {
+  MYOLO_REQUIRE(x.dtype == MYOLO_F16 && dy.dtype == MYOLO_F16 && x.ctot % 8 == 0 && dy.ctot % 8 == 0, "conv_wgrad: fp16 NHWC views expected");
+  MYOLO_REQUIRE(x.C >= ci && dy.C >= co, "conv_wgrad: views narrower than the weight (%d<%d or %d<%d)", x.C, ci, dy.C, co);
+  const long npix = (long)dy.B * dy.H * dy.W;
+  const int tiles = ceil_div(co, 64) * ceil_div(ci, 64) * k * k;
+  long chunks = (npix + 31) / 32;
+  int splits = (int)std::min<long>(chunks, std::max<long>(1, (148L * 8) / tiles));
+  dim3 grid(ceil_div(co, 64), ceil_div(ci, 64) * k * k, splits);
+  conv_wgrad_kernel<<<grid, 128, 0, s>>>(x, dy, k, stride, dil, dW, co, ci, splits);
+  MYOLO_LAUNCH_CHECK();
+  if (dbias) {
+    dim3 g(ceil_div(co, 32), (unsigned)std::min<long>(128, std::max<long>(1, npix / 256)));
+    chan_reduce_kernel<2><<<g, 256, 0, s>>>(dy, dy, nullptr, nullptr, nullptr, 0, dbias, npix, co);
+    MYOLO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// generic conv backward for tiny maps and fp32 tensors (PPM bins, FFM attention FCs): reads the fp32 master weights directly
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_small_dgrad_kernel(TensorView dy, TensorView dx, const float* __restrict__ w, int co, int ci, int k, int stride, int dil) {
+  const long total = (long)dx.B * dx.H * dx.W * ci;
+  const int pad = dil * (k / 2), taps = k * k;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % ci);
+    long p = i / ci;
+    const int x = (int)(p % dx.W); p /= dx.W;
+    const int y = (int)(p % dx.H);
+    const int b = (int)(p / dx.H);
+    float acc = 0.f;
+    for (int ky = 0; ky < k; ++ky) {
+      const int ny = y + pad - ky * dil;
+      if (ny < 0 || ny % stride) continue;
+      const int oy = ny / stride;
+      if (oy >= dy.H) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int nx = x + pad - kx * dil;
+        if (nx < 0 || nx % stride) continue;
+        const int ox = nx / stride;
+        if (ox >= dy.W) continue;
+        for (int o = 0; o < co; ++o) acc += ldv(dy, b, oy, ox, o) * w[((size_t)o * ci + c) * taps + ky * k + kx];
+      }
+    }
+    stv(dx, b, y, x, c, ldv(dx, b, y, x, c) + acc);
+  }
+}
+__global__ void conv_small_wgrad_kernel(TensorView x, TensorView dy, float* dW, int co, int ci, int k, int stride, int dil) {
+  const int taps = k * k, pad = dil * (k / 2);
+  const long total = (long)co * ci * taps;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const int c = (int)((i / taps) % ci);
+    const int o = (int)(i / ((long)taps * ci));
+    const int ky = t / k, kx = t % k;
+    float acc = 0.f;
+    for (int b = 0; b < dy.B; ++b)
+      for (int oy = 0; oy < dy.H; ++oy) {
+        const int iy = oy * stride - pad + ky * dil;
+        if (iy < 0 || iy >= x.H) continue;
+        for (int ox = 0; ox < dy.W; ++ox) {
+          const int ix = ox * stride - pad + kx * dil;
+          if (ix < 0 || ix >= x.W) continue;
+          acc += ldv(dy, b, oy, ox, o) * ldv(x, b, iy, ix, c);
+        }
+      }
+    dW[i] += acc;
+  }
+}
+int launch_conv_small_bwd(const TensorView& x, const TensorView& dy, const TensorView* dx, const float* w, float* dW, float* dbias, int co,
+                          int ci, int k, int stride, int dil, cudaStream_t s) {
+  if (dx) {
+    conv_small_dgrad_kernel<<<grid_for_t((long)dx->B * dx->H * dx->W * ci, 128), 128, 0, s>>>(dy, *dx, w, co, ci, k, stride, dil);
+    MYOLO_LAUNCH_CHECK();
+  }
+  conv_small_wgrad_kernel<<<grid_for_t((long)co * ci * k * k, 128), 128, 0, s>>>(x, dy, dW, co, ci, k, stride, dil);
+  MYOLO_LAUNCH_CHECK();
+  if (dbias) {
+    const long npix = (long)dy.B * dy.H * dy.W;
+    dim3 g(ceil_div(co, 32), 1);
+    chan_reduce_kernel<2><<<g, 256, 0, s>>>(dy, dy, nullptr, nullptr, nullptr, 0, dbias, npix, co);
+    MYOLO_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace myolo

@@ -10,8 +10,9 @@ from .plan import build_plan, to_ctypes
 
 
 class CompiledPlan:
-    def __init__(self, model, B, H, W, noalias=False):
-        self.pb = build_plan(model, B, H, W, noalias=noalias)
+    def __init__(self, model, B, H, W, noalias=False, train=False):
+        self.train = train
+        self.pb = build_plan(model, B, H, W, noalias=noalias, train=train)
         self.ops, self.bufs, self.extra = to_ctypes(self.pb)
         L = _lib.lib()
         h = C.c_void_p()
@@ -116,6 +117,65 @@ class Engine:
             out.append(amax)
         return out
 
+    # ---- training -----------------------------------------------------------------------
+    def train_plan_for(self, B, H, W) -> CompiledPlan:
+        key = ("train", B, H, W)
+        if key not in self.plans:
+            self.plans[key] = CompiledPlan(self.model, B, H, W, train=True)
+        return self.plans[key]
+
+    def ensure_flat_grads(self):
+        """every parameter's .grad is a view into ONE flat fp32 buffer (what the data-parallel all-reduce moves, reference
+        train.py:243-245 DDP semantics) that the backward kernels accumulate into."""
+        params = [p for p in self.model.parameters() if p.requires_grad]
+        if getattr(self, "_flat_grad", None) is not None and all(p.grad is not None and p.grad.data_ptr() == g.data_ptr()
+                                                                  for p, g in zip(params, self._grad_views)):
+            return self._flat_grad
+        for p in params:
+            assert p.dtype == torch.float32 and p.is_cuda, "training keeps fp32 master parameters on the GPU"
+        n = sum(p.numel() for p in params)
+        old = [p.grad for p in params]
+        self._flat_grad = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+        self._grad_views, off = [], 0
+        for p, g in zip(params, old):
+            v = self._flat_grad[off:off + p.numel()].view_as(p)
+            if g is not None:
+                v.copy_(g)
+            p.grad = v
+            self._grad_views.append(v)
+            off += p.numel()
+        return self._flat_grad
+
+    def train_forward(self, x: torch.Tensor):
+        assert x.is_cuda and x.dim() == 4, "expected a CUDA (B,3,H,W) tensor"
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        p = self.train_plan_for(B, H, W)
+        self.ensure_flat_grads()
+        L = _lib.lib()
+        sp = _lib.stream_ptr()
+        p.upload_weights()                       # parameters changed since the last step: re-pack (fp16, K-major, no BN folding)
+        for i, s in enumerate(p.pb.slots):
+            _lib.check(L.myolo_plan_set_conv_grad(p.handle, i, _lib.ptr(s.conv.weight.grad), _lib.ptr(s.conv.bias.grad if s.conv.bias is not None else None)))
+        for i, bn in enumerate(p.pb.bn_slots):
+            _lib.check(L.myolo_plan_set_bn(p.handle, i, bn.num_features, _lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
+                                           _lib.ptr(bn.running_var), _lib.ptr(bn.weight.grad), _lib.ptr(bn.bias.grad), float(bn.momentum), float(bn.eps)))
+            bn.num_batches_tracked += 1
+        det, seg_head = self.model.model[-1], self.model.model[-2]
+        dec = [o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]
+        raws = [torch.empty((B, det.na, v.h, v.w, det.no), dtype=torch.float32, device=x.device) for v in dec]
+        seg = torch.empty((B, seg_head.c_out, H, W), dtype=torch.float32, device=x.device)
+        raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])
+        _lib.check(L.myolo_plan_train_forward(p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), raw_ptrs, _lib.ptr(seg), sp))
+        self.last_plan = p
+        return raws, seg, p
+
+    def train_backward(self, plan, grad_raws, grad_seg):
+        gr = [g.float().contiguous() if g is not None else None for g in grad_raws]
+        gs = grad_seg.float().contiguous() if grad_seg is not None else None
+        ptrs = (C.c_void_p * 3)(*[_lib.ptr(g) for g in gr])
+        _lib.check(_lib.lib().myolo_plan_backward(plan.handle, ptrs, _lib.ptr(gs), _lib.stream_ptr()))
+
     def launches(self):
         return int(_lib.lib().myolo_plan_last_launch_count(self.last_plan.handle)) if self.last_plan else 0
 
@@ -125,3 +185,27 @@ class Engine:
         out = torch.empty((p.B, v.c, v.h, v.w), dtype=torch.float32, device="cuda")
         _lib.check(_lib.lib().myolo_plan_read_view(p.handle, _lib.View(v.buf.id, v.c_off, v.c), _lib.ptr(out), _lib.stream_ptr()))
         return out
+
+
+class _TrainFunction(torch.autograd.Function):
+    """Glue to torch.autograd: the losses (reference utils/loss.py) stay in PyTorch and seed the hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, x):
+        ctx.set_materialize_grads(False)
+        raws, seg, plan = engine.train_forward(x)
+        ctx.engine, ctx.plan = engine, plan
+        return (*raws, seg)
+
+    @staticmethod
+    def backward(ctx, g0, g1, g2, gseg):
+        ctx.engine.train_backward(ctx.plan, [g0, g1, g2], gseg)   # parameter gradients are accumulated into the flat .grad buffer
+        return None, None, None
+
+
+def train_forward(model, x):
+    eng = model.engine()
+    if not hasattr(eng, "_anchor"):
+        eng._anchor = torch.zeros((), device=x.device, requires_grad=True)
+    out = _TrainFunction.apply(eng._anchor, eng, x)
+    return [list(out[:3]), out[3]]

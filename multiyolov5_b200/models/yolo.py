@@ -222,5 +222,8 @@ class Model(nn.Module):
         if augment:
             raise NotImplementedError("TTA (augment=True) is broken in the reference fork itself (SURVEY.md section 2 #18)")
         if self.training:
-            raise NotImplementedError("training-mode forward/backward (SURVEY.md section 8 a13) is not built yet; call .eval()")
+            # train mode: `[[x0,x1,x2], seg]` with batch-statistics BatchNorm and a hand-written backward behind torch.autograd
+            # (reference models/yolo.py:225,316; train.py:363-392).  PSP / Lab / Base heads; BiSe's aux outputs are not built.
+            from ..engine import train_forward
+            return train_forward(self, x)
         return self.engine().forward(x, seg_argmax=seg_argmax)

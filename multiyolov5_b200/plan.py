@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_SIGMOID, ACT_SILU, F16, F32, OP_ADD, OP_BILINEAR, OP_BROADCAST, OP_CHANNEL_SCALE, OP_CONV,
-                   OP_DETECT_DECODE, OP_FOCUS_CONV, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
+                   OP_ACT, OP_BN_ACT, OP_CHANNEL_SCALE_OOP, OP_DETECT_DECODE, OP_FOCUS_CONV, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
                    OP_UPSAMPLE_NEAREST)
 from .models import common as cm
 
@@ -88,8 +88,10 @@ def adaptive_bins(n_in: int, k: int):
 
 
 class PlanBuilder:
-    def __init__(self, B: int, H: int, W: int):
+    def __init__(self, B: int, H: int, W: int, train: bool = False):
         self.B, self.H, self.W = B, H, W
+        self.train = train                      # train mode: raw conv -> batch-stat BN + act ops, nothing in place, no aliasing
+        self.bn_slots: List[nn.BatchNorm2d] = []
         self.bufs: List[Buf] = []
         self.ops: List[OpRec] = []
         self.slots: List[WeightSlot] = []
@@ -147,12 +149,26 @@ class PlanBuilder:
         self.emit(OpRec(OP_CONV, x, residual, dst, k, s, d, act, 0, slot))
         return dst
 
+    def bn_act(self, u: V, bn: nn.BatchNorm2d, act: int, dst: Optional[V], residual: Optional[V]) -> V:
+        """OP_BN_ACT (train mode): y = act(BN_batchstats(u)) (+ residual); aux[0] = bn slot."""
+        dst = dst or self.new_buf(u.h, u.w, u.c)
+        rec = OpRec(OP_BN_ACT, u, residual, dst, act=act)
+        rec.aux[0] = len(self.bn_slots)
+        self.bn_slots.append(bn)
+        self.emit(rec)
+        return dst
+
     def Conv(self, m: cm.Conv, x: V, dst=None, residual=None) -> V:
         act = ACT_SILU if isinstance(m.act, nn.SiLU) else ACT_NONE
         assert isinstance(m.act, (nn.SiLU, nn.Identity)), "only SiLU / identity activations are on the path"
+        if self.train:
+            u = self.conv(x, m.conv, None, ACT_NONE)
+            return self.bn_act(u, m.bn, act, dst, residual)
         return self.conv(x, m.conv, m.bn, act, dst, residual)
 
     def dilated(self, seq: nn.Sequential, x: V, dst=None) -> V:
+        if self.train:
+            return self.bn_act(self.conv(x, seq[0], None, ACT_NONE), seq[1], ACT_SILU, dst, None)
         return self.conv(x, seq[0], seq[1], ACT_SILU, dst)
 
     def bilinear(self, x: V, h, w, dst: Optional[V] = None) -> V:
@@ -231,7 +247,7 @@ class PlanBuilder:
         assert conv.in_channels == 12
         import os
         if (conv.kernel_size == (3, 3) and conv.out_channels in (32, 48) and isinstance(m.conv.act, nn.SiLU)
-                and os.environ.get("MYOLO_FOCUS_FUSION") == "1"):
+                and os.environ.get("MYOLO_FOCUS_FUSION") == "1" and not self.train):
             # opt-in: whole layer in one kernel straight from the NCHW image (csrc/focus_conv.cu).  Measured on B200 it is still
             # slower (190 us) than space-to-depth kernel + tcgen05 conv (26 + 108 us), so the two-kernel path stays the default.
             dst = dst or self.new_buf(self.H // 2, self.W // 2, conv.out_channels)
@@ -278,6 +294,16 @@ class PlanBuilder:
     def FFM(self, m: cm.FFM, x: V, dst=None) -> V:
         feat = self.Conv(m.convblk, x, dst)
         gap = self.pool_pyramid(feat, [1], out_dtype=F32)[0]
+        if self.train:   # keep pre-activations and the unscaled feature map for the backward pass
+            p1 = self.conv(gap, m.channel_attention[1], None, ACT_NONE, out_dtype=F32, name="ffm.att1")
+            a1 = self.new_buf(1, 1, p1.c, F32)
+            self.emit(OpRec(OP_ACT, p1, None, a1, act=ACT_SILU))
+            p2 = self.conv(a1, m.channel_attention[3], None, ACT_NONE, out_dtype=F32, name="ffm.att2")
+            a2 = self.new_buf(1, 1, p2.c, F32)
+            self.emit(OpRec(OP_ACT, p2, None, a2, act=ACT_SIGMOID))
+            out = self.new_buf(feat.h, feat.w, feat.c)
+            self.emit(OpRec(OP_CHANNEL_SCALE_OOP, feat, a2.sub(0, feat.c), out))
+            return out
         a = self.conv(gap, m.channel_attention[1], None, ACT_SILU, out_dtype=F32, name="ffm.att1")
         a = self.conv(a, m.channel_attention[3], None, ACT_SIGMOID, out_dtype=F32, name="ffm.att2")
         self.emit(OpRec(OP_CHANNEL_SCALE, feat, a.sub(0, feat.c), None))
@@ -382,11 +408,12 @@ def infer_strides(model):
     return _layer_meta(model)[1]
 
 
-def build_plan(model, B: int, H: int, W: int, noalias: bool = False) -> PlanBuilder:
-    """Lowers model.model (yaml layers) for a fixed input shape."""
+def build_plan(model, B: int, H: int, W: int, noalias: bool = False, train: bool = False) -> PlanBuilder:
+    """Lowers model.model (yaml layers) for a fixed input shape (train=True: batch-stat BN ops, everything kept for backward)."""
     from .models import yolo as Y
     assert H % 32 == 0 and W % 32 == 0, "input H, W must be multiples of the max stride 32 (reference check_img_size)"
-    pb = PlanBuilder(B, H, W)
+    pb = PlanBuilder(B, H, W, train=train)
+    noalias = noalias or train
     ch, st = _layer_meta(model)
     layers = list(model.model)
     n = len(layers)

@@ -41,8 +41,9 @@ def q16(t: torch.Tensor) -> torch.Tensor:
 
 
 class Ctx:
-    def __init__(self, sd: Dict[str, torch.Tensor], quantised: bool = False):
-        self.sd = {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in sd.items()}
+    def __init__(self, sd: Dict[str, torch.Tensor], quantised: bool = False, train: bool = False):
+        self.train = train   # train mode: BatchNorm uses batch statistics (reference train.py runs model.train()); tensors keep autograd
+        self.sd = sd if train else {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in sd.items()}
         self.quantised = quantised
         self.q: Callable = q16 if quantised else _ident
         self.taps: Dict[str, torch.Tensor] = {}  # optional named intermediates
@@ -65,6 +66,12 @@ def conv_bn_act(cx: Ctx, x, wkey: str, bnp: Optional[str], k: int, s: int = 1, d
     dilated bare branches use padding=dilation (models/common.py:482,487,243-253)."""
     w = cx.sd[wkey]
     pad = d * (k // 2)
+    if bnp is not None and cx.train:
+        y = F.conv2d(x, w, None, s, pad, d)
+        y = F.batch_norm(y, None, None, cx.sd[bnp + ".weight"], cx.sd[bnp + ".bias"], training=True, momentum=0.0, eps=BN_EPS)
+        if act:
+            y = y * torch.sigmoid(y)
+        return y if residual is None else residual + y
     if bnp is not None:
         scale, shift = _bn_affine(cx, bnp)
         if cx.quantised:  # fold BN into fp16 weights exactly like the CUDA pack kernel
@@ -457,3 +464,48 @@ def seg_postprocess(seg: np.ndarray, out_hw) -> np.ndarray:
     `.max(axis=0)[1]` (first maximum wins) per image.  seg: (B,C,h,w) -> (B,H0,W0) int64."""
     up = bilinear_align_corners_np(seg, out_hw)
     return up.argmax(axis=1).astype(np.int64)
+
+
+def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor):
+    """`Model.forward` in TRAIN mode (reference models/yolo.py:225,316): returns ([x0,x1,x2] raw head outputs, seg logits) with autograd
+    history, so tests can compare hand-written gradients with torch.autograd on the restated graph.  `sd` tensors that should receive
+    gradients must be leaf tensors with requires_grad=True."""
+    cx = Ctx(sd, quantised=False, train=True)
+    layers = parse_cfg(cfg)
+    ys: List[Optional[torch.Tensor]] = []
+    x = x.to(torch.float32)
+    raw = seg = None
+    for sp in layers:
+        i, f, t = sp["i"], sp["f"], sp["type"]
+        p = f"model.{i}"
+        inp = x if f == -1 else (ys[f] if isinstance(f, int) else [x if j == -1 else ys[j] for j in f])
+        if t == "Focus":
+            x = Focus(cx, p, inp)
+        elif t == "Conv":
+            x = Conv(cx, p, inp, sp["k"], sp["s"])
+        elif t == "C3":
+            x = C3(cx, p, inp, sp["n"], sp["shortcut"])
+        elif t == "SPP":
+            x = SPP(cx, p, inp, sp["ks"])
+        elif t == "nn.Upsample":
+            x = F.interpolate(inp, scale_factor=sp["scale"], mode=sp["mode"])
+        elif t == "Concat":
+            x = torch.cat(inp, 1)
+        elif t == "SegMaskPSP":
+            x = seg = SegMaskPSP(cx, p, inp, sp["c_hid"])
+        elif t == "SegMaskLab":
+            x = seg = SegMaskLab(cx, p, inp, sp["c_hid"], sp["n"])
+        elif t == "SegMaskBase":
+            x = seg = SegMaskBase(cx, p, inp, sp["n"], sp["shortcut"])
+        elif t == "Detect":
+            raw = []
+            no = sp["nc"] + 5
+            for li, xi in enumerate(inp):
+                y = conv_bn_act(cx, xi, f"{p}.m.{li}.weight", None, 1, act=False, bias_key=f"{p}.m.{li}.bias")
+                bs, _, ny, nx = y.shape
+                raw.append(y.view(bs, y.shape[1] // no, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous())
+            x = raw
+        else:
+            raise NotImplementedError(t)
+        ys.append(x)
+    return raw, seg
