@@ -39,7 +39,7 @@ def test_model_surface():
     with pytest.raises(Exception):
         m.model[1](torch.zeros(1, 32, 8, 8))       # shells hold parameters only: no eager fallback
     m.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(Exception):                 # train mode exists, but only on CUDA tensors: no CPU path
         m(torch.zeros(1, 3, 64, 64))
 
 
