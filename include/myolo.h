@@ -135,6 +135,15 @@ int myolo_plan_train_forward(myolo_plan* plan, const void* x, int x_dtype, float
 /* backward of the last train forward: grad_raw[i] / grad_seg are dL/d(raw[i]) / dL/d(seg) (fp32, nullable); parameter gradients are
  * ACCUMULATED into the registered pointers (the reference accumulates the det and the seg pass, train.py:371,392) */
 int myolo_plan_backward(myolo_plan* plan, const float* const* grad_raw, const float* grad_seg, void* stream);
+/* Optimiser step over FLAT fp32 buffers (all parameters of the model laid out back to back; `group[i]` in 0..n_groups-1 selects the
+ * lr / weight decay of element i): torch.optim.SGD(momentum, nesterov) as configured by reference train.py:108-126 (pg0 BN weights,
+ * pg1 conv weights + decay, pg2 biases).  Gradients are multiplied by *inv_scale (device scalar: 1 / (loss scale x world size),
+ * nullable = 1); when *found_inf != 0 the update is skipped (amp.GradScaler.step, train.py:396); zero_grad clears the gradients in the
+ * same pass (optimizer.zero_grad, train.py:398).  lr / weight_decay are HOST arrays of n_groups (<= 4) floats. */
+int myolo_grads_check_finite(const float* grad, int64_t n, int32_t* found_inf /* device */, void* stream);
+int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr,
+                   const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale /* device */,
+                   const int32_t* found_inf /* device, nullable */, int zero_grad, void* stream);
 
 /* ---- post-process ---- */
 /* utils.general.non_max_suppression (reference utils/general.py:421-509).  pred: (B,A,no) fp32.

@@ -628,7 +628,14 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
     MYOLO_REQUIRE(gout.C == sl.co && sl.co % 16 == 0, "op %d: fp16 conv gradient needs Co %% 16 == 0 (Co=%d)", i, sl.co);
   }
   // weight / bias gradients
-  if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, sl.d_bias, s))) return rc;
+  // (the bias gradient of an fp32 head gradient is summed from the fp32 values, not from their fp16 cast)
+  const bool bias_f32 = gout.dtype == MYOLO_F32 && sl.d_bias;
+  if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, bias_f32 ? nullptr : sl.d_bias, s))) return rc;
+  if (bias_f32) {
+    TensorView gy = gout;
+    gy.C = sl.co;
+    if ((rc = launch_bias_grad(gy, sl.d_bias, sl.co, s))) return rc;
+  }
   if (!need_dgrad) return 0;
   // data gradient = stride-1 conv of (zero-stuffed) dY with flipped / transposed weights, accumulated into grad(in)
   const int ci_out_pad = (int)align_up(sl.ci, 16);
@@ -685,20 +692,32 @@ extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw,
   for (const auto& op : pl->ops)
     if (op.kind == MYOLO_OP_INPUT_FOCUS && op.out.buf >= 0) is_input_buf[op.out.buf] = 1;
   int rc = 0;
+  // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
+  // iteration never touches the seg head, the seg pass never the Detect convs (reference train.py:364-392 runs two passes).
+  std::vector<char> live(pl->bufs.size(), 0);
+  auto is_live = [&](const myolo_view& v) { return v.buf >= 0 && live[v.buf]; };
+  auto mark = [&](const myolo_view& v) { if (v.buf >= 0) live[v.buf] = 1; };
   for (int i = n - 1; i >= 0 && !rc; --i) {
     const myolo_op& op = pl->ops[i];
     TensorView a, b, c, d;
+    if (op.kind != MYOLO_OP_SEG_UPSAMPLE && op.kind != MYOLO_OP_DETECT_DECODE && op.kind != MYOLO_OP_INPUT_FOCUS) {
+      if (!is_live(op.out)) continue;
+      mark(op.in);
+      mark(op.in2);
+    }
     switch (op.kind) {
       case MYOLO_OP_INPUT_FOCUS:
         break;
       case MYOLO_OP_SEG_UPSAMPLE:
         if (!grad_seg) break;
         if ((rc = grad_view(pl, op.in, &a))) break;
+        mark(op.in);
         rc = launch_seg_upsample_bwd(grad_seg, op.aux[0], pl->H, pl->W, a, s);
         break;
       case MYOLO_OP_DETECT_DECODE:
         if (!grad_raw || !grad_raw[op.aux[0]]) break;
         if ((rc = grad_view(pl, op.in, &a))) break;
+        mark(op.in);
         rc = launch_detect_raw_bwd(grad_raw[op.aux[0]], op.aux[1], op.aux[2], a, s);
         break;
       case MYOLO_OP_CONV:
@@ -758,6 +777,22 @@ extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw,
     }
   }
   return rc;
+}
+
+extern "C" int myolo_grads_check_finite(const float* grad, int64_t n, int32_t* found_inf, void* stream) {
+  MYOLO_REQUIRE(grad && found_inf && n > 0, "grads_check_finite: bad arguments");
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  return launch_grads_check_finite(grad, (long)n, found_inf, (cudaStream_t)stream);
+}
+
+extern "C" int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr,
+                              const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale,
+                              const int32_t* found_inf, int zero_grad, void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  return launch_sgd_step(param, grad, momentum_buf, group, (long)n, lr, weight_decay, n_groups, momentum, nesterov, inv_scale, found_inf,
+                         zero_grad, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -748,4 +748,65 @@ int launch_conv_small_bwd(const TensorView& x, const TensorView& dy, const Tenso
   return 0;
 }
 
+int launch_bias_grad(const TensorView& dy, float* dbias, int co, cudaStream_t s) {
+  const long npix = (long)dy.B * dy.H * dy.W;
+  dim3 g(ceil_div(co, 32), (unsigned)std::min<long>(128, std::max<long>(1, npix / 256)));
+  chan_reduce_kernel<2><<<g, 256, 0, s>>>(dy, dy, nullptr, nullptr, nullptr, 0, dbias, npix, co);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimiser step over the FLAT parameter / gradient buffers (one launch for all 229 tensors; HBM-bound: 5 floats + 1 byte per element)
+//   torch.optim.SGD(momentum, nesterov=True) with per-group lr / weight decay (reference train.py:108-126: pg0 BN weights, pg1 conv
+//   weights with decay, pg2 biases), gradients unscaled by *inv_scale (loss scale x world size) and the step skipped when a non-finite
+//   gradient was found (amp.GradScaler.step semantics, train.py:396-397); gradients are zeroed in the same pass (optimizer.zero_grad)
+// ------------------------------------------------------------------------------------------------
+__global__ void grads_check_finite_kernel(const float* __restrict__ g, long n, int* found_inf) {
+  int bad = 0;
+  const long n4 = n / 4;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(g)[i];
+    bad |= !isfinite(v.x) | !isfinite(v.y) | !isfinite(v.z) | !isfinite(v.w);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) bad |= !isfinite(g[n4 * 4 + threadIdx.x]);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0 && bad) atomicOr(found_inf, 1);
+}
+int launch_grads_check_finite(const float* g, long n, int* found_inf, cudaStream_t s) {
+  MYOLO_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grads_check_finite: gradient buffer must be 16-byte aligned");
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(found_inf, 0, sizeof(int), s));
+  grads_check_finite_kernel<<<grid_for_t(std::max<long>(1, n / 4), 256, 148 * 8), 256, 0, s>>>(g, n, found_inf);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+struct SgdGroups { float lr[4]; float wd[4]; };
+__global__ void sgd_step_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ buf, const unsigned char* __restrict__ group,
+                                long n, SgdGroups gr, float momentum, int nesterov, const float* inv_scale, const int* found_inf, int zero_grad) {
+  const bool skip = found_inf && *found_inf;
+  const float is = inv_scale ? *inv_scale : 1.0f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    if (!skip) {
+      const int k = group[i] & 3;
+      const float w = p[i];
+      float d = g[i] * is + gr.wd[k] * w;
+      const float m = momentum * buf[i] + d;
+      buf[i] = m;
+      d = nesterov ? d + momentum * m : m;
+      p[i] = w - gr.lr[k] * d;
+    }
+    if (zero_grad) g[i] = 0.f;
+  }
+}
+int launch_sgd_step(float* p, float* g, float* buf, const unsigned char* group, long n, const float* lr, const float* wd, int n_groups,
+                    float momentum, int nesterov, const float* inv_scale, const int* found_inf, int zero_grad, cudaStream_t s) {
+  MYOLO_REQUIRE(p && g && buf && group && n > 0 && n_groups >= 1 && n_groups <= 4, "sgd_step: bad arguments");
+  SgdGroups gr{};
+  for (int i = 0; i < n_groups; ++i) { gr.lr[i] = lr[i]; gr.wd[i] = wd[i]; }
+  sgd_step_kernel<<<grid_for_t(n, 256, 148 * 8), 256, 0, s>>>(p, g, buf, group, n, gr, momentum, nesterov, inv_scale, found_inf, zero_grad);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace myolo

@@ -55,6 +55,11 @@ int launch_cast_f16_to_f32_acc(const TensorView& src, const TensorView& dst, cud
 // conv parameter gradients: dW[co][ci][ky][kx] += sum_p dY[p][co] * X[p*stride + tap][ci];  dbias[co] += sum_p dY[p][co]
 int launch_conv_wgrad(const TensorView& x, const TensorView& dy, int k, int stride, int dil, float* dW, int co, int ci, float* dbias,
                       cudaStream_t s);
+int launch_bias_grad(const TensorView& dy, float* dbias, int co, cudaStream_t s);                     // dbias[co] += sum_p dy (fp32 or fp16 view)
+// optimiser over the flat parameter / gradient buffers (see train.cu)
+int launch_grads_check_finite(const float* g, long n, int* found_inf, cudaStream_t s);
+int launch_sgd_step(float* p, float* g, float* buf, const unsigned char* group, long n, const float* lr, const float* wd, int n_groups,
+                    float momentum, int nesterov, const float* inv_scale, const int* found_inf, int zero_grad, cudaStream_t s);
 // tiny maps / fp32 tensors: generic backward straight from the fp32 master weights (dx nullable: += ; dW += ; dbias += )
 int launch_conv_small_bwd(const TensorView& x, const TensorView& dy, const TensorView* dx, const float* w, float* dW, float* dbias, int co,
                           int ci, int k, int stride, int dil, cudaStream_t s);

@@ -1,0 +1,164 @@
+"""One training iteration of the joint det+seg model, mirroring the step glue of reference train.py:363-401:
+
+    det forward -> ComputeLoss x world_size x detgain -> scaled backward          (train.py:364-371)
+    seg forward -> SegmentationLosses x batch_size x seggain -> scaled backward   (train.py:381-392; gradients ACCUMULATE)
+    every `accumulate` iterations: ONE all-reduce of the flat gradient buffer (the reference's DDP reducer, train.py:243-245),
+    GradScaler-style finite check, SGD(momentum, nesterov) with the three parameter groups of train.py:108-126, zero_grad.
+
+What is B200-native here: forward/backward are the hand-written kernels behind `Model.forward` (engine._TrainFunction); all
+parameters, gradients and momentum buffers live in three FLAT fp32 buffers, so the collective is a single NCCL call over one
+contiguous 31 MB region and the optimiser is a single HBM-bound launch (`myolo_sgd_step`) that also unscales, skips on overflow and
+clears the gradients.  `torch.distributed` is plumbing only (process group + all_reduce on the flat buffer).
+
+Out of scope (the reference's outer loop, not the hot path): data loading, LR schedule / warm-up (call `set_lr` / `set_momentum`),
+EMA, checkpointing, plotting, DDP buffer broadcast.
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .utils.loss import ComputeLoss, SegmentationLosses
+
+
+def scale_hyp(hyp: dict, nl: int, nc: int, imgsz: int, total_batch_size: int, nbs: int = 64, label_smoothing: float = 0.0) -> dict:
+    """hyper-parameter scalings of reference train.py:102-104 (weight decay) and :248-251 (loss gains)"""
+    h = dict(hyp)
+    accumulate = max(round(nbs / total_batch_size), 1)
+    h["weight_decay"] = hyp["weight_decay"] * total_batch_size * accumulate / nbs
+    h["box"] = hyp["box"] * 3.0 / nl
+    h["cls"] = hyp["cls"] * nc / 80.0 * 3.0 / nl
+    h["obj"] = hyp["obj"] * (imgsz / 640) ** 2 * 3.0 / nl
+    h["label_smoothing"] = label_smoothing
+    return h
+
+
+def parameter_groups(model: nn.Module):
+    """{id(param): group} with group 0 = BatchNorm weights (no decay), 1 = other weights (decay), 2 = biases (reference train.py:108-116)"""
+    grp = {}
+    for _, m in model.named_modules():
+        b = getattr(m, "bias", None)
+        if isinstance(b, nn.Parameter):
+            grp[id(b)] = 2
+        w = getattr(m, "weight", None)
+        if isinstance(m, nn.BatchNorm2d):
+            grp[id(m.weight)] = 0
+        elif isinstance(w, nn.Parameter):
+            grp[id(w)] = 1
+    return grp
+
+
+class FlatState:
+    """Parameters, gradients and momentum of a model as three flat fp32 CUDA buffers; `p.data` / `p.grad` become views."""
+
+    def __init__(self, model: nn.Module):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params), "fp32 master parameters on the GPU"
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.n = n
+        self.param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.momentum = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.group = torch.empty(n, dtype=torch.uint8, device=dev)
+        groups = parameter_groups(model)
+        off = 0
+        self.offsets = []
+        for p in self.params:
+            k = p.numel()
+            self.param[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.param[off:off + k].view_as(p)
+            self.group[off:off + k] = groups.get(id(p), 1)
+            self.offsets.append(off)
+            off += k
+        self.grad = model.engine().ensure_flat_grads()
+        assert self.grad.numel() == n
+
+    def check_views(self, model):
+        """cheap guard: someone re-assigned parameters (.half(), load_state_dict with assign, .to()) -> views are stale"""
+        p0, p1 = self.params[0], self.params[-1]
+        ok = p0.data_ptr() == self.param.data_ptr() and p1.data_ptr() == self.param.data_ptr() + 4 * self.offsets[-1]
+        g = model.engine().ensure_flat_grads()
+        if not ok or g.data_ptr() != self.grad.data_ptr():
+            raise RuntimeError("model parameters / gradients no longer alias the flat training buffers; rebuild the Trainer")
+
+
+class Trainer:
+    """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
+
+    def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
+                 growth_interval=2000, process_group=None):
+        assert next(model.parameters()).is_cuda, "model.cuda() first"
+        self.model, self.hyp, self.batch_size = model, hyp, batch_size
+        self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
+        self.detgain, self.seggain = detgain, seggain          # train.py:290
+        model.hyp, model.gr = hyp, getattr(model, "gr", 1.0)
+        model.train()
+        self.compute_loss = ComputeLoss(model)
+        self.compute_seg_loss = SegmentationLosses(ignore_index=-1)
+        self.flat = FlatState(model)
+        dev = self.flat.param.device
+        self.lr = [hyp["lr0"]] * 3
+        self.wd = [0.0, hyp["weight_decay"], 0.0]
+        self.momentum = hyp["momentum"]
+        self.scale = torch.full((), float(init_scale), device=dev)
+        self.growth_tracker = torch.zeros((), dtype=torch.int32, device=dev)
+        self.growth_interval = growth_interval
+        self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.inv_scale = torch.ones((), device=dev)
+        self.ni = 0
+
+    def set_lr(self, lr_bn, lr_weight, lr_bias):
+        self.lr = [float(lr_bn), float(lr_weight), float(lr_bias)]
+
+    def set_momentum(self, m):
+        self.momentum = float(m)
+
+    # ---- the two passes --------------------------------------------------------------------------------------------
+    def backward_det(self, imgs, targets):
+        pred = self.model(imgs)                                                   # train mode: [[x0,x1,x2], seg]
+        loss, items = self.compute_loss(pred[0], targets)
+        if self.rank != -1:
+            loss = loss * self.world_size                                         # train.py:367-368
+        loss = loss * self.detgain
+        (loss * self.scale).backward()
+        return items
+
+    def backward_seg(self, segimgs, segtargets):
+        pred = self.model(segimgs)
+        segloss = self.compute_seg_loss(pred[1], segtargets) * self.batch_size * self.seggain   # train.py:385,391
+        (segloss * self.scale).backward()
+        return segloss.detach()
+
+    # ---- reduce + optimiser ------------------------------------------------------------------------------------------
+    def allreduce(self):
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.flat.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+
+    def optimizer_step(self):
+        f = self.flat
+        f.check_views(self.model)
+        self.allreduce()
+        L, sp = _lib.lib(), _lib.stream_ptr()
+        torch.reciprocal(self.scale * float(self.world_size), out=self.inv_scale)  # DDP averages: sum / world_size
+        _lib.check(L.myolo_grads_check_finite(_lib.ptr(f.grad), f.n, _lib.ptr(self.found_inf), sp))
+        lr = (C.c_float * 3)(*self.lr)
+        wd = (C.c_float * 3)(*self.wd)
+        _lib.check(L.myolo_sgd_step(_lib.ptr(f.param), _lib.ptr(f.grad), _lib.ptr(f.momentum), _lib.ptr(f.group), f.n, lr, wd, 3,
+                                    float(self.momentum), 1, _lib.ptr(self.inv_scale), _lib.ptr(self.found_inf), 1, sp))
+        # amp.GradScaler.update: halve on overflow, double after growth_interval clean steps (device-side, no host sync)
+        bad = self.found_inf[0] != 0
+        self.growth_tracker = torch.where(bad, torch.zeros_like(self.growth_tracker), self.growth_tracker + 1)
+        grow = self.growth_tracker >= self.growth_interval
+        self.scale = torch.where(bad, self.scale * 0.5, torch.where(grow, self.scale * 2.0, self.scale))
+        self.growth_tracker = torch.where(grow, torch.zeros_like(self.growth_tracker), self.growth_tracker)
+        self.model.engine().weights_dirty = True
+
+    def step(self, imgs, targets, segimgs, segtargets):
+        """one iteration (train.py:363-401).  Returns (det loss items [lbox,lobj,lcls,loss], seg loss) as device tensors."""
+        items = self.backward_det(imgs, targets)
+        segloss = self.backward_seg(segimgs, segtargets)
+        self.ni += 1
+        if self.ni % self.accumulate == 0:
+            self.optimizer_step()
+        return items, segloss

@@ -123,10 +123,83 @@ def gen_segpost():
     print("segpost", list(cases))
 
 
+def load_reference_loss():
+    """utils/loss.py of the reference, executed from where it lies with ONE in-memory textual fix: `gj.clamp_(0, gain[3] - 1)`
+    (utils/loss.py:212) passes a float tensor as the bound of a long tensor, which torch >= 1.12 rejects; `int(gain[k]) - 1` has the
+    same value.  Nothing is written to disk."""
+    import types
+    src = open(os.path.join(ref_shims.REF_ROOT, "utils", "loss.py")).read()
+    assert "gain[3] - 1" in src and "gain[2] - 1" in src
+    src = src.replace("gain[3] - 1", "int(gain[3]) - 1").replace("gain[2] - 1", "int(gain[2]) - 1")
+    mod = types.ModuleType("ref_loss_patched")
+    exec(compile(src, "reference:utils/loss.py", "exec"), mod.__dict__)
+    return mod
+
+
+def loss_hyp(nl=3, nc=10, imgsz=1024):
+    """data/hyp.scratch.yaml with the scalings of train.py:248-251 (imgsz = the long side, train.py:196)"""
+    import yaml
+    with open(os.path.join(ref_shims.REF_ROOT, "data", "hyp.scratch.yaml")) as f:
+        hyp = yaml.safe_load(f)
+    hyp["box"] *= 3.0 / nl
+    hyp["cls"] *= nc / 80.0 * 3.0 / nl
+    hyp["obj"] *= (imgsz / 640) ** 2 * 3.0 / nl
+    hyp["label_smoothing"] = 0.0
+    return hyp
+
+
+def gen_loss(ref_yolo):
+    """ComputeLoss.__call__ (utils/loss.py:115-162) + SegmentationLosses.forward (:235-237) on small seeded inputs; stores the loss,
+    loss_items and d(loss)/d(prediction) so both the restatement and the product loss can be checked."""
+    ref_loss = load_reference_loss()
+    cfg = synth.load_cfg("yolov5s_city_seg.yaml")
+    torch.manual_seed(0)
+    model = build_reference_model(ref_yolo, cfg)
+    hyp = loss_hyp(nl=3, nc=cfg["nc"], imgsz=256)
+    model.hyp, model.gr, model.nc = hyp, 1.0, cfg["nc"]
+    det = model.model[-1]
+    crit = ref_loss.ComputeLoss(model)
+    rs = np.random.RandomState(3)
+    B, H, W = 2, 128, 256
+    cases = {"hyp_json": np.frombuffer(json.dumps(hyp).encode(), dtype=np.uint8), "anchors": det.anchors.numpy().copy(),
+             "strides": det.stride.numpy().copy()}
+    for name, nt in (("a", 24), ("empty", 0), ("edge", 16)):
+        p = [torch.from_numpy(rs.normal(0, 1.0, (B, det.na, H // s, W // s, det.no)).astype(np.float32)).requires_grad_(True)
+             for s in (8, 16, 32)]
+        t = np.zeros((nt, 6), np.float32)
+        if nt:
+            t[:, 0] = rs.randint(0, B, nt)
+            t[:, 1] = rs.randint(0, cfg["nc"], nt)
+            t[:, 2:4] = rs.uniform(0.02, 0.98, (nt, 2)) if name != "edge" else rs.choice([0.001, 0.5, 0.999, 0.26, 0.74], (nt, 2))
+            t[:, 4:6] = rs.uniform(0.02, 0.5, (nt, 2))
+        loss, items = crit(p, torch.from_numpy(t))
+        loss.backward()
+        cases[f"{name}_targets"] = t
+        for i in range(3):
+            cases[f"{name}_p{i}"] = p[i].detach().numpy()
+            cases[f"{name}_g{i}"] = p[i].grad.numpy()
+        cases[f"{name}_loss"] = loss.detach().numpy()
+        cases[f"{name}_items"] = items.numpy()
+    # segmentation CE (ignore_index=-1)
+    seg = torch.from_numpy(rs.normal(0, 2.0, (2, 19, 32, 64)).astype(np.float32)).requires_grad_(True)
+    mask = torch.from_numpy(rs.randint(-1, 19, (2, 32, 64)).astype(np.int64))
+    sl = ref_loss.SegmentationLosses(ignore_index=-1)(seg, mask)
+    sl.backward()
+    cases.update(seg_logits=seg.detach().numpy(), seg_mask=mask.numpy(), seg_loss=sl.detach().numpy(), seg_grad=seg.grad.numpy())
+    np.savez_compressed(os.path.join(GOLD, "loss_cases.npz"), **cases)
+    print("loss", {k: v.shape for k, v in cases.items() if "loss" in k or "items" in k})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cwd = os.getcwd()
     ref_yolo, ref_general = ref_shims.import_reference()
-    gen_nets(ref_yolo)
-    gen_nms(ref_general)
-    gen_segpost()
+    only = set(sys.argv[1:])
+    if not only or "nets" in only:
+        gen_nets(ref_yolo)
+    if not only or "nms" in only:
+        gen_nms(ref_general)
+    if not only or "segpost" in only:
+        gen_segpost()
+    if not only or "loss" in only:
+        gen_loss(ref_yolo)

@@ -509,3 +509,114 @@ def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor)
             raise NotImplementedError(t)
         ys.append(x)
     return raw, seg
+
+
+# ------------------------------------------------------------------------------------------------
+# training losses - plain restatement, per-target Python loops; small cases only
+# ------------------------------------------------------------------------------------------------
+def ciou_xywh(pb: torch.Tensor, tb: torch.Tensor, eps: float = 1e-7) -> torch.Tensor:
+    """bbox_iou(box1.T, box2, x1y1x2y2=False, CIoU=True) of reference utils/general.py:343-380 for (n,4) xywh boxes."""
+    px1, px2 = pb[:, 0] - pb[:, 2] / 2, pb[:, 0] + pb[:, 2] / 2
+    py1, py2 = pb[:, 1] - pb[:, 3] / 2, pb[:, 1] + pb[:, 3] / 2
+    tx1, tx2 = tb[:, 0] - tb[:, 2] / 2, tb[:, 0] + tb[:, 2] / 2
+    ty1, ty2 = tb[:, 1] - tb[:, 3] / 2, tb[:, 1] + tb[:, 3] / 2
+    inter = (torch.min(px2, tx2) - torch.max(px1, tx1)).clamp(0) * (torch.min(py2, ty2) - torch.max(py1, ty1)).clamp(0)   # :358-359
+    w1, h1 = px2 - px1, py2 - py1 + eps                                                                                    # :362
+    w2, h2 = tx2 - tx1, ty2 - ty1 + eps                                                                                    # :363
+    union = w1 * h1 + w2 * h2 - inter + eps
+    iou = inter / union
+    cw = torch.max(px2, tx2) - torch.min(px1, tx1)
+    ch = torch.max(py2, ty2) - torch.min(py1, ty1)
+    c2 = cw ** 2 + ch ** 2 + eps
+    rho2 = ((tx1 + tx2 - px1 - px2) ** 2 + (ty1 + ty2 - py1 - py2) ** 2) / 4
+    v = (4 / math.pi ** 2) * torch.pow(torch.atan(w2 / h2) - torch.atan(w1 / h1), 2)
+    with torch.no_grad():
+        alpha = v / (v - iou + (1 + eps))                                                                                  # :378-379
+    return iou - (rho2 / c2 + v * alpha)
+
+
+def build_targets_loop(shapes, targets: np.ndarray, anchors: np.ndarray, anchor_t: float):
+    """ComputeLoss.build_targets (reference utils/loss.py:164-217) as explicit loops.  shapes[i] = (ny, nx); anchors (nl, na, 2) in grid
+    units.  Returns per level a list of (img, anchor, gj, gi, tbox(4), cls) in the reference's candidate order: the 5 offsets
+    (centre, x-1, y-1, x+1, y+1) outermost, then anchors, then targets."""
+    out = []
+    offs = np.array([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]], np.float32) * np.float32(0.5)
+    for i, (ny, nx) in enumerate(shapes):
+        gain = np.array([nx, ny], np.float32)
+        kept = []     # (anchor index, scaled target row)
+        for a in range(anchors.shape[1]):
+            for t in targets:
+                gxy = t[2:4] * gain
+                gwh = t[4:6] * gain
+                r = gwh / anchors[i, a]
+                if max(np.maximum(r, np.float32(1.0) / r)) < anchor_t:                         # :185-186
+                    kept.append((a, int(t[0]), int(t[1]), gxy.astype(np.float32), gwh.astype(np.float32)))
+        rows = []
+        for k in range(5):
+            for (a, img, cls, gxy, gwh) in kept:
+                gxi = gain - gxy
+                if k == 0:
+                    sel = True
+                elif k == 1:
+                    sel = (gxy[0] % 1.0 < 0.5) and (gxy[0] > 1.0)                              # j  :193
+                elif k == 2:
+                    sel = (gxy[1] % 1.0 < 0.5) and (gxy[1] > 1.0)                              # k
+                elif k == 3:
+                    sel = (gxi[0] % 1.0 < 0.5) and (gxi[0] > 1.0)                              # l  :194
+                else:
+                    sel = (gxi[1] % 1.0 < 0.5) and (gxi[1] > 1.0)                              # m
+                if not sel:
+                    continue
+                gij = (gxy - offs[k]).astype(np.int64)                                         # .long() truncation :206
+                gi = int(min(max(gij[0], 0), nx - 1))
+                gj = int(min(max(gij[1], 0), ny - 1))
+                # gj/gi are VIEWS of gij and clamp_ is in place (:211), so the box offset (:212) is relative to the CLAMPED cell
+                tb = np.concatenate([gxy - np.array([gi, gj], np.float32), gwh]).astype(np.float32)
+                rows.append((img, a, gj, gi, tb, cls))
+        out.append(rows)
+    return out
+
+
+def bce_logits(x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """nn.BCEWithLogitsLoss(pos_weight=1) elementwise"""
+    return x.clamp(min=0) - x * t + torch.log1p(torch.exp(-x.abs()))
+
+
+def compute_det_loss(p: List[torch.Tensor], targets: np.ndarray, anchors: np.ndarray, hyp: dict, nc: int, gr: float = 1.0):
+    """ComputeLoss.__call__ (reference utils/loss.py:115-162), fl_gamma = 0, label smoothing from hyp.  p[i]: (B, na, ny, nx, 5+nc).
+    Returns (loss * batch, items[lbox, lobj, lcls, loss])."""
+    eps_ls = hyp.get("label_smoothing", 0.0)
+    cp, cn = 1.0 - 0.5 * eps_ls, 0.5 * eps_ls
+    balance = [4.0, 1.0, 0.4]
+    shapes = [(pi.shape[2], pi.shape[3]) for pi in p]
+    cand = build_targets_loop(shapes, targets, anchors, hyp["anchor_t"])
+    lbox = torch.zeros(1); lobj = torch.zeros(1); lcls = torch.zeros(1)
+    for i, pi in enumerate(p):
+        tobj = torch.zeros(pi.shape[:4])
+        rows = cand[i]
+        if rows:
+            b = torch.tensor([r[0] for r in rows]); a = torch.tensor([r[1] for r in rows])
+            gj = torch.tensor([r[2] for r in rows]); gi = torch.tensor([r[3] for r in rows])
+            tb = torch.from_numpy(np.stack([r[4] for r in rows]))
+            tc = torch.tensor([r[5] for r in rows])
+            ps = pi[b, a, gj, gi]
+            pxy = ps[:, :2].sigmoid() * 2.0 - 0.5
+            pwh = (ps[:, 2:4].sigmoid() * 2) ** 2 * torch.from_numpy(anchors[i])[a]
+            iou = ciou_xywh(torch.cat((pxy, pwh), 1), tb)
+            lbox = lbox + (1.0 - iou).mean()
+            vals = (1.0 - gr) + gr * iou.detach().clamp(0)
+            for r in range(len(rows)):                     # sequential writes: the last candidate of a cell wins (CPU index_put_)
+                tobj[b[r], a[r], gj[r], gi[r]] = vals[r]
+            if nc > 1:
+                t = torch.full_like(ps[:, 5:], cn)
+                t[torch.arange(len(rows)), tc] = cp
+                lcls = lcls + bce_logits(ps[:, 5:], t).mean()
+        lobj = lobj + bce_logits(pi[..., 4], tobj).mean() * balance[i]
+    lbox = lbox * hyp["box"]; lobj = lobj * hyp["obj"]; lcls = lcls * hyp["cls"]
+    loss = lbox + lobj + lcls
+    return loss * p[0].shape[0], torch.cat((lbox, lobj, lcls, loss)).detach()
+
+
+def seg_ce_loss(seg: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """SegmentationLosses.forward without aux (reference utils/loss.py:235-237) == CrossEntropyLoss(ignore_index=-1), mean over valid"""
+    return F.cross_entropy(seg, mask, ignore_index=-1)

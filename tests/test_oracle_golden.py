@@ -75,3 +75,53 @@ def test_segpost_restatement():
             assert np.abs(up - g[f"up_{name}"]).max() <= 1e-5 * np.abs(g[f"up_{name}"]).max()
         # ATen's vectorised CPU kernel may contract a*b+c*d to FMA; argmax may only differ at 1-ulp near-ties
         assert mism.mean() < 1e-4, (name, mism.sum())
+
+
+# ---- training losses: fixtures from the unmodified reference's ComputeLoss / SegmentationLosses ----
+def _loss_fixture():
+    g = np.load(os.path.join(GOLD, "loss_cases.npz"))
+    hyp = json.loads(bytes(g["hyp_json"]).decode())
+    return g, hyp
+
+
+@pytest.mark.parametrize("name", ["a", "empty", "edge"])
+def test_det_loss_restatement_matches_reference(name):
+    g, hyp = _loss_fixture()
+    p = [torch.from_numpy(g[f"{name}_p{i}"]).requires_grad_(True) for i in range(3)]
+    loss, items = restate.compute_det_loss(p, g[f"{name}_targets"], g["anchors"], hyp, nc=10)
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g[f"{name}_loss"][0])) <= 1e-6 * abs(float(g[f"{name}_loss"][0]))
+    assert np.allclose(items.numpy(), g[f"{name}_items"], rtol=1e-6, atol=1e-7)
+    for i in range(3):
+        assert np.abs(p[i].grad.numpy() - g[f"{name}_g{i}"]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("name", ["a", "empty", "edge"])
+def test_det_loss_product_matches_reference(name):
+    """the mask-based (synchronisation-free) product loss gives the reference's loss, loss items and gradients (fp32 tolerance 1e-5)"""
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.utils.loss import ComputeLoss
+    g, hyp = _loss_fixture()
+    model = Model("yolov5s_city_seg.yaml")
+    model.hyp, model.gr = hyp, 1.0
+    assert np.allclose(model.model[-1].anchors.numpy(), g["anchors"])
+    crit = ComputeLoss(model)
+    p = [torch.from_numpy(g[f"{name}_p{i}"]).requires_grad_(True) for i in range(3)]
+    loss, items = crit(p, torch.from_numpy(g[f"{name}_targets"]))
+    loss.backward()
+    assert abs(float(loss.detach()) - float(g[f"{name}_loss"][0])) <= 1e-5 * abs(float(g[f"{name}_loss"][0]))
+    assert np.allclose(items.numpy(), g[f"{name}_items"], rtol=1e-5, atol=1e-6)
+    for i in range(3):
+        ref = g[f"{name}_g{i}"]
+        assert np.abs(p[i].grad.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+def test_seg_loss_matches_reference():
+    from multiyolov5_b200.utils.loss import SegmentationLosses
+    g, _ = _loss_fixture()
+    for fn in (restate.seg_ce_loss, SegmentationLosses(ignore_index=-1)):
+        seg = torch.from_numpy(g["seg_logits"]).requires_grad_(True)
+        loss = fn(seg, torch.from_numpy(g["seg_mask"]))
+        loss.backward()
+        assert abs(float(loss.detach()) - float(g["seg_loss"])) <= 1e-6
+        assert np.abs(seg.grad.numpy() - g["seg_grad"]).max() <= 1e-9
