@@ -1,6 +1,7 @@
 """Multi-GPU plumbing of the path.  Inference shards by image: one process per GPU, independent
 replicas, NO data-path collective; torch.distributed (NCCL on GPUs, gloo in CPU tests) is used only for the barrier and the
-max-over-ranks time so that throughput is reported for the whole job."""
+max-over-ranks time so that throughput is reported for the whole job.  Training (row a13) has ONE real exchange per optimiser step:
+the sum of the flat gradient buffer over ranks (the reference wraps the model in DistributedDataParallel, train.py:243-245)."""
 import torch
 import torch.distributed as dist
 
@@ -20,3 +21,15 @@ def aggregate_throughput(images_local: int, ms_local: float, device=None) -> flo
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
     return float(n.item() / (t.item() * 1e-3))
+
+
+def allreduce_flat_grads(flat_grad: torch.Tensor, group=None) -> int:
+    """ONE collective per optimiser step over the contiguous gradient buffer (31 MB fp32 for s/PSP): SUM over ranks, in place.
+    Averaging (DDP semantics) is folded into the optimiser's unscale factor, 1 / (loss scale x world size), so no extra pass over the
+    buffer is needed.  Returns the world size used."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+    return world

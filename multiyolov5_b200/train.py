@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .parallel import allreduce_flat_grads
 from .utils.loss import ComputeLoss, SegmentationLosses
 
 
@@ -133,7 +134,8 @@ class Trainer:
     # ---- reduce + optimiser ------------------------------------------------------------------------------------------
     def allreduce(self):
         if self.world_size > 1:
-            torch.distributed.all_reduce(self.flat.grad, op=torch.distributed.ReduceOp.SUM, group=self.pg)
+            world = allreduce_flat_grads(self.flat.grad, group=self.pg)
+            assert world == self.world_size, f"process group has {world} ranks, Trainer was built for {self.world_size}"
 
     def optimizer_step(self):
         f = self.flat

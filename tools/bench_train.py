@@ -1,0 +1,136 @@
+"""Training-step measurement (BASELINE.json configs[3]): yolov5s_city_seg.yaml (PSP head), per GPU
+4 det images + 4 seg images of 3x512x1024, 20 boxes per det image, seg labels randint(-1,19); one step = det forward/backward +
+seg forward/backward + ONE flat-gradient all-reduce + SGD (reference train.py:363-401).  Not the headline metric (bench.py is);
+this is the a13 row's number and its breakdown.
+
+    python tools/bench_train.py [--steps 10 --warmup 3 --batch 4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/bench_train.py
+
+Prints ONE JSON line on rank 0.  Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+H, W = 512, 1024
+GFLOP_FWD_PER_IMG = 29.70          # SURVEY.md section 8d (Conv2d MACs x 2, s/PSP)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=4, help="det images per GPU (= seg images per GPU)")
+    ap.add_argument("--breakdown", action="store_true", help="also time the phases of one step separately (extra synchronisation)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+    from oracle import synth                     # synthetic weights only (test infrastructure used as a data generator, like bench.py)
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.train import Trainer, scale_hyp
+    yml, tag = "yolov5s_city_seg.yaml", "s_psp"
+    cfg = synth.load_cfg(yml)
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1, gain=1.0)
+    model = Model(yml)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    B = args.batch
+    hyp = dict(lr0=0.0015, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
+    hyp = scale_hyp(hyp, nl=3, nc=cfg["nc"], imgsz=W, total_batch_size=B * world)      # data/hyp.scratch.yaml values
+    tr = Trainer(model, hyp, batch_size=B, world_size=world, rank=rank if world > 1 else -1, init_scale=2.0 ** 10)
+    gen = torch.Generator(device="cuda").manual_seed(77 + rank)
+    NROT = 3
+    imgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+    segimgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+    rs = np.random.RandomState(5 + rank)
+    tg = []
+    for _ in range(NROT):
+        t = np.zeros((20 * B, 6), np.float32)
+        t[:, 0] = np.repeat(np.arange(B), 20)
+        t[:, 1] = rs.randint(0, 10, 20 * B)
+        t[:, 2:4] = rs.uniform(0.1, 0.9, (20 * B, 2))
+        t[:, 4:6] = rs.uniform(0.02, 0.22, (20 * B, 2))
+        tg.append(torch.from_numpy(t).cuda())
+    masks = [torch.randint(-1, 19, (B, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+
+    def step(i):
+        k = i % NROT
+        return tr.step(imgs[k], tg[k], segimgs[k], masks[k])
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        items, segloss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    breakdown = None
+    if args.breakdown:
+        def ev():
+            e = torch.cuda.Event(enable_timing=True); e.record(); return e
+        acc = np.zeros(7)
+        reps = 3
+        for r in range(reps):
+            k = r % NROT
+            t0 = ev(); pred = model(imgs[k])
+            t1 = ev(); loss, _ = tr.compute_loss(pred[0], tg[k]); loss = loss * tr.detgain * tr.scale
+            t2 = ev(); loss.backward()
+            t3 = ev(); pred = model(segimgs[k])
+            t4 = ev(); sl = tr.compute_seg_loss(pred[1], masks[k]) * B * tr.seggain * tr.scale
+            t5 = ev(); sl.backward()
+            t6 = ev(); tr.optimizer_step()
+            t7 = ev()
+            torch.cuda.synchronize()
+            acc += np.array([a.elapsed_time(b) for a, b in zip((t0, t1, t2, t3, t4, t5, t6), (t1, t2, t3, t4, t5, t6, t7))])
+        names = ["det_forward", "det_loss", "det_loss_bwd+net_bwd", "seg_forward", "seg_loss", "seg_loss_bwd+net_bwd", "allreduce+sgd"]
+        breakdown = {n: round(v / reps, 3) for n, v in zip(names, acc)}
+    if rank == 0:
+        n_img = 2 * B * world * args.steps
+        flops = 3.0 * GFLOP_FWD_PER_IMG * 1e9 * 2 * B * world           # per step, all ranks (fwd + dgrad + wgrad)
+        line = {"metric": "train images/sec @1024x512 (det pass + seg pass + allreduce + SGD)", "value": n_img / (ms * 1e-3),
+                "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "dtype": "f16 storage / f32 accumulate, fp32 master weights", "data": "synthetic",
+                "config": {"workload": f"{yml} train step, per GPU {B} det + {B} seg images 3x{H}x{W}, 20 boxes/img", "global_batch": 2 * B * world,
+                           "parallelism": f"dp{world} (one flat-gradient all-reduce of {tr.flat.n * 4 / 1e6:.1f} MB per step)"},
+                "conv_tflops_algorithmic": flops / (ms / args.steps * 1e-3) / 1e12, "loss_scale": float(tr.scale),
+                "last_losses": {"det": [float(v) for v in items], "seg": float(segloss)}, "breakdown_ms": breakdown}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
