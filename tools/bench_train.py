@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="det images per GPU (= seg images per GPU)")
+    ap.add_argument("--kernel-table", default=None, help="write a per-kernel device-time table (torch.profiler / CUPTI, 2 steps) to this file")
     ap.add_argument("--breakdown", action="store_true", help="also time the phases of one step separately (extra synchronisation)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -116,6 +117,22 @@ def main():
             acc += np.array([a.elapsed_time(b) for a, b in zip((t0, t1, t2, t3, t4, t5, t6), (t1, t2, t3, t4, t5, t6, t7))])
         names = ["det_forward", "det_loss", "det_loss_bwd+net_bwd", "seg_forward", "seg_loss", "seg_loss_bwd+net_bwd", "allreduce+sgd"]
         breakdown = {n: round(v / reps, 3) for n, v in zip(names, acc)}
+    if args.kernel_table and rank == 0:
+        import time
+        from torch.profiler import profile, ProfilerActivity
+        torch.cuda.synchronize()
+        w0 = time.time()
+        for i in range(2):
+            step(i)
+        torch.cuda.synchronize()
+        wall = (time.time() - w0) / 2
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            for i in range(2):
+                step(i)
+            torch.cuda.synchronize()
+        with open(args.kernel_table, "w") as f:
+            f.write("wall ms per step (no profiler): %.2f\n" % (wall * 1e3))
+            f.write(prof.key_averages().table(sort_by="cuda_time_total", row_limit=60, max_name_column_width=70))
     if rank == 0:
         n_img = 2 * B * world * args.steps
         flops = 3.0 * GFLOP_FWD_PER_IMG * 1e9 * 2 * B * world           # per step, all ranks (fwd + dgrad + wgrad)
