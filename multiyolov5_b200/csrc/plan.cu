@@ -56,6 +56,7 @@ struct WeightSlot {
   float* d_bias = nullptr;
   __half* w_dgrad = nullptr;         // flipped / transposed fp16 pack for the data gradient
   float* zero_bias = nullptr;
+  bool dgrad_valid = false;          // w_dgrad matches the current master weights
 };
 
 }  // namespace myolo
@@ -239,6 +240,7 @@ extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float
   s.ci_pad = ci_pad;
   s.set = true;
   s.w_master = w;
+  s.dgrad_valid = false;
   return pack_conv_weights(w, co, ci, k, gamma, beta, mean, var, eps, bias, s.w, s.bias, co_pad, ci_pad, (cudaStream_t)stream);
 }
 
@@ -331,7 +333,7 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
       MYOLO_REQUIRE(op.aux[0] >= 0 && op.aux[0] < (int)pl->bns.size() && pl->bns[op.aux[0]].set, "op %d: BN slot %d not set", i, op.aux[0]);
       const BnParams& bn = pl->bns[op.aux[0]];
       if ((int)pl->bn_stats.size() <= i) pl->bn_stats.resize(pl->ops.size(), nullptr);
-      if (!pl->bn_stats[i]) MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], 4 * (size_t)bn.C * sizeof(float)));
+      if (!pl->bn_stats[i]) MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], (4 * (size_t)bn.C + 4) * sizeof(float)));
       if ((rc = launch_bn_stats(in, bn, pl->bn_stats[i], pl->bn_stats[i] + 2 * bn.C, s))) return rc;
       return launch_bn_act_fwd(in, has_res ? &in2 : nullptr, out, bn, pl->bn_stats[i], op.act, s);
     }
@@ -587,6 +589,16 @@ static int grad_view(const myolo_plan* pl, const myolo_view& v, TensorView* out)
   return 0;
 }
 
+static int ensure_scratch(myolo_plan* pl, size_t bytes) {      // fp32 scratch shared by the pooling / resampling adjoints (stream ordered)
+  if (pl->spp_scratch_bytes >= bytes) return 0;
+  if (pl->spp_scratch) cudaFree(pl->spp_scratch);
+  pl->spp_scratch = nullptr;
+  pl->spp_scratch_bytes = 0;
+  MYOLO_CHECK_CUDA(cudaMalloc(&pl->spp_scratch, bytes));
+  pl->spp_scratch_bytes = bytes;
+  return 0;
+}
+
 static int ensure_tmp16(myolo_plan* pl, size_t bytes) {
   if (pl->tmp16_bytes >= bytes) return 0;
   if (pl->tmp16) cudaFree(pl->tmp16);
@@ -644,7 +656,10 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.w_dgrad, (size_t)n_pad * op.k * op.k * cpad * 2));
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.zero_bias, (size_t)n_pad * 4));
   }
-  if ((rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, op.k, sl.w_dgrad, sl.zero_bias, n_pad, cpad, s))) return rc;
+  if (!sl.dgrad_valid) {
+    if ((rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, op.k, sl.w_dgrad, sl.zero_bias, n_pad, cpad, s))) return rc;
+    sl.dgrad_valid = true;
+  }
   TensorView din = dy16;
   if (s2) {
     din = TensorView{reinterpret_cast<unsigned char*>(pl->tmp16) + stuffed_off, gout.B, 2 * gout.H, 2 * gout.W, cpad, cpad, MYOLO_F16};
@@ -749,17 +764,12 @@ extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw,
         break;
       case MYOLO_OP_BILINEAR:
         if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
-        rc = launch_bilinear_bwd(a, b, s);
+        if ((rc = ensure_scratch(pl, bilinear_bwd_scratch_bytes(a, b)))) break;
+        rc = launch_bilinear_bwd(a, b, pl->spp_scratch, s);
         break;
       case MYOLO_OP_SPP_POOL: {
         if ((rc = resolve_view(pl, op.in, &a)) || (rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
-        const size_t need = (size_t)a.B * a.H * a.W * a.C * sizeof(float);
-        if (pl->spp_scratch_bytes < need) {
-          if (pl->spp_scratch) cudaFree(pl->spp_scratch);
-          pl->spp_scratch = nullptr;
-          if (cudaMalloc(&pl->spp_scratch, need) != cudaSuccess) { set_error("backward: spp scratch allocation failed"); rc = MYOLO_E_CUDA; break; }
-          pl->spp_scratch_bytes = need;
-        }
+        if ((rc = ensure_scratch(pl, (size_t)a.B * a.H * a.W * a.C * sizeof(float)))) break;
         rc = launch_spp_bwd(a, b, c, pl->spp_scratch, s);
         break;
       }

@@ -85,6 +85,88 @@ __global__ void chan_reduce_kernel(TensorView a, TensorView bview, const float* 
   }
 }
 
+// Vectorised variant for fp16 views (the BN forward statistics and the BN backward sums): a thread owns 8 channels (one 16-byte load
+// per pixel), the block's threads tile (pixel lanes x channel vectors) so a pixel's channels are read as one contiguous run; per-block
+// partials are combined through shared memory and added atomically; the LAST block to finish (ticket) runs the per-channel epilogue:
+//   MODE 0: mean / inverse std -> stats, running-statistics update        MODE 1: dgamma += sum(dz*xhat), dbeta += sum(dz)
+template <int MODE>
+__global__ void __launch_bounds__(256) chan_reduce_v_kernel(TensorView a, TensorView bview, const float* __restrict__ stats,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                            float* out, long npix, int C, BnParams bn, float* stats_out,
+                                                            unsigned* ticket) {
+  __shared__ float sh[2][2048];
+  __shared__ int is_last;
+  const int nv = C >> 3, lanes = 256 / nv;
+  const int t = threadIdx.x;
+  const bool active = t < lanes * nv;
+  const int cv = active ? t % nv : 0, lane = active ? t / nv : 0;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  if (active) {
+    float mean[8], istd[8], g[8], bt[8];
+    if (MODE == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int c = cv * 8 + k; mean[k] = stats[c]; istd[k] = stats[C + c]; g[k] = gamma[c]; bt[k] = beta[c]; }
+    }
+    const __half* ab = reinterpret_cast<const __half*>(a.base);
+    const __half* bb = reinterpret_cast<const __half*>(bview.base);
+    for (long p = (long)blockIdx.x * lanes + lane; p < npix; p += (long)gridDim.x * lanes) {
+      const uint4 q = *reinterpret_cast<const uint4*>(ab + (size_t)p * a.ctot + cv * 8);
+      const __half* h = reinterpret_cast<const __half*>(&q);
+      if (MODE == 0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const float u = __half2float(h[k]); s0[k] += u; s1[k] += u * u; }
+      } else {
+        const uint4 r = *reinterpret_cast<const uint4*>(bb + (size_t)p * bview.ctot + cv * 8);
+        const __half* hr = reinterpret_cast<const __half*>(&r);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float xh = (__half2float(h[k]) - mean[k]) * istd[k];
+          const float dz = __half2float(hr[k]) * act_grad(g[k] * xh + bt[k], act);
+          s0[k] += dz; s1[k] += dz * xh;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sh[0][lane * C + cv * 8 + k] = s0[k]; sh[1][lane * C + cv * 8 + k] = s1[k]; }
+  }
+  __syncthreads();
+  for (int c = t; c < C; c += 256) {
+    float x0 = 0.f, x1 = 0.f;
+    for (int l = 0; l < lanes; ++l) { x0 += sh[0][l * C + c]; x1 += sh[1][l * C + c]; }
+    atomicAdd(out + c, x0);
+    atomicAdd(out + C + c, x1);
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int c = t; c < C; c += 256) {
+    const float x0 = __ldcg(out + c), x1 = __ldcg(out + C + c);
+    if (MODE == 0) {
+      const float n = (float)npix;
+      const float mean = x0 / n;
+      const float var = fmaxf(x1 / n - mean * mean, 0.f);          // biased variance normalises (F.batch_norm, training=True)
+      stats_out[c] = mean;
+      stats_out[C + c] = rsqrtf(var + bn.eps);
+      if (bn.running_mean) {                                       // running stats: unbiased variance, momentum 0.03
+        bn.running_mean[c] = (1.f - bn.momentum) * bn.running_mean[c] + bn.momentum * mean;
+        bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * var * (n / fmaxf(n - 1.f, 1.f));
+      }
+    } else {
+      if (bn.d_beta) bn.d_beta[c] += x0;
+      if (bn.d_gamma) bn.d_gamma[c] += x1;
+    }
+  }
+}
+static inline int reduce_v_grid(long npix, int C) {
+  const int lanes = 256 / (C / 8);
+  return (int)std::max<long>(1, std::min<long>(148 * 2, npix / ((long)lanes * 4)));
+}
+
 __global__ void bn_finalize_kernel(float* sums, float* stats, BnParams bn, long npix) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= bn.C) return;
@@ -102,7 +184,14 @@ __global__ void bn_finalize_kernel(float* sums, float* stats, BnParams bn, long 
 int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s) {
   MYOLO_REQUIRE(u.dtype == MYOLO_F16 && bn.set && bn.C == u.C, "bn_stats: bad view / BN parameters not set");
   const long npix = (long)u.B * u.H * u.W;
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)u.C * sizeof(float), s));
+  // scratch: 2*C sums followed by the completion ticket
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C + 1) * sizeof(float), s));
+  if (u.C % 8 == 0 && u.C <= 2048 && u.ctot % 8 == 0) {
+    chan_reduce_v_kernel<0><<<reduce_v_grid(npix, u.C), 256, 0, s>>>(u, u, nullptr, nullptr, nullptr, 0, scratch, npix, u.C, bn, stats,
+                                                                    reinterpret_cast<unsigned*>(scratch + 2 * u.C));
+    MYOLO_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
   chan_reduce_kernel<0><<<g, 256, 0, s>>>(u, u, nullptr, nullptr, nullptr, 0, scratch, npix, u.C);
   MYOLO_LAUNCH_CHECK();
@@ -146,8 +235,9 @@ int launch_bn_act_fwd(const TensorView& u, const TensorView* res, const TensorVi
   return 0;
 }
 
-__global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ stats, const float* __restrict__ sums, int act, float inv_n) {
+__global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, TensorView dres, bool has_res, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ sums, int act,
+                                  float inv_n) {
   const long total = (long)u.B * u.H * u.W * (u.C / 8);
   const int nv = u.C / 8, C = u.C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -167,6 +257,18 @@ __global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, co
       ho[k] = __float2half_rn(gamma[c] * stats[C + c] * (dz - sums[c] * inv_n - xh * sums[C + c] * inv_n));
     }
     *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(du.base) + (size_t)p * du.ctot + v * 8) = o;
+    if (has_res) {                                              // shortcut gradient: d(residual) += dy
+      uint4* dp = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(dres.base) + (size_t)p * dres.ctot + v * 8);
+      uint4 r = *dp;
+      __half2* hr = reinterpret_cast<__half2*>(&r);
+      const __half2* hb = reinterpret_cast<const __half2*>(&g);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = __half22float2(hr[k]), fb = __half22float2(hb[k]);
+        hr[k] = __floats2half2_rn(fa.x + fb.x, fa.y + fb.y);
+      }
+      *dp = r;
+    }
   }
 }
 __global__ void bn_param_grad_kernel(const float* sums, BnParams bn) {
@@ -196,20 +298,24 @@ __global__ void add_acc_kernel(TensorView dst, TensorView src) {   // dst += src
 }
 int launch_bn_act_bwd(const TensorView& u, const TensorView& dy, const TensorView& du, const TensorView* d_res, const BnParams& bn,
                       const float* stats, int act, float* scratch, cudaStream_t s) {
-  MYOLO_REQUIRE(u.C % 8 == 0 && dy.C == u.C && du.C == u.C && dy.ctot % 8 == 0 && du.ctot % 8 == 0, "bn_act_bwd: bad views");
+  MYOLO_REQUIRE(u.C % 8 == 0 && dy.C == u.C && du.C == u.C && dy.ctot % 8 == 0 && du.ctot % 8 == 0 && u.ctot % 8 == 0, "bn_act_bwd: bad views");
+  MYOLO_REQUIRE(!d_res || (d_res->C == u.C && d_res->ctot % 8 == 0), "bn_act_bwd: bad residual gradient view");
   const long npix = (long)u.B * u.H * u.W;
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, 2 * (size_t)u.C * sizeof(float), s));
-  dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
-  chan_reduce_kernel<1><<<g, 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C);
-  MYOLO_LAUNCH_CHECK();
-  bn_act_bwd_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(u, dy, du, bn.gamma, bn.beta, stats, scratch, act, 1.0f / (float)npix);
-  MYOLO_LAUNCH_CHECK();
-  bn_param_grad_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, bn);
-  MYOLO_LAUNCH_CHECK();
-  if (d_res) {
-    add_acc_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(*d_res, dy);
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C + 1) * sizeof(float), s));
+  if (u.C <= 2048) {
+    chan_reduce_v_kernel<1><<<reduce_v_grid(npix, u.C), 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C, bn, nullptr,
+                                                                    reinterpret_cast<unsigned*>(scratch + 2 * u.C));
+    MYOLO_LAUNCH_CHECK();
+  } else {
+    dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
+    chan_reduce_kernel<1><<<g, 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C);
+    MYOLO_LAUNCH_CHECK();
+    bn_param_grad_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, bn);
     MYOLO_LAUNCH_CHECK();
   }
+  bn_act_bwd_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(u, dy, du, d_res ? *d_res : du, d_res != nullptr, bn.gamma, bn.beta, stats,
+                                                                     scratch, act, 1.0f / (float)npix);
+  MYOLO_LAUNCH_CHECK();
   return 0;
 }
 
@@ -267,15 +373,19 @@ int launch_channel_scale_oop(const TensorView& f, const TensorView& a, const Ten
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
-// df += dout*(1+a);  da[b,c] += sum_p dout*f    (one block per (b, 32-channel group))
+// df += dout*(1+a);  da[b,c] += sum_p dout*f    (block = (b, 32-channel group, pixel slab); da is accumulated atomically when fp32)
 __global__ void channel_scale_bwd_kernel(TensorView f, TensorView a, TensorView dout, TensorView df, TensorView da) {
   __shared__ float sh[8][32];
-  const int cg = blockIdx.x % ((f.C + 31) / 32), b = blockIdx.x / ((f.C + 31) / 32);
+  const int ncg = (f.C + 31) / 32;
+  const int cg = blockIdx.x % ncg, b = blockIdx.x / ncg;
   const int c = cg * 32 + (threadIdx.x & 31), lp = threadIdx.x >> 5;
+  const int npix = f.H * f.W;
+  const int per = (npix + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(npix, p0 + per);
   float acc = 0.f;
   if (c < f.C) {
     const float sc = 1.0f + ldv(a, b, 0, 0, c);
-    for (int p = lp; p < f.H * f.W; p += 8) {
+    for (int p = p0 + lp; p < p1; p += 8) {
       const int y = p / f.W, x = p % f.W;
       const float g = ldv(dout, b, y, x, c);
       acc += g * ldv(f, b, y, x, c);
@@ -286,12 +396,15 @@ __global__ void channel_scale_bwd_kernel(TensorView f, TensorView a, TensorView 
   __syncthreads();
   if (lp == 0 && c < f.C) {
     for (int l = 1; l < 8; ++l) acc += sh[l][threadIdx.x & 31];
-    stv(da, b, 0, 0, c, ldv(da, b, 0, 0, c) + acc);
+    if (da.dtype == MYOLO_F32) atomicAdd(reinterpret_cast<float*>(da.base) + (size_t)b * da.H * da.W * da.ctot + c, acc);
+    else stv(da, b, 0, 0, c, ldv(da, b, 0, 0, c) + acc);
   }
 }
 int launch_channel_scale_bwd(const TensorView& f, const TensorView& a, const TensorView& dout, const TensorView& df, const TensorView& da,
                              cudaStream_t s) {
-  channel_scale_bwd_kernel<<<f.B * ceil_div(f.C, 32), 256, 0, s>>>(f, a, dout, df, da);
+  MYOLO_REQUIRE(da.H == 1 && da.W == 1 && a.H == 1 && a.W == 1, "channel_scale_bwd: attention must be a 1x1 map");
+  const int slabs = da.dtype == MYOLO_F32 ? std::max(1, std::min(64, f.H * f.W / 64)) : 1;
+  channel_scale_bwd_kernel<<<dim3(f.B * ceil_div(f.C, 32), slabs), 256, 0, s>>>(f, a, dout, df, da);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -332,36 +445,56 @@ __device__ __forceinline__ void dst_range(int src_i, int n_in, int n_out, int* l
   *lo = max(0, (int)floorf((src_i - 1) * inv) - 1);
   *hi = min(n_out - 1, (int)ceilf((src_i + 1) * inv) + 1);
 }
-__global__ void bilinear_bwd_kernel(TensorView dout, TensorView din) {
+// separable adjoint: tmp[b,sy,dx,c] = sum_dy wy(dy->sy) dout[b,dy,dx,c]  (fp32 scratch), then din[b,sy,sx,c] += sum_dx wx(dx->sx) tmp
+__global__ void bilinear_bwd_rows_kernel(TensorView dout, int in_h, float* __restrict__ tmp) {
+  const long total = (long)dout.B * in_h * dout.W * dout.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dout.C);
+    long p = i / dout.C;
+    const int dx = (int)(p % dout.W); p /= dout.W;
+    const int sy = (int)(p % in_h);
+    const int b = (int)(p / in_h);
+    int lo, hi;
+    dst_range(sy, in_h, dout.H, &lo, &hi);
+    float acc = 0.f;
+    for (int dy = lo; dy <= hi; ++dy) {
+      int a0, a1; float w0, w1;
+      lerp_src(dy, in_h, dout.H, &a0, &a1, &w0, &w1);
+      const float wy = (a0 == sy ? w0 : 0.f) + (a1 == sy ? w1 : 0.f);
+      if (wy != 0.f) acc += wy * ldv(dout, b, dy, dx, c);
+    }
+    tmp[i] = acc;
+  }
+}
+__global__ void bilinear_bwd_cols_kernel(const float* __restrict__ tmp, int out_w, TensorView din) {
   const long total = (long)din.B * din.H * din.W * din.C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % din.C);
     long p = i / din.C;
-    const int x = (int)(p % din.W); p /= din.W;
-    const int y = (int)(p % din.H);
+    const int sx = (int)(p % din.W); p /= din.W;
+    const int sy = (int)(p % din.H);
     const int b = (int)(p / din.H);
-    int ylo, yhi, xlo, xhi;
-    dst_range(y, din.H, dout.H, &ylo, &yhi);
-    dst_range(x, din.W, dout.W, &xlo, &xhi);
+    int lo, hi;
+    dst_range(sx, din.W, out_w, &lo, &hi);
     float acc = 0.f;
-    for (int dy = ylo; dy <= yhi; ++dy) {
-      int a0, a1; float w0, w1;
-      lerp_src(dy, din.H, dout.H, &a0, &a1, &w0, &w1);
-      const float wy = (a0 == y ? w0 : 0.f) + (a1 == y ? w1 : 0.f);
-      if (wy == 0.f) continue;
-      for (int dx = xlo; dx <= xhi; ++dx) {
-        int b0, b1; float v0, v1;
-        lerp_src(dx, din.W, dout.W, &b0, &b1, &v0, &v1);
-        const float wx = (b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f);
-        if (wx != 0.f) acc += wy * wx * ldv(dout, b, dy, dx, c);
-      }
+    const float* row = tmp + (((size_t)b * din.H + sy) * out_w) * din.C + c;
+    for (int dx = lo; dx <= hi; ++dx) {
+      int b0, b1; float v0, v1;
+      lerp_src(dx, din.W, out_w, &b0, &b1, &v0, &v1);
+      const float wx = (b0 == sx ? v0 : 0.f) + (b1 == sx ? v1 : 0.f);
+      if (wx != 0.f) acc += wx * row[(size_t)dx * din.C];
     }
-    stv(din, b, y, x, c, ldv(din, b, y, x, c) + acc);
+    stv(din, b, sy, sx, c, ldv(din, b, sy, sx, c) + acc);
   }
 }
-int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s) {
-  MYOLO_REQUIRE(dout.C == din.C, "bilinear_bwd: bad views");
-  bilinear_bwd_kernel<<<grid_for_t((long)din.B * din.H * din.W * din.C, 128), 128, 0, s>>>(dout, din);
+size_t bilinear_bwd_scratch_bytes(const TensorView& dout, const TensorView& din) {
+  return (size_t)dout.B * din.H * dout.W * dout.C * sizeof(float);
+}
+int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, float* scratch, cudaStream_t s) {
+  MYOLO_REQUIRE(dout.C == din.C && scratch, "bilinear_bwd: bad views");
+  bilinear_bwd_rows_kernel<<<grid_for_t((long)dout.B * din.H * dout.W * dout.C, 256), 256, 0, s>>>(dout, din.H, scratch);
+  MYOLO_LAUNCH_CHECK();
+  bilinear_bwd_cols_kernel<<<grid_for_t((long)din.B * din.H * din.W * din.C, 128), 128, 0, s>>>(scratch, dout.W, din);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }

@@ -40,7 +40,8 @@ int launch_act_bwd(const TensorView& x, const TensorView& dy, const TensorView& 
 int launch_channel_scale_bwd(const TensorView& f, const TensorView& a, const TensorView& dout, const TensorView& df, const TensorView& da,
                              cudaStream_t s);
 int launch_nearest2x_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s);             // din += 2x2 sums
-int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s);              // din += adjoint(align_corners)
+size_t bilinear_bwd_scratch_bytes(const TensorView& dout, const TensorView& din);
+int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, float* scratch, cudaStream_t s);  // din += adjoint(align_corners)
 int launch_spp_bwd(const TensorView& x, const TensorView& dout3, const TensorView& dx, float* scratch_f32, cudaStream_t s);
 int launch_region_bwd(const TensorView& datoms_or_bins, const TensorView& dx, const int* d_yb, int ny, const int* d_xb, int nx,
                       cudaStream_t s);                                                                // dx[p] += datoms[atom(p)]

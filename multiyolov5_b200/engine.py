@@ -128,6 +128,7 @@ class Engine:
         """every parameter's .grad is a view into ONE flat fp32 buffer (what the data-parallel all-reduce moves, reference
         train.py:243-245 DDP semantics) that the backward kernels accumulate into."""
         params = [p for p in self.model.parameters() if p.requires_grad]
+        self._train_params = params
         if getattr(self, "_flat_grad", None) is not None and all(p.grad is not None and p.grad.data_ptr() == g.data_ptr()
                                                                   for p, g in zip(params, self._grad_views)):
             return self._flat_grad
@@ -154,13 +155,27 @@ class Engine:
         self.ensure_flat_grads()
         L = _lib.lib()
         sp = _lib.stream_ptr()
-        p.upload_weights()                       # parameters changed since the last step: re-pack (fp16, K-major, no BN folding)
-        for i, s in enumerate(p.pb.slots):
-            _lib.check(L.myolo_plan_set_conv_grad(p.handle, i, _lib.ptr(s.conv.weight.grad), _lib.ptr(s.conv.bias.grad if s.conv.bias is not None else None)))
-        for i, bn in enumerate(p.pb.bn_slots):
-            _lib.check(L.myolo_plan_set_bn(p.handle, i, bn.num_features, _lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
-                                           _lib.ptr(bn.running_var), _lib.ptr(bn.weight.grad), _lib.ptr(bn.bias.grad), float(bn.momentum), float(bn.eps)))
-            bn.num_batches_tracked += 1
+        params = self._train_params
+        # re-pack the fp16 weights only when the parameters changed (in-place torch updates bump _version; Trainer's fused optimiser
+        # writes through raw pointers and sets weights_dirty)
+        ver = sum(q._version for q in params)
+        if self.weights_dirty or getattr(p, "_w_version", None) != ver:
+            for q in self.plans.values():        # every plan (inference ones too) holds packed copies of the old values
+                q.weights_uploaded = False
+            self.weights_dirty = False
+        if not p.weights_uploaded:
+            p.upload_weights()                   # fp16, K-major, no BN folding
+            p._w_version = ver
+        sig = (self._flat_grad.data_ptr(), params[0].data_ptr(), params[-1].data_ptr(), len(params))
+        if getattr(p, "_ptr_sig", None) != sig:  # (re)register parameter / gradient pointers only when they moved
+            for i, s in enumerate(p.pb.slots):
+                _lib.check(L.myolo_plan_set_conv_grad(p.handle, i, _lib.ptr(s.conv.weight.grad), _lib.ptr(s.conv.bias.grad if s.conv.bias is not None else None)))
+            for i, bn in enumerate(p.pb.bn_slots):
+                _lib.check(L.myolo_plan_set_bn(p.handle, i, bn.num_features, _lib.ptr(bn.weight), _lib.ptr(bn.bias), _lib.ptr(bn.running_mean),
+                                               _lib.ptr(bn.running_var), _lib.ptr(bn.weight.grad), _lib.ptr(bn.bias.grad), float(bn.momentum), float(bn.eps)))
+            p._ptr_sig = sig
+            p._nbt = [bn.num_batches_tracked for bn in p.pb.bn_slots]
+        torch._foreach_add_(p._nbt, 1)
         det, seg_head = self.model.model[-1], self.model.model[-2]
         dec = [o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]
         raws = [torch.empty((B, det.na, v.h, v.w, det.no), dtype=torch.float32, device=x.device) for v in dec]
