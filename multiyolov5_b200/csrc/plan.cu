@@ -57,6 +57,7 @@ struct WeightSlot {
   __half* w_dgrad = nullptr;         // flipped / transposed fp16 pack for the data gradient
   float* zero_bias = nullptr;
   bool dgrad_valid = false;          // w_dgrad matches the current master weights
+  int dgrad_n_pad = 0, dgrad_cpad = 0;
 };
 
 }  // namespace myolo
@@ -97,6 +98,11 @@ struct myolo_plan {
   std::vector<ConvOp> dconvs;         // data-gradient convs (parallel to ops)
   std::vector<int> dconv_ready;
   bool train_fwd_done = false;
+  // backward replay: one single-lane captured graph per seed mask (bit i = grad_raw[i] given, bit 3 = grad_seg given)
+  cudaGraphExec_t bwd_exec[16] = {};
+  int bwd_ops[16] = {};
+  bool bwd_warm[16] = {};
+  bool bwd_dirty = false;
 };
 
 static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
@@ -191,6 +197,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   if (pl->ws) cudaFree(pl->ws);
   if (pl->d_extra) cudaFree(pl->d_extra);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
+  for (auto& e : pl->bwd_exec) if (e) cudaGraphExecDestroy(e);
   if (pl->graph) cudaGraphDestroy(pl->graph);
   for (auto e : pl->op_ev) cudaEventDestroy(e);
   if (pl->ev_start) cudaEventDestroy(pl->ev_start);
@@ -557,6 +564,11 @@ extern "C" int myolo_plan_set_bn(myolo_plan* pl, int bn_slot, int channels, floa
   MYOLO_REQUIRE(pl && bn_slot >= 0 && gamma && beta && channels > 0, "set_bn: bad arguments");
   if ((int)pl->bns.size() <= bn_slot) pl->bns.resize(bn_slot + 1);
   BnParams& b = pl->bns[bn_slot];
+  if (b.gamma != gamma || b.beta != beta || b.running_mean != running_mean || b.running_var != running_var || b.d_gamma != d_gamma ||
+      b.d_beta != d_beta || b.momentum != momentum || b.eps != eps) {
+    pl->graph_dirty = true;      // kernel arguments are baked into the captured graphs
+    pl->bwd_dirty = true;
+  }
   b.gamma = gamma; b.beta = beta; b.running_mean = running_mean; b.running_var = running_var;
   b.d_gamma = d_gamma; b.d_beta = d_beta; b.momentum = momentum; b.eps = eps; b.C = channels; b.set = true;
   return 0;
@@ -564,6 +576,7 @@ extern "C" int myolo_plan_set_bn(myolo_plan* pl, int bn_slot, int channels, floa
 
 extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weight, float* d_bias) {
   MYOLO_REQUIRE(pl && slot >= 0 && slot < (int)pl->slots.size(), "set_conv_grad: bad slot %d", slot);
+  if (pl->slots[slot].d_w != d_weight || pl->slots[slot].d_bias != d_bias) pl->bwd_dirty = true;
   pl->slots[slot].d_w = d_weight;
   pl->slots[slot].d_bias = d_bias;
   return 0;
@@ -571,13 +584,10 @@ extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weigh
 
 extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream) {
   MYOLO_REQUIRE(pl && x, "train_forward: null plan / input");
-  cudaStream_t s = (cudaStream_t)stream;
-  const int64_t l0 = g_launch_count;
-  for (size_t i = 0; i < pl->ops.size(); ++i) {
-    int rc = run_op(pl, (int)i, x, x_dtype, nullptr, raw, seg, MYOLO_F32, nullptr, s);
-    if (rc) return rc;
-  }
-  pl->last_launches = g_launch_count - l0;
+  // same executor as inference: first call in order (lazy allocations / tensor maps), then multi-lane CUDA-graph replay of the internal
+  // ops with the input conversion before and the caller-owned outputs (raw x_i, seg logits) after the graph
+  int rc = myolo_plan_forward(pl, x, x_dtype, nullptr, raw, seg, MYOLO_F32, nullptr, stream);
+  if (rc) return rc;
   pl->train_fwd_done = true;
   return 0;
 }
@@ -596,6 +606,7 @@ static int ensure_scratch(myolo_plan* pl, size_t bytes) {      // fp32 scratch s
   pl->spp_scratch_bytes = 0;
   MYOLO_CHECK_CUDA(cudaMalloc(&pl->spp_scratch, bytes));
   pl->spp_scratch_bytes = bytes;
+  pl->bwd_dirty = true;
   return 0;
 }
 
@@ -606,6 +617,7 @@ static int ensure_tmp16(myolo_plan* pl, size_t bytes) {
   MYOLO_CHECK_CUDA(cudaMalloc(&pl->tmp16, bytes));
   pl->tmp16_bytes = bytes;
   for (auto& r : pl->dconv_ready) r = 0;   // tensor maps point into tmp16
+  pl->bwd_dirty = true;
   return 0;
 }
 
@@ -656,9 +668,11 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.w_dgrad, (size_t)n_pad * op.k * op.k * cpad * 2));
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.zero_bias, (size_t)n_pad * 4));
   }
-  if (!sl.dgrad_valid) {
+  if (!sl.dgrad_valid) {   // (first use; later refreshes happen in refresh_dgrad_packs, outside any captured graph)
     if ((rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, op.k, sl.w_dgrad, sl.zero_bias, n_pad, cpad, s))) return rc;
     sl.dgrad_valid = true;
+    sl.dgrad_n_pad = n_pad;
+    sl.dgrad_cpad = cpad;
   }
   TensorView din = dy16;
   if (s2) {
@@ -696,45 +710,105 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
   return c.use_tc ? conv_tc_launch(c, s) : conv_simt_launch(c, s);
 }
 
+// seeds: dL/d(raw x_i) and dL/d(seg) written into the gradient buffers of the head convs (caller-owned memory: never captured)
+static int backward_seeds(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, std::vector<char>& live, cudaStream_t s) {
+  for (int i = (int)pl->ops.size() - 1; i >= 0; --i) {
+    const myolo_op& op = pl->ops[i];
+    TensorView a;
+    int rc;
+    if (op.kind == MYOLO_OP_SEG_UPSAMPLE && grad_seg) {
+      if ((rc = grad_view(pl, op.in, &a))) return rc;
+      live[op.in.buf] = 1;
+      if ((rc = launch_seg_upsample_bwd(grad_seg, op.aux[0], pl->H, pl->W, a, s))) return rc;
+    } else if (op.kind == MYOLO_OP_DETECT_DECODE && grad_raw && grad_raw[op.aux[0]]) {
+      if ((rc = grad_view(pl, op.in, &a))) return rc;
+      live[op.in.buf] = 1;
+      if ((rc = launch_detect_raw_bwd(grad_raw[op.aux[0]], op.aux[1], op.aux[2], a, s))) return rc;
+    }
+  }
+  return 0;
+}
+
+// data-gradient weight packs follow the master weights; refreshed here (never inside a captured graph)
+static int refresh_dgrad_packs(myolo_plan* pl, cudaStream_t s) {
+  for (auto& sl : pl->slots)
+    if (sl.w_dgrad && !sl.dgrad_valid) {
+      int rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, sl.k, sl.w_dgrad, sl.zero_bias, sl.dgrad_n_pad, sl.dgrad_cpad, s);
+      if (rc) return rc;
+      sl.dgrad_valid = true;
+    }
+  return 0;
+}
+
+static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s, int* n_ops);
+
 extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream) {
   MYOLO_REQUIRE(pl && pl->train_fwd_done, "backward: call myolo_plan_train_forward first");
   cudaStream_t s = (cudaStream_t)stream;
   if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
   MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
+  int mask = grad_seg ? 8 : 0;
+  for (int i = 0; i < 3; ++i)
+    if (grad_raw && grad_raw[i]) mask |= 1 << i;
+  // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
+  // iteration never touches the seg head, the seg pass never the Detect convs (reference train.py:364-392 runs two passes).
+  std::vector<char> live(pl->bufs.size(), 0);
+  int rc = backward_seeds(pl, grad_raw, grad_seg, live, s);
+  if (rc) return rc;
+  if ((rc = refresh_dgrad_packs(pl, s))) return rc;
+  if (pl->bwd_dirty) {
+    for (auto& e : pl->bwd_exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
+    for (auto& w : pl->bwd_warm) w = false;
+    pl->bwd_dirty = false;
+  }
+  int n_ops = 0;
+  if (!pl->use_graph || !pl->bwd_warm[mask]) {
+    // first backward with this seed set: in order on the caller's stream (allocations, tensor maps, weight packs happen here)
+    rc = backward_walk(pl, live, s, &n_ops);
+    if (!rc && !pl->bwd_dirty) pl->bwd_warm[mask] = true;
+    return rc;
+  }
+  if (!pl->bwd_exec[mask]) {
+    if (pl->lanes.empty()) { set_error("backward: forward graph state missing"); return MYOLO_E_INVALID; }
+    cudaStream_t cs = pl->lanes[0];
+    MYOLO_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    rc = backward_walk(pl, live, cs, &n_ops);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    if (rc || e != cudaSuccess || pl->bwd_dirty) {
+      if (!rc && e != cudaSuccess) { set_error("backward graph capture failed: %s", cudaGetErrorString(e)); rc = MYOLO_E_CUDA; }
+      if (!rc) { set_error("backward graph capture needed a (re)allocation"); rc = MYOLO_E_INVALID; }
+      cudaGetLastError();
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    cudaError_t ie = cudaGraphInstantiate(&pl->bwd_exec[mask], g, 0);
+    cudaGraphDestroy(g);
+    MYOLO_CHECK_CUDA(ie);
+    pl->bwd_ops[mask] = n_ops;
+  }
+  MYOLO_CHECK_CUDA(cudaGraphLaunch(pl->bwd_exec[mask], s));
+  return 0;
+}
+
+static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s, int* n_ops) {
   const int n = (int)pl->ops.size();
   // which buffers are produced by the input conversion (no data gradient needed into them)
   std::vector<char> is_input_buf(pl->bufs.size(), 0);
   for (const auto& op : pl->ops)
     if (op.kind == MYOLO_OP_INPUT_FOCUS && op.out.buf >= 0) is_input_buf[op.out.buf] = 1;
   int rc = 0;
-  // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
-  // iteration never touches the seg head, the seg pass never the Detect convs (reference train.py:364-392 runs two passes).
-  std::vector<char> live(pl->bufs.size(), 0);
   auto is_live = [&](const myolo_view& v) { return v.buf >= 0 && live[v.buf]; };
   auto mark = [&](const myolo_view& v) { if (v.buf >= 0) live[v.buf] = 1; };
   for (int i = n - 1; i >= 0 && !rc; --i) {
     const myolo_op& op = pl->ops[i];
     TensorView a, b, c, d;
-    if (op.kind != MYOLO_OP_SEG_UPSAMPLE && op.kind != MYOLO_OP_DETECT_DECODE && op.kind != MYOLO_OP_INPUT_FOCUS) {
-      if (!is_live(op.out)) continue;
-      mark(op.in);
-      mark(op.in2);
-    }
+    if (op.kind == MYOLO_OP_SEG_UPSAMPLE || op.kind == MYOLO_OP_DETECT_DECODE || op.kind == MYOLO_OP_INPUT_FOCUS) continue;
+    if (!is_live(op.out)) continue;
+    mark(op.in);
+    mark(op.in2);
+    ++*n_ops;
     switch (op.kind) {
-      case MYOLO_OP_INPUT_FOCUS:
-        break;
-      case MYOLO_OP_SEG_UPSAMPLE:
-        if (!grad_seg) break;
-        if ((rc = grad_view(pl, op.in, &a))) break;
-        mark(op.in);
-        rc = launch_seg_upsample_bwd(grad_seg, op.aux[0], pl->H, pl->W, a, s);
-        break;
-      case MYOLO_OP_DETECT_DECODE:
-        if (!grad_raw || !grad_raw[op.aux[0]]) break;
-        if ((rc = grad_view(pl, op.in, &a))) break;
-        mark(op.in);
-        rc = launch_detect_raw_bwd(grad_raw[op.aux[0]], op.aux[1], op.aux[2], a, s);
-        break;
       case MYOLO_OP_CONV:
         rc = conv_backward(pl, i, !is_input_buf[op.in.buf], s);
         break;
