@@ -30,6 +30,12 @@ static int check_device(int* sms) {
     set_error("no CUDA device: %s", cudaGetErrorString(e));
     return MYOLO_E_NODEVICE;
   }
+  // cudaGetDeviceProperties costs milliseconds (and sometimes far more): query each device once
+  static int cached_sms[64] = {};
+  if (dev >= 0 && dev < 64 && cached_sms[dev] > 0) {
+    if (sms) *sms = cached_sms[dev];
+    return 0;
+  }
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) {
@@ -41,6 +47,7 @@ static int check_device(int* sms) {
               prop.minor, prop.name);
     return MYOLO_E_NODEVICE;
   }
+  if (dev >= 0 && dev < 64) cached_sms[dev] = prop.multiProcessorCount;
   if (sms) *sms = prop.multiProcessorCount;
   return 0;
 }

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=4, help="det images per GPU (= seg images per GPU)")
     ap.add_argument("--kernel-table", default=None, help="write a per-kernel device-time table (torch.profiler / CUPTI, 2 steps) to this file")
+    ap.add_argument("--per-step", action="store_true", help="print synchronised wall time of every step to stderr (diagnostic)")
     ap.add_argument("--breakdown", action="store_true", help="also time the phases of one step separately (extra synchronisation)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -79,6 +80,14 @@ def main():
         k = i % NROT
         return tr.step(imgs[k], tg[k], segimgs[k], masks[k])
 
+    if args.per_step:
+        import time
+        for i in range(args.steps):
+            torch.cuda.synchronize(); t0 = time.time()
+            tr.backward_det(imgs[i % NROT], tg[i % NROT]); torch.cuda.synchronize(); t1 = time.time()
+            tr.backward_seg(segimgs[i % NROT], masks[i % NROT]); torch.cuda.synchronize(); t2 = time.time()
+            tr.optimizer_step(); torch.cuda.synchronize(); t3 = time.time()
+            print("step %2d: det %.1f ms  seg %.1f ms  opt %.1f ms" % (i, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3), file=sys.stderr)
     for i in range(max(args.warmup, 3)):
         step(i)
     torch.cuda.synchronize()
