@@ -49,17 +49,21 @@ def amp_yardstick(cfg, sd, x, Rs, S, ref_raw, ref_seg, ref_sdg):
     return fwd, grd
 
 
-def test_train_forward_and_backward_match_autograd_oracle():
+TRAIN_CASES = {"s_psp": "yolov5s_city_seg.yaml", "m_lab": "yolov5m_city_seg_lab.yaml", "s_base": "yolov5s_city_seg_base.yaml"}
+
+
+@pytest.mark.parametrize("tag", list(TRAIN_CASES))
+def test_train_forward_and_backward_match_autograd_oracle(tag):
     """Parity bar for fp16-storage training: against the fp32 autograd oracle our forward / gradients must be (a) no further away than
     torch's own fp16 autocast of the same graph (x1.25 slack for run-to-run noise) and (b) within absolute bounds: forward 5e-2
     relative Frobenius, gradients median 8e-2 / worst 0.25 with cosine >= 0.98 on every parameter.  (Deep BN networks amplify
     fp16 rounding noise - max-pool argmax flips in SPP alone double the error upstream of it; tools/train_diag.py prints the
     per-layer picture.  Measured on B200: ours 1.3-2.6e-2 fwd, 4.2e-2 median grad; torch autocast 1.5-3.2e-2 fwd, 5.0e-2.)"""
-    model, cfg, sd, x = setup()
+    model, cfg, sd, x = setup(tag, TRAIN_CASES[tag], B=4 if tag == "s_psp" else 2)
     gen = torch.Generator().manual_seed(11)
     out = model(x.cuda())
     raws, seg = out
-    assert len(raws) == 3 and raws[0].shape == (4, 3, 16, 32, 15) and seg.shape == (4, 19, 128, 256) and seg.requires_grad
+    assert len(raws) == 3 and raws[0].shape == (x.shape[0], 3, 16, 32, 15) and seg.shape == (x.shape[0], 19, 128, 256) and seg.requires_grad
     Rs = [torch.randn(r.shape, generator=gen) * 4.0 for r in raws]
     S = torch.randn(seg.shape, generator=gen) * 0.05
     loss = sum((r * R.cuda()).sum() for r, R in zip(raws, Rs)) + (seg * S.cuda()).sum()
@@ -84,11 +88,13 @@ def test_train_forward_and_backward_match_autograd_oracle():
     med, amp_med = float(np.median(list(errs.values()))), float(np.median(list(amp_grd.values())))
     print("gradient rel err: ours median %.3e max %.3e | torch autocast median %.3e max %.3e; worst %s"
           % (med, worst[0][1], amp_med, max(amp_grd.values()), [(k, round(v, 4)) for k, v in worst]))
-    assert len(errs) > 200
+    assert len(errs) > 150
     assert med < 8e-2 and worst[0][1] < 0.25 and min(coss.values()) > 0.98, (med, worst, min(coss.values()))
     assert med <= 1.25 * amp_med, (med, amp_med)
     # biases of the fp32 heads see the fp32 gradient: exact up to summation order
-    assert errs["model.25.m.0.bias"] < 1e-5 and errs["model.24.out.3.bias"] < 1e-5
+    assert errs["model.25.m.0.bias"] < 1e-5
+    if tag == "s_psp":
+        assert errs["model.24.out.3.bias"] < 1e-5
 
 
 def test_running_stats_and_accumulation():
