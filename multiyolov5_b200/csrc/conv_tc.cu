@@ -503,6 +503,11 @@ static int encode_map(CUtensorMap* m, int rank, void* addr, const uint64_t* dims
   return 0;
 }
 
+int encode_tensor_map(CUtensorMap* m, int rank, void* addr, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                      int swizzle_bytes) {
+  return encode_map(m, rank, addr, dims, strides_bytes, box, swizzle_bytes);
+}
+
 static void choose_tile(int W, int H, int* tw, int* th) {
   long best = -1;
   for (int t = 128; t >= 8; t >>= 1) {

@@ -63,6 +63,7 @@ struct WeightSlot {
   float* d_bias = nullptr;
   __half* w_dgrad = nullptr;         // flipped / transposed fp16 pack for the data gradient
   float* zero_bias = nullptr;
+  float* dw_packed = nullptr;        // fp32 [co][k*k][ci] accumulation buffer of the tcgen05 weight-gradient kernel
   bool dgrad_valid = false;          // w_dgrad matches the current master weights
   int dgrad_n_pad = 0, dgrad_cpad = 0;
 };
@@ -215,6 +216,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   }
   for (auto p : pl->bn_stats) if (p) cudaFree(p);
   if (pl->gws) cudaFree(pl->gws);
+  for (auto& sl : pl->slots) if (sl.dw_packed) cudaFree(sl.dw_packed);
   if (pl->tmp16) cudaFree(pl->tmp16);
   if (pl->spp_scratch) cudaFree(pl->spp_scratch);
   delete pl;
@@ -659,11 +661,18 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
     MYOLO_REQUIRE(gout.C == sl.co && sl.co % 16 == 0, "op %d: fp16 conv gradient needs Co %% 16 == 0 (Co=%d)", i, sl.co);
   }
   // weight / bias gradients
-  // (the bias gradient of an fp32 head gradient is summed from the fp32 values, not from their fp16 cast)
-  const bool bias_f32 = gout.dtype == MYOLO_F32 && sl.d_bias;
-  if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, bias_f32 ? nullptr : sl.d_bias, s))) return rc;
-  if (bias_f32) {
-    TensorView gy = gout;
+  if (conv_wgrad_tc_eligible(xin, dy16, op.k, op.stride, op.dil, sl.co, sl.ci)) {
+    if (!sl.dw_packed) {
+      const size_t nb = conv_wgrad_packed_bytes(sl.co, sl.ci, op.k);
+      MYOLO_CHECK_CUDA(cudaMalloc(&sl.dw_packed, nb));
+      MYOLO_CHECK_CUDA(cudaMemset(sl.dw_packed, 0, nb));
+    }
+    if ((rc = launch_conv_wgrad_tc(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.dw_packed, sl.co, sl.ci, pl->num_sms, s))) return rc;
+  } else if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, nullptr, s))) {
+    return rc;
+  }
+  if (sl.d_bias) {   // the bias gradient of an fp32 head gradient is summed from the fp32 values, not from their fp16 cast
+    TensorView gy = gout.dtype == MYOLO_F32 ? gout : dy16;
     gy.C = sl.co;
     if ((rc = launch_bias_grad(gy, sl.d_bias, sl.co, s))) return rc;
   }
@@ -867,6 +876,29 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
         rc = MYOLO_E_INVALID;
     }
   }
+  return rc;
+}
+
+extern "C" int myolo_conv_wgrad(const void* x, const void* dy, int B, int H, int W, int ci, int co, int k, int stride, int dil, float* dW,
+                                int path, void* stream) {
+  MYOLO_REQUIRE(x && dy && dW && B > 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2), "conv_wgrad: bad arguments");
+  int sms = 0;
+  int rc = check_device(&sms);
+  if (rc) return rc;
+  const int pad = dil * (k / 2);
+  const int Ho = (H + 2 * pad - dil * (k - 1) - 1) / stride + 1, Wo = (W + 2 * pad - dil * (k - 1) - 1) / stride + 1;
+  TensorView xv{const_cast<void*>(x), B, H, W, ci, ci, MYOLO_F16};
+  TensorView dv{const_cast<void*>(dy), B, Ho, Wo, co, co, MYOLO_F16};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (path == 0) return launch_conv_wgrad(xv, dv, k, stride, dil, dW, co, ci, nullptr, s);
+  MYOLO_REQUIRE(conv_wgrad_tc_eligible(xv, dv, k, stride, dil, co, ci), "conv_wgrad: geometry not supported by the tcgen05 kernel");
+  float* packed = nullptr;
+  const size_t nb = conv_wgrad_packed_bytes(co, ci, k);
+  MYOLO_CHECK_CUDA(cudaMalloc(&packed, nb));
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(packed, 0, nb, s));
+  rc = launch_conv_wgrad_tc(xv, dv, k, stride, dil, dW, packed, co, ci, sms, s);
+  cudaStreamSynchronize(s);
+  cudaFree(packed);
   return rc;
 }
 

@@ -61,6 +61,11 @@ int launch_bias_grad(const TensorView& dy, float* dbias, int co, cudaStream_t s)
 int launch_grads_check_finite(const float* g, long n, int* found_inf, cudaStream_t s);
 int launch_sgd_step(float* p, float* g, float* buf, const unsigned char* group, long n, const float* lr, const float* wd, int n_groups,
                     float momentum, int nesterov, const float* inv_scale, const int* found_inf, int zero_grad, cudaStream_t s);
+// tcgen05 weight gradient (wgrad_tc.cu): dw_packed is a zeroed fp32 [co][k*k][ci] accumulation buffer owned by the caller
+bool conv_wgrad_tc_eligible(const TensorView& x, const TensorView& dy, int k, int stride, int dil, int co, int ci);
+size_t conv_wgrad_packed_bytes(int co, int ci, int k);
+int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int stride, int dil, float* dW, float* dw_packed, int co, int ci,
+                         int num_sms, cudaStream_t s);
 // tiny maps / fp32 tensors: generic backward straight from the fp32 master weights (dx nullable: += ; dW += ; dbias += )
 int launch_conv_small_bwd(const TensorView& x, const TensorView& dy, const TensorView* dx, const float* w, float* dW, float* dbias, int co,
                           int ci, int k, int stride, int dil, cudaStream_t s);
