@@ -662,8 +662,8 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
   }
   // weight / bias gradients
   if (conv_wgrad_tc_eligible(xin, dy16, op.k, op.stride, op.dil, sl.co, sl.ci)) {
-    if (!sl.dw_packed) {
-      const size_t nb = conv_wgrad_packed_bytes(sl.co, sl.ci, op.k);
+    const size_t nb = conv_wgrad_packed_bytes(sl.d_w, sl.co, sl.ci, op.k);
+    if (!sl.dw_packed && nb) {
       MYOLO_CHECK_CUDA(cudaMalloc(&sl.dw_packed, nb));
       MYOLO_CHECK_CUDA(cudaMemset(sl.dw_packed, 0, nb));
     }
@@ -893,12 +893,14 @@ extern "C" int myolo_conv_wgrad(const void* x, const void* dy, int B, int H, int
   if (path == 0) return launch_conv_wgrad(xv, dv, k, stride, dil, dW, co, ci, nullptr, s);
   MYOLO_REQUIRE(conv_wgrad_tc_eligible(xv, dv, k, stride, dil, co, ci), "conv_wgrad: geometry not supported by the tcgen05 kernel");
   float* packed = nullptr;
-  const size_t nb = conv_wgrad_packed_bytes(co, ci, k);
-  MYOLO_CHECK_CUDA(cudaMalloc(&packed, nb));
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(packed, 0, nb, s));
+  const size_t nb = conv_wgrad_packed_bytes(dW, co, ci, k);
+  if (nb) {
+    MYOLO_CHECK_CUDA(cudaMalloc(&packed, nb));
+    MYOLO_CHECK_CUDA(cudaMemsetAsync(packed, 0, nb, s));
+  }
   rc = launch_conv_wgrad_tc(xv, dv, k, stride, dil, dW, packed, co, ci, sms, s);
   cudaStreamSynchronize(s);
-  cudaFree(packed);
+  if (packed) cudaFree(packed);
   return rc;
 }
 

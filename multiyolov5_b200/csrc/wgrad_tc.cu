@@ -27,6 +27,7 @@ struct WgradTcParams {
   int B, Ho, Wo, Co, Ci, k, stride, dil;
   int Kc, steps_per_row, rows_total, rows_per_cta;
   int m_tiles, n_tiles, N, n_boxes;
+  int bc, ci_pad, a_boxes;            // channels per X box (64 / 32 / 16 -> 128 / 64 / 32-byte swizzle); padded Ci of the packed buffer
   int num_stages, stage_bytes, a_bytes, b_bytes;
   int tmem_cols;
   float* dw_packed;
@@ -34,13 +35,15 @@ struct WgradTcParams {
 
 static constexpr int kWgThreads = 192;
 
-__device__ __forceinline__ uint64_t mn_major_desc(uint32_t saddr, uint32_t lbo_bytes) {
+// MN-major canonical layout: rows of `row_bytes` (128 / 64 / 32 = the swizzle width) per pixel, 8-pixel swizzle atoms
+__device__ __forceinline__ uint64_t mn_major_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next 64-channel chunk
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next group of 8 pixels
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next channel chunk (one box)
+  d |= (uint64_t)((8 * row_bytes) >> 4) << 32;       // stride byte offset: next group of 8 pixels
   d |= (uint64_t)1 << 46;                            // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  d |= layout << 61;                                 // swizzle mode
   return d;
 }
 
@@ -98,9 +101,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
         const int ox0 = st * p.Kc;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_bytes + p.k * p.b_bytes));
+        mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_boxes * p.Kc * 128 + p.k * p.b_bytes));
         tma_load_4d(sa, &tmDy, &full[stage], co0, ox0, oy, b);
-        tma_load_4d(sa + p.Kc * 128, &tmDy, &full[stage], co0 + 64, ox0, oy, b);
+        if (p.a_boxes == 2) tma_load_4d(sa + p.Kc * 128, &tmDy, &full[stage], co0 + 64, ox0, oy, b);
         for (int kx = 0; kx < p.k; ++kx) {
           uint8_t* sb = sa + p.a_bytes + kx * p.b_bytes;
           int ix0, px = 0;
@@ -108,7 +111,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
           else { px = (kx == 1) ? 0 : 1; ix0 = ox0 + (kx == 0 ? -1 : 0); }
           const int m = py * 2 + px;
           const CUtensorMap* tm = m == 0 ? &tmX0 : (m == 1 ? &tmX1 : (m == 2 ? &tmX2 : &tmX3));
-          for (int nb = 0; nb < p.n_boxes; ++nb) tma_load_4d(sb + nb * p.Kc * 128, tm, &full[stage], ci0 + nb * 64, ix0, iy, b);
+          for (int nb = 0; nb < p.n_boxes; ++nb) tma_load_4d(sb + nb * p.Kc * p.bc * 2, tm, &full[stage], ci0 + nb * p.bc, ix0, iy, b);
         }
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
@@ -123,16 +126,18 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t lbo = (uint32_t)p.Kc * 128;
+    const uint32_t rb = (uint32_t)p.bc * 2, lbo_b = (uint32_t)p.Kc * rb;
+    const uint32_t jb = (16 * rb) >> 4;   // descriptor start-address step of B per 16 pixels
     const int jn = p.Kc / 16;
     for (int s = 0; s < n_steps; ++s) {
       mbar_wait(&full[stage], phase);
       tcgen05_fence_after();
       const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-      const uint64_t da = mn_major_desc(sa, lbo);
+      const uint64_t da = mn_major_desc(sa, lbo, 128);
       for (int kx = 0; kx < p.k; ++kx) {
-        const uint64_t db = mn_major_desc(sa + p.a_bytes + kx * p.b_bytes, lbo);
+        const uint64_t db = mn_major_desc(sa + p.a_bytes + kx * p.b_bytes, lbo_b, rb);
         for (int j = 0; j < jn; ++j)   // 16 pixels per instruction = two 8-pixel groups = 2048 bytes
-          umma_f16_ss(tmem_base + kx * p.N, da + (uint64_t)(j * 128), db + (uint64_t)(j * 128), idesc, (uint32_t)((s | j) != 0));
+          umma_f16_ss(tmem_base + kx * p.N, da + (uint64_t)(j * 128), db + (uint64_t)(j * jb), idesc, (uint32_t)((s | j) != 0));
       }
       umma_commit(&empty[stage]);
       if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
@@ -147,7 +152,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
       const int co = co0 + q * 32 + lane;
       const int taps = p.k * p.k;
       for (int kx = 0; kx < p.k; ++kx) {
-        float* dst = p.dw_packed + ((size_t)co * taps + ky * p.k + kx) * p.Ci + ci0;
+        float* dst = p.dw_packed + ((size_t)co * taps + ky * p.k + kx) * p.ci_pad + ci0;
         for (int c = 0; c < p.N; c += 16) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kx * p.N + c, v);
@@ -170,15 +175,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
 }
 
 // dW[co][ci][t] += packed[co][t][ci]; packed = 0
-__global__ void wgrad_unpack_kernel(float* __restrict__ packed, float* __restrict__ dW, int co, int ci, int taps) {
-  const long total = (long)co * ci * taps;
+__global__ void wgrad_unpack_kernel(float* __restrict__ packed, float* __restrict__ dW, int co, int ci, int ci_pad, int taps) {
+  const long total = (long)co * ci_pad * taps;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % ci);
-    const int t = (int)((i / ci) % taps);
-    const int o = (int)(i / ((long)ci * taps));
+    const int c = (int)(i % ci_pad);
+    const int t = (int)((i / ci_pad) % taps);
+    const int o = (int)(i / ((long)ci_pad * taps));
     const float v = packed[i];
     packed[i] = 0.f;
-    dW[((size_t)o * ci + c) * taps + t] += v;
+    if (c < ci) dW[((size_t)o * ci + c) * taps + t] += v;
   }
 }
 
@@ -192,38 +197,51 @@ bool conv_wgrad_tc_eligible(const TensorView& x, const TensorView& dy, int k, in
   if (x.dtype != MYOLO_F16 || dy.dtype != MYOLO_F16) return false;
   if (!(k == 1 || k == 3)) return false;
   if (!((stride == 1) || (stride == 2 && k == 3 && dil == 1 && !((x.H | x.W) & 1)))) return false;
-  if (ci % 64 != 0 || x.C < ci || dy.C < co) return false;
+  const int cp = (ci + 15) / 16 * 16;                       // the view may carry zero-padded channels (layer 0: 12 -> 16)
+  if (!(cp % 64 == 0 || cp == 32 || cp == 16) || x.C < cp || dy.C < co) return false;
   if (dy.W % 16 != 0 || (long)dy.B * dy.H * dy.W < 2048) return false;
   if (x.ctot % 8 != 0 || dy.ctot % 8 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(x.base) & 15) || (reinterpret_cast<uintptr_t>(dy.base) & 15)) return false;
   return true;
 }
 
-size_t conv_wgrad_packed_bytes(int co, int ci, int k) { return (size_t)co * ci * k * k * sizeof(float); }
+// k == 1 with unpadded ci accumulates straight into the caller's [Co][Ci] gradient (when it is 16-byte aligned): no packed buffer
+size_t conv_wgrad_packed_bytes(const float* dW, int co, int ci, int k) {
+  const int cp = (ci + 15) / 16 * 16;
+  const bool direct = k == 1 && cp == ci && (reinterpret_cast<uintptr_t>(dW) & 15) == 0;
+  return direct ? 0 : (size_t)co * cp * k * k * sizeof(float);
+}
 
 int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int stride, int dil, float* dW, float* dw_packed, int co, int ci,
                          int num_sms, cudaStream_t s) {
-  MYOLO_REQUIRE(conv_wgrad_tc_eligible(x, dy, k, stride, dil, co, ci) && dW && dw_packed, "conv_wgrad_tc: unsupported geometry");
+  MYOLO_REQUIRE(conv_wgrad_tc_eligible(x, dy, k, stride, dil, co, ci) && dW, "conv_wgrad_tc: unsupported geometry");
+  const int cp = (ci + 15) / 16 * 16;
+  const bool direct = conv_wgrad_packed_bytes(dW, co, ci, k) == 0;
+  MYOLO_REQUIRE(direct || dw_packed, "conv_wgrad_tc: packed accumulation buffer missing");
   WgradTcParams p;
   memset(&p, 0, sizeof(p));
   p.B = dy.B; p.Ho = dy.H; p.Wo = dy.W; p.Co = co; p.Ci = ci; p.k = k; p.stride = stride; p.dil = dil;
   p.Kc = dy.W % 64 == 0 ? 64 : (dy.W % 32 == 0 ? 32 : 16);
-  p.N = ci % 128 == 0 ? 128 : 64;
-  p.n_boxes = p.N / 64;
-  p.a_bytes = 2 * p.Kc * 128;
-  p.b_bytes = p.n_boxes * p.Kc * 128;
-  p.stage_bytes = p.a_bytes + k * p.b_bytes;
+  p.ci_pad = cp;
+  p.N = cp % 128 == 0 ? 128 : (cp % 64 == 0 ? 64 : cp);
+  p.bc = p.N >= 64 ? 64 : p.N;
+  p.n_boxes = p.N / p.bc;
+  p.a_boxes = co > 64 ? 2 : 1;                          // the second 64-channel dY box is skipped when it would be all padding
+  auto geom = [&]() {
+    p.a_bytes = 2 * p.Kc * 128;                         // (the MMA still addresses 128 rows; rows 64.. feed unused TMEM lanes)
+    p.b_bytes = (int)align_up(p.n_boxes * p.Kc * p.bc * 2, 1024);
+    p.stage_bytes = p.a_bytes + k * p.b_bytes;
+  };
+  geom();
   if (p.stage_bytes > 48 * 1024 && p.Kc > 32) {       // keep at least 4 stages in flight
     p.Kc = 32;
-    p.a_bytes = 2 * p.Kc * 128;
-    p.b_bytes = p.n_boxes * p.Kc * 128;
-    p.stage_bytes = p.a_bytes + k * p.b_bytes;
+    geom();
   }
   p.num_stages = std::min(8, (200 * 1024) / p.stage_bytes);
   p.steps_per_row = p.Wo / p.Kc;
   p.rows_total = p.B * p.Ho;
   p.m_tiles = ceil_div(co, 128);
-  p.n_tiles = ci / p.N;
+  p.n_tiles = cp / p.N;
   const int items = p.m_tiles * p.n_tiles * k;
   int slabs = std::max(1, (2 * num_sms) / items);
   const int min_rows = std::max(1, 8 / p.steps_per_row);            // at least ~8 pipeline steps per CTA
@@ -232,7 +250,7 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
   slabs = ceil_div(p.rows_total, p.rows_per_cta);
   const int cols = k * p.N;
   p.tmem_cols = cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : (cols <= 256 ? 256 : 512)));
-  p.dw_packed = dw_packed;
+  p.dw_packed = direct ? dW : dw_packed;
 
   CUtensorMap tmDy, tmX[4];
   const int esz = 2;
@@ -246,8 +264,8 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
   if (stride == 1) {
     uint64_t dims[4] = {(uint64_t)x.C, (uint64_t)x.W, (uint64_t)x.H, (uint64_t)x.B};
     uint64_t str[3] = {(uint64_t)x.ctot * esz, (uint64_t)x.W * x.ctot * esz, (uint64_t)x.H * x.W * x.ctot * esz};
-    uint32_t box[4] = {64, (uint32_t)p.Kc, 1, 1};
-    int rc = encode_tensor_map(&tmX[0], 4, x.base, dims, str, box, 128);
+    uint32_t box[4] = {(uint32_t)p.bc, (uint32_t)p.Kc, 1, 1};
+    int rc = encode_tensor_map(&tmX[0], 4, x.base, dims, str, box, p.bc * 2);
     if (rc) return rc;
     tmX[1] = tmX[2] = tmX[3] = tmX[0];
   } else {
@@ -255,9 +273,9 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
       for (int px = 0; px < 2; ++px) {
         uint64_t dims[4] = {(uint64_t)x.C, (uint64_t)x.W / 2, (uint64_t)x.H / 2, (uint64_t)x.B};
         uint64_t str[3] = {(uint64_t)2 * x.ctot * esz, (uint64_t)2 * x.W * x.ctot * esz, (uint64_t)x.H * x.W * x.ctot * esz};
-        uint32_t box[4] = {64, (uint32_t)p.Kc, 1, 1};
+        uint32_t box[4] = {(uint32_t)p.bc, (uint32_t)p.Kc, 1, 1};
         void* base = reinterpret_cast<__half*>(x.base) + ((size_t)py * x.W + px) * x.ctot;
-        int rc = encode_tensor_map(&tmX[py * 2 + px], 4, base, dims, str, box, 128);
+        int rc = encode_tensor_map(&tmX[py * 2 + px], 4, base, dims, str, box, p.bc * 2);
         if (rc) return rc;
       }
   }
@@ -269,8 +287,10 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
   }
   conv_wgrad_tc_kernel<<<dim3(items, slabs), kWgThreads, smem, s>>>(tmDy, tmX[0], tmX[1], tmX[2], tmX[3], p);
   MYOLO_LAUNCH_CHECK();
-  wgrad_unpack_kernel<<<std::min(148 * 8, ceil_div(co * ci * k * k, 256)), 256, 0, s>>>(dw_packed, dW, co, ci, k * k);
-  MYOLO_LAUNCH_CHECK();
+  if (!direct) {
+    wgrad_unpack_kernel<<<std::min(148 * 8, ceil_div(co * cp * k * k, 256)), 256, 0, s>>>(dw_packed, dW, co, ci, cp, k * k);
+    MYOLO_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -134,17 +134,21 @@ class Engine:
             return self._flat_grad
         for p in params:
             assert p.dtype == torch.float32 and p.is_cuda, "training keeps fp32 master parameters on the GPU"
-        n = sum(p.numel() for p in params)
+        # every tensor starts on a 16-byte boundary (vector loads / vector reductions in the kernels); the gaps stay zero
+        self._flat_offsets, off = [], 0
+        for p in params:
+            self._flat_offsets.append(off)
+            off += (p.numel() + 3) // 4 * 4
+        n = off
         old = [p.grad for p in params]
         self._flat_grad = torch.zeros(n, dtype=torch.float32, device=params[0].device)
-        self._grad_views, off = [], 0
-        for p, g in zip(params, old):
+        self._grad_views = []
+        for p, g, off in zip(params, old, self._flat_offsets):
             v = self._flat_grad[off:off + p.numel()].view_as(p)
             if g is not None:
                 v.copy_(g)
             p.grad = v
             self._grad_views.append(v)
-            off += p.numel()
         return self._flat_grad
 
     def train_forward(self, x: torch.Tensor):

@@ -57,23 +57,19 @@ class FlatState:
         self.params = [p for p in model.parameters() if p.requires_grad]
         assert self.params and all(p.is_cuda and p.dtype == torch.float32 for p in self.params), "fp32 master parameters on the GPU"
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
+        self.grad = model.engine().ensure_flat_grads()          # defines the (16-byte aligned) offsets shared by all three buffers
+        self.offsets = list(model.engine()._flat_offsets)
+        n = self.grad.numel()
         self.n = n
-        self.param = torch.empty(n, dtype=torch.float32, device=dev)
+        self.param = torch.zeros(n, dtype=torch.float32, device=dev)
         self.momentum = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.group = torch.empty(n, dtype=torch.uint8, device=dev)
+        self.group = torch.ones(n, dtype=torch.uint8, device=dev)
         groups = parameter_groups(model)
-        off = 0
-        self.offsets = []
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             k = p.numel()
             self.param[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.param[off:off + k].view_as(p)
             self.group[off:off + k] = groups.get(id(p), 1)
-            self.offsets.append(off)
-            off += k
-        self.grad = model.engine().ensure_flat_grads()
-        assert self.grad.numel() == n
 
     def check_views(self, model):
         """cheap guard: someone re-assigned parameters (.half(), load_state_dict with assign, .to()) -> views are stale"""
