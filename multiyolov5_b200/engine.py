@@ -151,7 +151,9 @@ class Engine:
             self._grad_views.append(v)
         return self._flat_grad
 
-    def train_forward(self, x: torch.Tensor):
+    def train_forward(self, x: torch.Tensor, out_raws=None, want_seg=True):
+        """out_raws: optional list of three preallocated (B,na,ny,nx,no) fp32 tensors to write the head outputs into (static buffers of a
+        captured loss graph); want_seg=False skips the full-resolution logits (the det pass never reads them)."""
         assert x.is_cuda and x.dim() == 4, "expected a CUDA (B,3,H,W) tensor"
         x = x.contiguous()
         B, _, H, W = x.shape
@@ -182,8 +184,13 @@ class Engine:
         torch._foreach_add_(p._nbt, 1)
         det, seg_head = self.model.model[-1], self.model.model[-2]
         dec = [o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]
-        raws = [torch.empty((B, det.na, v.h, v.w, det.no), dtype=torch.float32, device=x.device) for v in dec]
-        seg = torch.empty((B, seg_head.c_out, H, W), dtype=torch.float32, device=x.device)
+        shapes = [(B, det.na, v.h, v.w, det.no) for v in dec]
+        if out_raws is not None:
+            assert all(tuple(r.shape) == sh and r.dtype == torch.float32 and r.is_contiguous() for r, sh in zip(out_raws, shapes))
+            raws = list(out_raws)
+        else:
+            raws = [torch.empty(sh, dtype=torch.float32, device=x.device) for sh in shapes]
+        seg = torch.empty((B, seg_head.c_out, H, W), dtype=torch.float32, device=x.device) if want_seg else None
         raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])
         _lib.check(L.myolo_plan_train_forward(p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), raw_ptrs, _lib.ptr(seg), sp))
         self.last_plan = p

@@ -84,7 +84,7 @@ class Trainer:
     """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
 
     def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
-                 growth_interval=2000, process_group=None):
+                 growth_interval=2000, process_group=None, graph_loss=True):
         assert next(model.parameters()).is_cuda, "model.cuda() first"
         self.model, self.hyp, self.batch_size = model, hyp, batch_size
         self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
@@ -104,6 +104,8 @@ class Trainer:
         self.found_inf = torch.zeros(1, dtype=torch.int32, device=dev)
         self.inv_scale = torch.ones((), device=dev)
         self.ni = 0
+        self.graph_loss = graph_loss        # replay the detection loss (forward + autograd backward, ~700 tiny kernels) as ONE CUDA graph
+        self._det_graphs = {}
 
     def set_lr(self, lr_bn, lr_weight, lr_bias):
         self.lr = [float(lr_bn), float(lr_weight), float(lr_bias)]
@@ -112,14 +114,63 @@ class Trainer:
         self.momentum = float(m)
 
     # ---- the two passes --------------------------------------------------------------------------------------------
-    def backward_det(self, imgs, targets):
-        pred = self.model(imgs)                                                   # train mode: [[x0,x1,x2], seg]
-        loss, items = self.compute_loss(pred[0], targets)
+    def _det_loss_scaled(self, p, targets):
+        loss, items = self.compute_loss(p, targets)
         if self.rank != -1:
             loss = loss * self.world_size                                         # train.py:367-368
-        loss = loss * self.detgain
-        (loss * self.scale).backward()
-        return items
+        return loss * self.detgain * self.scale, items
+
+    def _det_graph(self, shapes, nt_pad, dev):
+        """static inputs (head outputs, padded targets) -> static outputs (d loss / d head outputs, loss items), captured once per
+        (grid shapes, padded target count).  Padding rows are all-zero targets: zero width/height never matches an anchor."""
+        key = (tuple(shapes), nt_pad)
+        st = self._det_graphs.get(key)
+        if st is not None:
+            return st
+
+        class _St:
+            pass
+        st = _St()
+        st.p = [torch.zeros(sh, dtype=torch.float32, device=dev, requires_grad=True) for sh in shapes]
+        st.t = torch.zeros((nt_pad, 6), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                             # warm-up off the capture stream (allocator, cuBLAS-free)
+            for _ in range(2):
+                for q in st.p:
+                    q.grad = None
+                loss, _ = self._det_loss_scaled(st.p, st.t)
+                loss.backward()
+        torch.cuda.current_stream().wait_stream(side)
+        for q in st.p:
+            q.grad = None
+        st.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st.graph):
+            loss, st.items = self._det_loss_scaled(st.p, st.t)
+            loss.backward()
+        self._det_graphs[key] = st
+        return st
+
+    def backward_det(self, imgs, targets):
+        if not self.graph_loss:
+            pred = self.model(imgs)                                               # train mode: [[x0,x1,x2], seg]
+            loss, items = self._det_loss_scaled(pred[0], targets)
+            loss.backward()
+            return items
+        eng = self.model.engine()
+        B, _, H, W = imgs.shape
+        det = self.model.model[-1]
+        shapes = [(B, det.na, H // int(s), W // int(s), det.no) for s in det.stride.tolist()]
+        nt = targets.shape[0]
+        nt_pad = max(64, (nt + 63) // 64 * 64)
+        st = self._det_graph(shapes, nt_pad, imgs.device)
+        st.t.zero_()
+        if nt:
+            st.t[:nt].copy_(targets)
+        _, _, plan = eng.train_forward(imgs, out_raws=st.p, want_seg=False)       # head outputs land in the graph's static inputs
+        st.graph.replay()
+        eng.train_backward(plan, [q.grad for q in st.p], None)
+        return st.items
 
     def backward_seg(self, segimgs, segtargets):
         pred = self.model(segimgs)
@@ -146,10 +197,10 @@ class Trainer:
                                     float(self.momentum), 1, _lib.ptr(self.inv_scale), _lib.ptr(self.found_inf), 1, sp))
         # amp.GradScaler.update: halve on overflow, double after growth_interval clean steps (device-side, no host sync)
         bad = self.found_inf[0] != 0
-        self.growth_tracker = torch.where(bad, torch.zeros_like(self.growth_tracker), self.growth_tracker + 1)
-        grow = self.growth_tracker >= self.growth_interval
-        self.scale = torch.where(bad, self.scale * 0.5, torch.where(grow, self.scale * 2.0, self.scale))
-        self.growth_tracker = torch.where(grow, torch.zeros_like(self.growth_tracker), self.growth_tracker)
+        tracker = torch.where(bad, torch.zeros_like(self.growth_tracker), self.growth_tracker + 1)
+        grow = tracker >= self.growth_interval
+        self.scale.copy_(torch.where(bad, self.scale * 0.5, torch.where(grow, self.scale * 2.0, self.scale)))   # in place: graphs read it
+        self.growth_tracker.copy_(torch.where(grow, torch.zeros_like(tracker), tracker))
         self.model.engine().weights_dirty = True
 
     def step(self, imgs, targets, segimgs, segtargets):

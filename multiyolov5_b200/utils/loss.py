@@ -73,18 +73,30 @@ class ComputeLoss:
         self.na, self.nc, self.nl, self.anchors = det.na, det.nc, det.nl, det.anchors
         self.balance = {3: [4.0, 1.0, 0.4]}.get(det.nl, [4.0, 1.0, 0.25, 0.06, 0.02])
         self.ssi = list(det.stride).index(16) if autobalance else 0
+        self._cache = {}        # device constants (built once per grid shape: nothing is uploaded from the host inside __call__, which
+                                # keeps the loss capturable in a CUDA graph)
+
+    def _consts(self, dev, ny, nx, i):
+        key = (str(dev), ny, nx, i)
+        c = self._cache.get(key)
+        if c is None:
+            c = dict(gain=torch.tensor([nx, ny], device=dev, dtype=torch.float32),
+                     off=torch.tensor([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]], device=dev, dtype=torch.float32) * 0.5,
+                     anchors=self.anchors[i].to(dev).float().clone())
+            self._cache[key] = c
+        return c
 
     def _elem(self, x, t, pw):
         loss = _bce_with_logits(x, t, pw)
         return _focal(loss, x, t, self.gamma) if self.gamma > 0 else loss
 
-    def assign(self, shape, targets, anchors):
+    def assign(self, shape, targets, anchors, consts=None):
         """Candidate grid for one level.  shape = (ny, nx); targets (nt,6) [img, cls, x, y, w, h] normalised; anchors (na,2) grid units.
         Returns dict of (5,na,nt)-shaped tensors: valid, b, a, gj, gi, tbox (…,4), cls."""
         ny, nx = shape
         dev = targets.device
         nt, na = targets.shape[0], anchors.shape[0]
-        gain = torch.tensor([nx, ny], device=dev, dtype=torch.float32)
+        gain = consts["gain"] if consts else torch.tensor([nx, ny], device=dev, dtype=torch.float32)
         gxy = targets[:, 2:4] * gain
         gwh = targets[:, 4:6] * gain
         r = gwh[None] / anchors[:, None]                                        # (na,nt,2)
@@ -93,7 +105,7 @@ class ComputeLoss:
         near_lo = (gxy % 1.0 < 0.5) & (gxy > 1.0)                               # neighbour on the low side in x / y
         near_hi = (gxi % 1.0 < 0.5) & (gxi > 1.0)
         sel = torch.stack((torch.ones(nt, dtype=torch.bool, device=dev), near_lo[:, 0], near_lo[:, 1], near_hi[:, 0], near_hi[:, 1]))
-        off = torch.tensor([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]], device=dev, dtype=torch.float32) * 0.5
+        off = consts["off"] if consts else torch.tensor([[0, 0], [1, 0], [0, 1], [-1, 0], [0, -1]], device=dev, dtype=torch.float32) * 0.5
         cell = (gxy[None] - off[:, None]).long()                                # (5,nt,2) truncation toward zero
         gi = cell[..., 0].clamp(0, nx - 1)
         gj = cell[..., 1].clamp(0, ny - 1)
@@ -118,8 +130,9 @@ class ComputeLoss:
             n_cells = B * na * ny * nx
             tobj = torch.zeros(n_cells, device=dev)
             if nt:
-                anchors = self.anchors[i].to(dev).float()
-                c = self.assign((ny, nx), targets, anchors)
+                k = self._consts(dev, ny, nx, i)
+                anchors = k["anchors"]
+                c = self.assign((ny, nx), targets, anchors, k)
                 valid = c["valid"]
                 vf = valid.float()
                 n = vf.sum()
