@@ -631,7 +631,9 @@ static int ensure_tmp16(myolo_plan* pl, size_t bytes) {
 }
 
 // backward of one conv op: dY = grad(out); grad(in) += conv^T(dY, W); dW += ...; dbias += ...
-static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s) {
+// `ws`: stream of the weight / bias gradient kernels.  Nothing downstream in the backward pass reads them, so the walk forks them onto a
+// side lane (ws != s) where they overlap the latency-bound chain of data-gradient / BN kernels; the caller joins the lane at the end.
+static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s, cudaStream_t ws, bool* used_side) {
   const myolo_op& op = pl->ops[i];
   WeightSlot& sl = pl->slots[op.weight_slot];
   MYOLO_REQUIRE(sl.set && sl.w_master && sl.d_w, "op %d: conv slot %d has no master weights / gradient pointer", i, op.weight_slot);
@@ -661,20 +663,27 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s)
     MYOLO_REQUIRE(gout.C == sl.co && sl.co % 16 == 0, "op %d: fp16 conv gradient needs Co %% 16 == 0 (Co=%d)", i, sl.co);
   }
   // weight / bias gradients
+  // dY in the shared fp16 scratch (fp32 head gradients) is overwritten by the next conv: those few layers stay on the main stream
+  cudaStream_t wst = (ws != s && gout.dtype != MYOLO_F32 && (int)pl->op_ev.size() > i) ? ws : s;
+  if (wst != s) {
+    MYOLO_CHECK_CUDA(cudaEventRecord(pl->op_ev[i], s));          // dY (and everything before it on the main chain) is final here
+    MYOLO_CHECK_CUDA(cudaStreamWaitEvent(wst, pl->op_ev[i], 0));
+    *used_side = true;
+  }
   if (conv_wgrad_tc_eligible(xin, dy16, op.k, op.stride, op.dil, sl.co, sl.ci)) {
     const size_t nb = conv_wgrad_packed_bytes(sl.d_w, sl.co, sl.ci, op.k);
     if (!sl.dw_packed && nb) {
       MYOLO_CHECK_CUDA(cudaMalloc(&sl.dw_packed, nb));
       MYOLO_CHECK_CUDA(cudaMemset(sl.dw_packed, 0, nb));
     }
-    if ((rc = launch_conv_wgrad_tc(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.dw_packed, sl.co, sl.ci, pl->num_sms, s))) return rc;
-  } else if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, nullptr, s))) {
+    if ((rc = launch_conv_wgrad_tc(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.dw_packed, sl.co, sl.ci, pl->num_sms, wst))) return rc;
+  } else if ((rc = launch_conv_wgrad(xin, dy16, op.k, op.stride, op.dil, sl.d_w, sl.co, sl.ci, nullptr, wst))) {
     return rc;
   }
   if (sl.d_bias) {   // the bias gradient of an fp32 head gradient is summed from the fp32 values, not from their fp16 cast
     TensorView gy = gout.dtype == MYOLO_F32 ? gout : dy16;
     gy.C = sl.co;
-    if ((rc = launch_bias_grad(gy, sl.d_bias, sl.co, s))) return rc;
+    if ((rc = launch_bias_grad(gy, sl.d_bias, sl.co, wst))) return rc;
   }
   if (!need_dgrad) return 0;
   // data gradient = stride-1 conv of (zero-stuffed) dY with flipped / transposed weights, accumulated into grad(in)
@@ -816,6 +825,14 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
   int rc = 0;
   auto is_live = [&](const myolo_view& v) { return v.buf >= 0 && live[v.buf]; };
   auto mark = [&](const myolo_view& v) { if (v.buf >= 0) live[v.buf] = 1; };
+  static int side_env = -1;
+  if (side_env < 0) {
+    const char* e = getenv("MYOLO_WGRAD_LANE");
+    side_env = e ? atoi(e) : 1;
+  }
+  // weight-gradient lane (exists once the forward graph has created the plan's streams / events)
+  cudaStream_t side = (side_env && pl->lanes.size() >= 2 && pl->lanes[1] != s && (int)pl->op_ev.size() >= n + 2) ? pl->lanes[1] : s;
+  bool used_side = false;
   for (int i = n - 1; i >= 0 && !rc; --i) {
     const myolo_op& op = pl->ops[i];
     TensorView a, b, c, d;
@@ -826,7 +843,7 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
     ++*n_ops;
     switch (op.kind) {
       case MYOLO_OP_CONV:
-        rc = conv_backward(pl, i, !is_input_buf[op.in.buf], s);
+        rc = conv_backward(pl, i, !is_input_buf[op.in.buf], s, side, &used_side);
         break;
       case MYOLO_OP_BN_ACT: {
         const bool has_res = op.in2.buf >= 0;
@@ -874,6 +891,11 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
       default:
         set_error("backward: op %d of kind %d has no backward (training supports the PSP-head graphs)", i, op.kind);
         rc = MYOLO_E_INVALID;
+    }
+  }
+  if (used_side) {   // join the weight-gradient lane (required to close a capture; in eager mode it orders the optimiser after it)
+    if (cudaEventRecord(pl->op_ev[n + 1], side) != cudaSuccess || cudaStreamWaitEvent(s, pl->op_ev[n + 1], 0) != cudaSuccess) {
+      if (!rc) { set_error("backward: joining the weight-gradient lane failed"); rc = MYOLO_E_CUDA; }
     }
   }
   return rc;

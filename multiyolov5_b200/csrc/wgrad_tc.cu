@@ -244,7 +244,7 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
   p.n_tiles = cp / p.N;
   const int items = p.m_tiles * p.n_tiles * k;
   int slabs = std::max(1, (2 * num_sms) / items);
-  const int min_rows = std::max(1, 8 / p.steps_per_row);            // at least ~8 pipeline steps per CTA
+  const int min_rows = std::max(1, 4 / p.steps_per_row);            // at least ~4 pipeline steps per CTA
   slabs = std::min(slabs, std::max(1, p.rows_total / min_rows));
   p.rows_per_cta = ceil_div(p.rows_total, slabs);
   slabs = ceil_div(p.rows_total, p.rows_per_cta);
