@@ -149,6 +149,15 @@ int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t
                    const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale /* device */,
                    const int32_t* found_inf /* device, nullable */, int zero_grad, void* stream);
 
+/* ---- pre-process ----
+ * `letterbox` of reference utils/datasets.py:818-848 (cv2.resize INTER_LINEAR to resized_w x resized_h, constant border) on uint8 HWC
+ * frames (B,H0,W0,3), bit exact with OpenCV's 8-bit path; optionally fused with the BGR->RGB swap, HWC->CHW transpose
+ * (utils/datasets.py:185-189) and the uint8 -> fp16/fp32 /255 conversion (detect.py:135-137).  The caller computes the geometry
+ * (resized size, top/left offsets, output H x W) with the reference's host arithmetic.  pad_bgr: 3 ints in SOURCE channel order (NULL =
+ * 114).  out: (B,3,H,W) if chw else (B,H,W,3), dtype MYOLO_U8 / MYOLO_F16 / MYOLO_F32 (float = value / 255). */
+int myolo_letterbox(const uint8_t* src, int B, int H0, int W0, int resized_w, int resized_h, int top, int left, int H, int W,
+                    const int32_t* pad_bgr, void* out, int out_dtype, int chw, int swap_rb, void* stream);
+
 /* ---- post-process ---- */
 /* utils.general.non_max_suppression (reference utils/general.py:421-509).  pred: (B,A,no) fp32.
  * out: (B,max_det,6) fp32 rows [x1,y1,x2,y2,conf,cls] in the reference's order; out_count: (B) int32.

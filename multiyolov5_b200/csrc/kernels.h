@@ -28,4 +28,8 @@ int launch_seg_upsample(const TensorView& in, int n_cls, int H, int W, void* seg
                         cudaStream_t s);
 int launch_read_view(const TensorView& v, float* dst_nchw, cudaStream_t s);
 
+// pre-process (preprocess.cu): letterbox resize + border + channel swap / layout / dtype conversion of uint8 HWC frames
+int launch_letterbox(const unsigned char* src, int B, int H0, int W0, int rw, int rh, int top, int left, int H, int W, const int* pad3,
+                     void* dst, int out_dtype, int chw, int swap_rb, cudaStream_t s);
+
 }  // namespace myolo

@@ -901,6 +901,13 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
   return rc;
 }
 
+extern "C" int myolo_letterbox(const uint8_t* src, int B, int H0, int W0, int resized_w, int resized_h, int top, int left, int H, int W,
+                               const int32_t* pad_bgr, void* out, int out_dtype, int chw, int swap_rb, void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  return launch_letterbox(src, B, H0, W0, resized_w, resized_h, top, left, H, W, pad_bgr, out, out_dtype, chw, swap_rb, (cudaStream_t)stream);
+}
+
 extern "C" int myolo_conv_wgrad(const void* x, const void* dy, int B, int H, int W, int ci, int co, int k, int stride, int dil, float* dW,
                                 int path, void* stream) {
   MYOLO_REQUIRE(x && dy && dW && B > 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2), "conv_wgrad: bad arguments");

@@ -190,6 +190,31 @@ def gen_loss(ref_yolo):
     print("loss", {k: v.shape for k, v in cases.items() if "loss" in k or "items" in k})
 
 
+def gen_letterbox():
+    """the reference's own `letterbox` (utils/datasets.py:818-848, cv2 underneath) on small synthetic frames + one photo crop"""
+    import cv2
+    import utils.datasets as ref_datasets     # the reference's module (sys.path set by import_reference)
+    rs = np.random.RandomState(9)
+    cases = {}
+    photo = cv2.imread(os.path.join(ref_shims.REF_ROOT, "data", "images", "bus.jpg"))
+    frames = {"rand_a": rs.randint(0, 256, (97, 131, 3), dtype=np.uint8), "rand_b": rs.randint(0, 256, (128, 256, 3), dtype=np.uint8),
+              "photo": np.ascontiguousarray(photo[200:360, 300:520]) if photo is not None else rs.randint(0, 256, (160, 220, 3), dtype=np.uint8),
+              "smooth": (np.add.outer(np.arange(150), np.arange(90))[..., None] * np.array([1, 2, 3]) % 256).astype(np.uint8)}
+    settings = {"a64": dict(new_shape=64, stride=32), "half": dict(new_shape=(64, 128), stride=32), "up": dict(new_shape=192, stride=32),
+                "noauto": dict(new_shape=(96, 160), auto=False), "fill": dict(new_shape=(80, 112), auto=False, scaleFill=True),
+                "noup": dict(new_shape=320, scaleup=False, stride=64)}
+    meta = {}
+    for fn, frame in frames.items():
+        cases[f"in_{fn}"] = frame
+        for sn, kw in settings.items():
+            out, ratio, dwdh = ref_datasets.letterbox(frame.copy(), **kw)
+            cases[f"out_{fn}_{sn}"] = out
+            meta[f"{fn}_{sn}"] = dict(kw=kw, ratio=[float(ratio[0]), float(ratio[1])], dwdh=[float(dwdh[0]), float(dwdh[1])])
+    cases["meta_json"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLD, "letterbox_cases.npz"), **cases)
+    print("letterbox", len(meta), "cases")
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cwd = os.getcwd()
@@ -203,3 +228,5 @@ if __name__ == "__main__":
         gen_segpost()
     if not only or "loss" in only:
         gen_loss(ref_yolo)
+    if not only or "letterbox" in only:
+        gen_letterbox()

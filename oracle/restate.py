@@ -620,3 +620,90 @@ def compute_det_loss(p: List[torch.Tensor], targets: np.ndarray, anchors: np.nda
 def seg_ce_loss(seg: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     """SegmentationLosses.forward without aux (reference utils/loss.py:235-237) == CrossEntropyLoss(ignore_index=-1), mean over valid"""
     return F.cross_entropy(seg, mask, ignore_index=-1)
+
+
+# ------------------------------------------------------------------------------------------------
+# pre-process (SURVEY.md section 8f rank 1): letterbox + BGR->RGB + HWC->CHW  (reference utils/datasets.py:818-848, :185-189)
+# The arithmetic lives in a third-party dependency that is not under /root/reference: OpenCV `cv2.resize(..., INTER_LINEAR)` and
+# `cv2.copyMakeBorder` (requirements.txt: opencv-python>=4.1.2; 4.13.0 installed).  Its published 8-bit algorithm (imgproc/resize.cpp)
+# is restated here and pinned against cv2 itself through the fixtures (tests/golden/letterbox_cases.npz, generated by running the
+# reference's own `letterbox`).
+# ------------------------------------------------------------------------------------------------
+def _cv_lin_coeffs(dst: int, src: int):
+    """source index / fraction per destination index: fx = float((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double"""
+    scale = 1.0 / (float(dst) / float(src))
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int32)
+    return s, (f - s.astype(np.float32)).astype(np.float32)
+
+
+def cv2_resize_linear_u8(img: np.ndarray, dw: int, dh: int) -> np.ndarray:
+    """cv2.resize(img, (dw, dh), interpolation=cv2.INTER_LINEAR) for uint8 HWC images, bit for bit:
+    * exact 2x down-scaling is routed to the INTER_AREA fast path: (a + b + c + d + 2) >> 2;
+    * otherwise 11-bit fixed point: coefficients saturate_cast<short>(w * 2048) (round half to even), horizontal pass in int32,
+      vertical pass ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2; x indices clamp with fx = 0 at both borders,
+      y rows clamp."""
+    sh, sw = img.shape[:2]
+    sx_, sy_ = 1.0 / (dw / sw), 1.0 / (dh / sh)
+    eps = np.finfo(np.float64).eps
+    if abs(sx_ - 2) < eps and abs(sy_ - 2) < eps:
+        a = img.astype(np.int32)
+        return ((a[0::2, 0::2] + a[0::2, 1::2] + a[1::2, 0::2] + a[1::2, 1::2] + 2) >> 2).astype(np.uint8)
+    sx, fx = _cv_lin_coeffs(dw, sw)
+    lo = sx < 0
+    fx = np.where(lo, np.float32(0), fx); sx = np.where(lo, 0, sx)
+    hi = sx >= sw - 1
+    fx = np.where(hi, np.float32(0), fx); sx = np.where(hi, sw - 1, sx)
+    a0 = np.rint((np.float32(1) - fx) * np.float32(2048)).astype(np.int32)
+    a1 = np.rint(fx * np.float32(2048)).astype(np.int32)
+    sx1 = np.minimum(sx + 1, sw - 1)
+    sy, fy = _cv_lin_coeffs(dh, sh)
+    b0 = np.rint((np.float32(1) - fy) * np.float32(2048)).astype(np.int32)
+    b1 = np.rint(fy * np.float32(2048)).astype(np.int32)
+    y0, y1 = np.clip(sy, 0, sh - 1), np.clip(sy + 1, 0, sh - 1)
+    s = img.astype(np.int32)
+    hz = s[:, sx] * a0[None, :, None] + s[:, sx1] * a1[None, :, None]
+    out = (((b0[:, None, None] * (hz[y0] >> 4)) >> 16) + ((b1[:, None, None] * (hz[y1] >> 4)) >> 16) + 2) >> 2
+    return out.astype(np.uint8)
+
+
+def letterbox_geometry(shape, new_shape=(640, 640), auto=True, scaleFill=False, scaleup=True, stride=32):
+    """the host arithmetic of reference utils/datasets.py:818-845: returns (new_unpad (w,h), ratio (w,h), (dw,dh), (top,bottom,left,right))"""
+    if isinstance(new_shape, int):
+        new_shape = (new_shape, new_shape)
+    r = min(new_shape[0] / shape[0], new_shape[1] / shape[1])
+    if not scaleup:
+        r = min(r, 1.0)
+    ratio = r, r
+    new_unpad = int(round(shape[1] * r)), int(round(shape[0] * r))
+    dw, dh = new_shape[1] - new_unpad[0], new_shape[0] - new_unpad[1]
+    if auto:
+        dw, dh = np.mod(dw, stride), np.mod(dh, stride)
+    elif scaleFill:
+        dw, dh = 0.0, 0.0
+        new_unpad = (new_shape[1], new_shape[0])
+        ratio = new_shape[1] / shape[1], new_shape[0] / shape[0]
+    dw /= 2
+    dh /= 2
+    top, bottom = int(round(dh - 0.1)), int(round(dh + 0.1))
+    left, right = int(round(dw - 0.1)), int(round(dw + 0.1))
+    return new_unpad, ratio, (dw, dh), (top, bottom, left, right)
+
+
+def letterbox_np(img: np.ndarray, new_shape=(640, 640), color=(114, 114, 114), auto=True, scaleFill=False, scaleup=True, stride=32):
+    """reference utils/datasets.py:818-848 `letterbox` (uint8 HWC in, padded uint8 HWC out, ratio, (dw, dh))"""
+    shape = img.shape[:2]
+    new_unpad, ratio, (dw, dh), (top, bottom, left, right) = letterbox_geometry(shape, new_shape, auto, scaleFill, scaleup, stride)
+    if shape[::-1] != new_unpad:
+        img = cv2_resize_linear_u8(img, new_unpad[0], new_unpad[1])
+    out = np.empty((img.shape[0] + top + bottom, img.shape[1] + left + right, 3), np.uint8)
+    out[...] = np.array(color, np.uint8)
+    out[top:top + img.shape[0], left:left + img.shape[1]] = img
+    return out, ratio, (dw, dh)
+
+
+def preprocess_np(img0: np.ndarray, img_size=640, stride=32) -> np.ndarray:
+    """LoadImages.__next__ (reference utils/datasets.py:185-189): letterbox, BGR->RGB, HWC->CHW; uint8 (3,H,W)"""
+    img = letterbox_np(img0, img_size, stride=stride)[0]
+    return np.ascontiguousarray(img[:, :, ::-1].transpose(2, 0, 1))

@@ -125,3 +125,17 @@ def test_seg_loss_matches_reference():
         loss.backward()
         assert abs(float(loss.detach()) - float(g["seg_loss"])) <= 1e-6
         assert np.abs(seg.grad.numpy() - g["seg_grad"]).max() <= 1e-9
+
+
+# ---- pre-process: fixtures from the reference's own letterbox (cv2.resize / copyMakeBorder underneath) ----
+def test_letterbox_restatement_bit_exact():
+    g = np.load(os.path.join(GOLD, "letterbox_cases.npz"))
+    meta = json.loads(bytes(g["meta_json"]).decode())
+    assert len(meta) >= 24
+    for key, m in meta.items():
+        fn, sn = key.rsplit("_", 1)
+        out, ratio, dwdh = restate.letterbox_np(g[f"in_{fn}"], **m["kw"])
+        ref = g[f"out_{key}"]
+        assert out.shape == ref.shape, (key, out.shape, ref.shape)
+        assert np.array_equal(out, ref), (key, int((out != ref).sum()))          # integer arithmetic: bit exact
+        assert np.allclose(ratio, m["ratio"]) and np.allclose(dwdh, m["dwdh"]), key
