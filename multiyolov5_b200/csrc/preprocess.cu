@@ -1,7 +1,7 @@
 // Device-side pre-process: letterbox (cv2.resize INTER_LINEAR + constant border 114) fused with
 // BGR->RGB, HWC->CHW and the uint8 -> fp16/fp32 /255 conversion - the step right before Model.forward (reference
 // utils/datasets.py:818-848 `letterbox`, :185-189 LoadImages, detect.py:135-137).  Integer work: bit exact with OpenCV's 8-bit path
-// (11-bit fixed-point coefficients, two-pass rounding; exact 2x down-scaling = 2x2 area mean), see oracle/restate.py.
+// (11-bit fixed-point coefficients, two-pass rounding; exact 2x down-scaling = 2x2 area mean); parity: tests/test_gpu_pre.py.
 // HBM bound: reads <= 4 source pixels per output pixel (L1/L2 absorb the overlap), writes the output once.
 #include "kernels.h"
 
@@ -79,8 +79,9 @@ __global__ void letterbox_kernel(const LetterboxParams p) {
       const int val = v[p.swap_rb ? 2 - c : c];
       const size_t o = p.chw ? (((size_t)b * 3 + c) * p.H + y) * p.W + x : (((size_t)b * p.H + y) * p.W + x) * 3 + c;
       if (p.out_dtype == MYOLO_U8) reinterpret_cast<unsigned char*>(p.dst)[o] = (unsigned char)val;
-      else if (p.out_dtype == MYOLO_F16) reinterpret_cast<__half*>(p.dst)[o] = __float2half_rn(__fdiv_rn((float)val, 255.0f));
-      else reinterpret_cast<float*>(p.dst)[o] = __fdiv_rn((float)val, 255.0f);
+      // `img /= 255.0` on a CUDA tensor (detect.py:137): ATen multiplies by the fp32 reciprocal of a scalar divisor
+      else if (p.out_dtype == MYOLO_F16) reinterpret_cast<__half*>(p.dst)[o] = __float2half_rn(__fmul_rn((float)val, 1.0f / 255.0f));
+      else reinterpret_cast<float*>(p.dst)[o] = __fmul_rn((float)val, 1.0f / 255.0f);
     }
   }
 }

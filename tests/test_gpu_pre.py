@@ -50,5 +50,5 @@ def test_preprocess_batch_of_frames():
     frames = rs.randint(0, 256, (3, 300, 400, 3), dtype=np.uint8)
     out, _, _ = preprocess(torch.from_numpy(frames).cuda(), 256, stride=32, half=False)
     for b in range(3):
-        want = torch.from_numpy(restate.preprocess_np(frames[b], 256, stride=32)).float() / 255.0
-        assert torch.equal(out[b].cpu(), want)
+        want = torch.from_numpy(restate.preprocess_np(frames[b], 256, stride=32)).cuda().float() / 255.0    # CUDA arithmetic, as detect.py
+        assert torch.equal(out[b], want)
