@@ -158,6 +158,17 @@ int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t
 int myolo_letterbox(const uint8_t* src, int B, int H0, int W0, int resized_w, int resized_h, int top, int left, int H, int W,
                     const int32_t* pad_bgr, void* out, int out_dtype, int chw, int swap_rb, void* stream);
 
+/* ---- consumers of the seg output ----
+ * myolo_seg_lut_blend: out[i][c] = lut[class_map[i]][c] (label2image / trainid2id, reference detect.py:69-77; reverse_channels gives the
+ * BGR order of detect.py:193) and, if `blend` is given, blend[i][c] = cv2.addWeighted(out, alpha, image, beta, 0) (detect.py:194).
+ * class_map: uint8 or int64 (dtype code); lut: device (n_entries x channels) uint8; out / blend: (n_pixels x channels) uint8, each nullable.
+ * myolo_seg_metrics: the counters of utils/metrics.py:234-275 from a class map and int64 labels (-1 = ignore), ACCUMULATED into
+ * counters[2 + 3*n_classes] (device uint64): [correct, labeled, intersection[n], prediction area[n], label area[n]]. */
+int myolo_seg_lut_blend(const void* class_map, int map_dtype, int64_t n_pixels, const uint8_t* lut, int n_entries, int channels,
+                        int reverse_channels, uint8_t* out, const uint8_t* image, float alpha, float beta, uint8_t* blend, void* stream);
+int myolo_seg_metrics(const void* pred, int pred_dtype, const int64_t* target, int64_t n_pixels, int n_classes, uint64_t* counters,
+                      void* stream);
+
 /* ---- post-process ---- */
 /* utils.general.non_max_suppression (reference utils/general.py:421-509).  pred: (B,A,no) fp32.
  * out: (B,max_det,6) fp32 rows [x1,y1,x2,y2,conf,cls] in the reference's order; out_count: (B) int32.

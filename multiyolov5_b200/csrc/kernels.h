@@ -32,4 +32,9 @@ int launch_read_view(const TensorView& v, float* dst_nchw, cudaStream_t s);
 int launch_letterbox(const unsigned char* src, int B, int H0, int W0, int rw, int rh, int top, int left, int H, int W, const int* pad3,
                      void* dst, int out_dtype, int chw, int swap_rb, cudaStream_t s);
 
+// seg output consumers (consumers.cu)
+int launch_lut_blend(const void* idx, int idx_dtype, long n, const unsigned char* lut, int n_entries, int ch, int reverse, unsigned char* out,
+                     const unsigned char* im, float alpha, float beta, unsigned char* blend, cudaStream_t s);
+int launch_seg_hist(const void* pred, int pred_dtype, const long long* target, long n, int n_cls, unsigned long long* counters, cudaStream_t s);
+
 }  // namespace myolo

@@ -908,6 +908,23 @@ extern "C" int myolo_letterbox(const uint8_t* src, int B, int H0, int W0, int re
   return launch_letterbox(src, B, H0, W0, resized_w, resized_h, top, left, H, W, pad_bgr, out, out_dtype, chw, swap_rb, (cudaStream_t)stream);
 }
 
+extern "C" int myolo_seg_lut_blend(const void* class_map, int map_dtype, int64_t n_pixels, const uint8_t* lut, int n_entries, int channels,
+                                   int reverse_channels, uint8_t* out, const uint8_t* image, float alpha, float beta, uint8_t* blend,
+                                   void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  return launch_lut_blend(class_map, map_dtype, (long)n_pixels, lut, n_entries, channels, reverse_channels, out, image, alpha, beta, blend,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int myolo_seg_metrics(const void* pred, int pred_dtype, const int64_t* target, int64_t n_pixels, int n_classes, uint64_t* counters,
+                                 void* stream) {
+  int rc = check_device(nullptr);
+  if (rc) return rc;
+  return launch_seg_hist(pred, pred_dtype, reinterpret_cast<const long long*>(target), (long)n_pixels, n_classes,
+                         reinterpret_cast<unsigned long long*>(counters), (cudaStream_t)stream);
+}
+
 extern "C" int myolo_conv_wgrad(const void* x, const void* dy, int B, int H, int W, int ci, int co, int k, int stride, int dil, float* dW,
                                 int path, void* stream) {
   MYOLO_REQUIRE(x && dy && dW && B > 0 && (k == 1 || k == 3) && (stride == 1 || stride == 2), "conv_wgrad: bad arguments");

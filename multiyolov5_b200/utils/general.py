@@ -67,3 +67,52 @@ def bilinear_align_corners(seg, out_hw):
     out = torch.empty((B, Cc, out_hw[0], out_hw[1]), dtype=torch.float32, device=seg.device)
     _lib.check(_lib.lib().myolo_bilinear_nchw(_lib.ptr(seg), B, Cc, h, w, out_hw[0], out_hw[1], _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+# ---- seg output consumers (reference detect.py:69-77,193-194,206) ----
+# standard Cityscapes trainId palette (RGB) and trainId -> labelId table, the data of detect.py:19-61
+Cityscapes_COLORMAP = [[128, 64, 128], [244, 35, 232], [70, 70, 70], [102, 102, 156], [190, 153, 153], [153, 153, 153], [250, 170, 30],
+                       [220, 220, 0], [107, 142, 35], [152, 251, 152], [0, 130, 180], [220, 20, 60], [255, 0, 0], [0, 0, 142], [0, 0, 70],
+                       [0, 60, 100], [0, 80, 100], [0, 0, 230], [119, 11, 32]]
+Cityscapes_IDMAP = [[7], [8], [11], [12], [13], [17], [19], [20], [21], [22], [23], [24], [25], [26], [27], [28], [31], [32], [33]]
+_lut_cache = {}
+
+
+def _lut(table, device):
+    key = (id(table), str(device))
+    if key not in _lut_cache:
+        _lut_cache[key] = torch.tensor(table, dtype=torch.uint8, device=device).contiguous()
+    return _lut_cache[key]
+
+
+def _lut_call(pred, table, reverse, image=None, alpha=0.0, beta=0.0, want_out=True):
+    assert pred.is_cuda and pred.dtype in (torch.uint8, torch.int64), "class map: CUDA uint8 / int64 tensor"
+    pred = pred.contiguous()
+    lut = _lut(table, pred.device)
+    n_entries, ch = lut.shape
+    out = torch.empty(tuple(pred.shape) + (ch,), dtype=torch.uint8, device=pred.device) if want_out else None
+    blend = None
+    if image is not None:
+        image = image.contiguous()
+        assert image.dtype == torch.uint8 and tuple(image.shape) == tuple(pred.shape) + (ch,) and image.is_cuda
+        blend = torch.empty_like(image)
+    _lib.check(_lib.lib().myolo_seg_lut_blend(_lib.ptr(pred), _lib.torch_dtype_code(pred.dtype), pred.numel(), _lib.ptr(lut), n_entries, ch,
+                                              int(reverse), _lib.ptr(out), _lib.ptr(image), float(alpha), float(beta), _lib.ptr(blend),
+                                              _lib.stream_ptr()))
+    return out, blend
+
+
+def label2image(pred, COLORMAP=Cityscapes_COLORMAP):
+    """class ids (H,W) -> (H,W,3) uint8 colours (reference detect.py:69-72), on the device"""
+    return _lut_call(pred, COLORMAP, False)[0]
+
+
+def trainid2id(pred, IDMAP=Cityscapes_IDMAP):
+    """trainIds -> Cityscapes label ids (H,W,1) uint8 (reference detect.py:74-77), on the device"""
+    return _lut_call(pred, IDMAP, False)[0]
+
+
+def seg_overlay(pred, im0, COLORMAP=Cityscapes_COLORMAP, alpha=0.4, beta=0.6):
+    """detect.py:193-194 in one kernel: mask = label2image(pred)[:, :, ::-1] (BGR) and dst = cv2.addWeighted(mask, alpha, im0, beta, 0).
+    pred: (H,W) class map, im0: (H,W,3) uint8 BGR frame, both on the GPU.  Returns (mask, dst)."""
+    return _lut_call(pred, COLORMAP, True, image=im0, alpha=alpha, beta=beta)

@@ -215,6 +215,30 @@ def gen_letterbox():
     print("letterbox", len(meta), "cases")
 
 
+def gen_consumers():
+    """seg output consumers: the reference's label2image / trainid2id (detect.py:69-77), the blend
+    cv2.addWeighted(mask, 0.4, im0, 0.6, 0) (detect.py:194) and batch_pix_accuracy / batch_intersection_union (utils/metrics.py:234-275)"""
+    import importlib
+    import cv2
+    det = importlib.import_module("detect")
+    met = importlib.import_module("utils.metrics")
+    rs = np.random.RandomState(21)
+    cases = {"colormap": np.array(det.Cityscapes_COLORMAP, np.uint8), "idmap": np.array(det.Cityscapes_IDMAP, np.uint8)}
+    pred = rs.randint(0, 19, (96, 160)).astype(np.int64)
+    im0 = rs.randint(0, 256, (96, 160, 3), dtype=np.uint8)
+    mask = det.label2image(pred, det.Cityscapes_COLORMAP)[:, :, ::-1]
+    cases.update(pred=pred, im0=im0, mask_bgr=np.ascontiguousarray(mask), ids=det.trainid2id(pred, det.Cityscapes_IDMAP),
+                 blend=cv2.addWeighted(np.ascontiguousarray(mask), 0.4, im0, 0.6, 0))
+    out = torch.from_numpy(rs.normal(0, 1, (2, 19, 48, 64)).astype(np.float32))
+    tgt = torch.from_numpy(rs.randint(-1, 19, (2, 48, 64)).astype(np.int64))
+    correct, labeled = met.batch_pix_accuracy(out, tgt)
+    inter, union = met.batch_intersection_union(out, tgt, 19)
+    cases.update(m_out=out.numpy(), m_tgt=tgt.numpy(), m_correct=np.int64(correct), m_labeled=np.int64(labeled), m_inter=inter.astype(np.int64),
+                 m_union=union.astype(np.int64))
+    np.savez_compressed(os.path.join(GOLD, "consumer_cases.npz"), **cases)
+    print("consumers", int(correct), int(labeled), inter[:4], union[:4])
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cwd = os.getcwd()
@@ -230,3 +254,5 @@ if __name__ == "__main__":
         gen_loss(ref_yolo)
     if not only or "letterbox" in only:
         gen_letterbox()
+    if not only or "consumers" in only:
+        gen_consumers()

@@ -707,3 +707,32 @@ def preprocess_np(img0: np.ndarray, img_size=640, stride=32) -> np.ndarray:
     """LoadImages.__next__ (reference utils/datasets.py:185-189): letterbox, BGR->RGB, HWC->CHW; uint8 (3,H,W)"""
     img = letterbox_np(img0, img_size, stride=stride)[0]
     return np.ascontiguousarray(img[:, :, ::-1].transpose(2, 0, 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# seg output consumers (SURVEY.md section 8f rank 2)
+# ------------------------------------------------------------------------------------------------
+def label2image_np(pred: np.ndarray, colormap: np.ndarray) -> np.ndarray:
+    """detect.py:69-72 (also trainid2id :74-77): palette look-up, (H,W) class ids -> (H,W,ch) uint8"""
+    return np.asarray(colormap, np.uint8)[pred.astype(np.int32), :]
+
+
+def add_weighted_u8(a: np.ndarray, alpha: float, b: np.ndarray, beta: float) -> np.ndarray:
+    """cv2.addWeighted(a, alpha, b, beta, 0) for uint8 (detect.py:194): fp32 products and sum, round half to even, saturate"""
+    r = a.astype(np.float32) * np.float32(alpha) + b.astype(np.float32) * np.float32(beta)
+    return np.clip(np.rint(r), 0, 255).astype(np.uint8)
+
+
+def seg_metrics_np(output: np.ndarray, target: np.ndarray, nclass: int):
+    """batch_pix_accuracy + batch_intersection_union (reference utils/metrics.py:234-275) on (B,C,H,W) logits and (B,H,W) labels with
+    -1 = ignore: returns (pixel_correct, pixel_labeled, area_inter[nclass], area_union[nclass])"""
+    predict = output.argmax(1).astype(np.int64) + 1          # torch.max(output, 1): first maximum wins, like numpy
+    tgt = target.astype(np.int64) + 1
+    labeled = int((tgt > 0).sum())
+    correct = int(((predict == tgt) * (tgt > 0)).sum())
+    predict = predict * (tgt > 0)
+    inter = predict * (predict == tgt)
+    area_inter, _ = np.histogram(inter, bins=nclass, range=(1, nclass))
+    area_pred, _ = np.histogram(predict, bins=nclass, range=(1, nclass))
+    area_lab, _ = np.histogram(tgt, bins=nclass, range=(1, nclass))
+    return correct, labeled, area_inter.astype(np.int64), (area_pred + area_lab - area_inter).astype(np.int64)

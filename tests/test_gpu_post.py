@@ -94,3 +94,30 @@ def test_seg_argmax_full_size_property():
     # oracle on a crop-sized case
     small = lo[:1, :, :8, :16].contiguous()
     assert np.array_equal(seg_argmax(small, (64, 128)).cpu().numpy(), restate.seg_postprocess(small.cpu().numpy(), (64, 128)))
+
+
+# ---- consumers of the seg output: fixtures from the reference's detect.py / utils/metrics.py ----
+def test_seg_consumers_match_reference_fixtures():
+    import os
+    from multiyolov5_b200.utils.general import label2image, seg_overlay, trainid2id
+    from multiyolov5_b200.utils.metrics import batch_intersection_union, batch_pix_accuracy, seg_eval_batch
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "consumer_cases.npz"))
+    for dt in (torch.int64, torch.uint8):
+        pred = torch.from_numpy(g["pred"]).to(dt).cuda()
+        assert np.array_equal(label2image(pred).cpu().numpy()[:, :, ::-1], g["mask_bgr"])
+        assert np.array_equal(trainid2id(pred).cpu().numpy(), g["ids"])
+        mask, dst = seg_overlay(pred, torch.from_numpy(g["im0"]).cuda())
+        assert np.array_equal(mask.cpu().numpy(), g["mask_bgr"]) and np.array_equal(dst.cpu().numpy(), g["blend"])
+    out, tgt = torch.from_numpy(g["m_out"]).cuda(), torch.from_numpy(g["m_tgt"]).cuda()
+    assert batch_pix_accuracy(out, tgt) == (int(g["m_correct"]), int(g["m_labeled"]))
+    inter, union = batch_intersection_union(out, tgt, 19)
+    assert np.array_equal(inter, g["m_inter"]) and np.array_equal(union, g["m_union"])
+    # fused path from low-resolution logits at full size (test.py:38-41): against the oracle on the same inputs
+    from oracle import restate
+    rs = np.random.RandomState(2)
+    seg = rs.normal(0, 1, (2, 19, 64, 128)).astype(np.float32)
+    tg = rs.randint(-1, 19, (2, 512, 1024)).astype(np.int64)
+    c, l, inter, union = seg_eval_batch(torch.from_numpy(seg).cuda(), torch.from_numpy(tg).cuda(), 19)
+    up = restate.bilinear_align_corners_np(seg, (512, 1024))
+    c0, l0, i0, u0 = restate.seg_metrics_np(up, tg, 19)
+    assert l == l0 and abs(c - c0) <= 1e-4 * l0 and np.abs(inter - i0).max() <= 1e-3 * max(1, i0.max())   # argmax near-ties only

@@ -139,3 +139,14 @@ def test_letterbox_restatement_bit_exact():
         assert out.shape == ref.shape, (key, out.shape, ref.shape)
         assert np.array_equal(out, ref), (key, int((out != ref).sum()))          # integer arithmetic: bit exact
         assert np.allclose(ratio, m["ratio"]) and np.allclose(dwdh, m["dwdh"]), key
+
+
+def test_seg_consumer_restatements_match_reference():
+    g = np.load(os.path.join(GOLD, "consumer_cases.npz"))
+    mask = restate.label2image_np(g["pred"], g["colormap"])[:, :, ::-1]
+    assert np.array_equal(mask, g["mask_bgr"])
+    assert np.array_equal(restate.label2image_np(g["pred"], g["idmap"]), g["ids"])
+    assert np.array_equal(restate.add_weighted_u8(g["mask_bgr"], 0.4, g["im0"], 0.6), g["blend"])
+    c, l, inter, union = restate.seg_metrics_np(g["m_out"], g["m_tgt"], 19)
+    assert (c, l) == (int(g["m_correct"]), int(g["m_labeled"]))
+    assert np.array_equal(inter, g["m_inter"]) and np.array_equal(union, g["m_union"])
