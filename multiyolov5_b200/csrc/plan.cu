@@ -111,6 +111,7 @@ struct myolo_plan {
   int bwd_ops[16] = {};
   bool bwd_warm[16] = {};
   bool bwd_dirty = false;
+  void* ce_scratch = nullptr;      // 16 bytes for the fused seg loss (valid-pixel count, loss sum)
 };
 
 static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
@@ -218,6 +219,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   if (pl->gws) cudaFree(pl->gws);
   for (auto& sl : pl->slots) if (sl.dw_packed) cudaFree(sl.dw_packed);
   if (pl->tmp16) cudaFree(pl->tmp16);
+  if (pl->ce_scratch) cudaFree(pl->ce_scratch);
   if (pl->spp_scratch) cudaFree(pl->spp_scratch);
   delete pl;
 }
@@ -564,6 +566,16 @@ extern "C" int myolo_plan_read_view(myolo_plan* pl, myolo_view view, float* dst,
   return launch_read_view(v, dst, (cudaStream_t)stream);
 }
 
+// debug / parity tests: the same slice of the GRADIENT workspace (valid after a backward call)
+extern "C" int myolo_plan_read_grad_view(myolo_plan* pl, myolo_view view, float* dst, void* stream) {
+  MYOLO_REQUIRE(pl && dst && pl->gws, "read_grad_view: null argument / no backward has run");
+  TensorView v;
+  int rc = resolve_view(pl, view, &v);
+  if (rc) return rc;
+  v.base = pl->gws + (reinterpret_cast<unsigned char*>(v.base) - pl->ws);
+  return launch_read_view(v, dst, (cudaStream_t)stream);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // training: forward with batch-statistics BN, backward over the op list in reverse
@@ -767,19 +779,8 @@ static int refresh_dgrad_packs(myolo_plan* pl, cudaStream_t s) {
 
 static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s, int* n_ops);
 
-extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream) {
-  MYOLO_REQUIRE(pl && pl->train_fwd_done, "backward: call myolo_plan_train_forward first");
-  cudaStream_t s = (cudaStream_t)stream;
-  if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
-  int mask = grad_seg ? 8 : 0;
-  for (int i = 0; i < 3; ++i)
-    if (grad_raw && grad_raw[i]) mask |= 1 << i;
-  // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
-  // iteration never touches the seg head, the seg pass never the Detect convs (reference train.py:364-392 runs two passes).
-  std::vector<char> live(pl->bufs.size(), 0);
-  int rc = backward_seeds(pl, grad_raw, grad_seg, live, s);
-  if (rc) return rc;
+static int backward_run(myolo_plan* pl, int mask, std::vector<char>& live, cudaStream_t s) {
+  int rc;
   if ((rc = refresh_dgrad_packs(pl, s))) return rc;
   if (pl->bwd_dirty) {
     for (auto& e : pl->bwd_exec) if (e) { cudaGraphExecDestroy(e); e = nullptr; }
@@ -814,6 +815,46 @@ extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw,
   }
   MYOLO_CHECK_CUDA(cudaGraphLaunch(pl->bwd_exec[mask], s));
   return 0;
+}
+
+extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream) {
+  MYOLO_REQUIRE(pl && pl->train_fwd_done, "backward: call myolo_plan_train_forward first");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
+  int mask = grad_seg ? 8 : 0;
+  for (int i = 0; i < 3; ++i)
+    if (grad_raw && grad_raw[i]) mask |= 1 << i;
+  // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
+  // iteration never touches the seg head, the seg pass never the Detect convs (reference train.py:364-392 runs two passes).
+  std::vector<char> live(pl->bufs.size(), 0);
+  int rc = backward_seeds(pl, grad_raw, grad_seg, live, s);
+  if (rc) return rc;
+  return backward_run(pl, mask, live, s);
+}
+
+// fused seg loss: CE(ignore_index) of the x8-upsampled logits of the last train forward is evaluated and
+// differentiated straight from the low-resolution logits; the backward then runs as the seg pass (seed mask 8)
+extern "C" int myolo_plan_backward_seg_ce(myolo_plan* pl, const int64_t* labels, int ignore_index, float factor, const float* scale_dev,
+                                          float* loss_out, void* stream) {
+  MYOLO_REQUIRE(pl && pl->train_fwd_done && labels, "backward_seg_ce: call myolo_plan_train_forward first / null labels");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
+  if (!pl->ce_scratch) MYOLO_CHECK_CUDA(cudaMalloc(&pl->ce_scratch, 16));
+  std::vector<char> live(pl->bufs.size(), 0);
+  int rc = MYOLO_E_INVALID;
+  for (const auto& op : pl->ops)
+    if (op.kind == MYOLO_OP_SEG_UPSAMPLE) {
+      TensorView lo, dlo;
+      if ((rc = resolve_view(pl, op.in, &lo)) || (rc = grad_view(pl, op.in, &dlo))) return rc;
+      live[op.in.buf] = 1;
+      rc = launch_seg_ce_fused(lo, op.aux[0], reinterpret_cast<const long long*>(labels), pl->H, pl->W, ignore_index, dlo, factor, scale_dev,
+                               pl->ce_scratch, loss_out, s);
+      break;
+    }
+  if (rc) { if (rc == MYOLO_E_INVALID) set_error("backward_seg_ce: the plan has no segmentation output"); return rc; }
+  return backward_run(pl, 8, live, s);
 }
 
 static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s, int* n_ops) {

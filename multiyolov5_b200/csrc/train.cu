@@ -616,6 +616,113 @@ int launch_seg_upsample_bwd(const float* dseg, int n_cls, int H, int W, const Te
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused segmentation loss: CrossEntropyLoss(ignore_index) of the x8 bilinear (align_corners=True) upsample
+// of the low-resolution logits, forward AND backward, without materialising the (B,C,H,W) logits or their gradient
+// (reference models/yolo.py:163 + utils/loss.py:237 + autograd).  Thread = (low-res pixel, chunk of its footprint rows): every
+// full-resolution pixel that reads this low-res pixel is revisited, its interpolated logits and softmax are recomputed from the 4
+// low-res neighbours, and (p - onehot) * weight is accumulated; the thread that owns the pixel's top-left neighbour adds its loss.
+//   dlo[b,y,x,c] += coef * sum_{(Y,X) reading (y,x)} w(Y,X;y,x) * (softmax_c(z(Y,X)) - [c == t(Y,X)]),   coef = factor * scale / n_valid
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+__global__ void count_valid_kernel(const long long* __restrict__ labels, long n, int ignore_index, unsigned long long* out) {
+  unsigned int c = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) c += labels[i] != ignore_index;
+  c = __reduce_add_sync(0xFFFFFFFFu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
+}
+
+template <int MAXC>
+__global__ void seg_ce_fused_kernel(TensorView lo, int ncls, const long long* __restrict__ labels, int H, int W, int ignore_index,
+                                    TensorView dlo, float factor, const float* __restrict__ scale_dev,
+                                    const unsigned long long* __restrict__ n_valid, float* loss_sum, int rsplit) {
+  const long total = (long)lo.B * lo.H * lo.W * rsplit;
+  const unsigned long long nv = *n_valid;
+  const float coef = nv ? factor * (scale_dev ? *scale_dev : 1.0f) / (float)nv : 0.f;
+  float loss_local = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int part = (int)(i % rsplit);
+    long p = i / rsplit;
+    const int x = (int)(p % lo.W); p /= lo.W;
+    const int y = (int)(p % lo.H);
+    const int b = (int)(p / lo.H);
+    int ylo, yhi, xlo, xhi;
+    dst_range(y, lo.H, H, &ylo, &yhi);
+    dst_range(x, lo.W, W, &xlo, &xhi);
+    const int rows = yhi - ylo + 1, per = (rows + rsplit - 1) / rsplit;
+    const int r0 = ylo + part * per, r1 = min(yhi, r0 + per - 1);
+    float acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+    for (int Y = r0; Y <= r1; ++Y) {
+      int a0, a1; float w0, w1;
+      lerp_src(Y, lo.H, H, &a0, &a1, &w0, &w1);
+      const float wy = (a0 == y ? w0 : 0.f) + (a1 == y ? w1 : 0.f);
+      if (wy == 0.f) continue;
+      const long long* lab_row = labels + ((size_t)b * H + Y) * W;
+      for (int X = xlo; X <= xhi; ++X) {
+        int b0, b1; float v0, v1;
+        lerp_src(X, lo.W, W, &b0, &b1, &v0, &v1);
+        const float wx = (b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f);
+        if (wx == 0.f) continue;
+        const long long t = lab_row[X];
+        if (t == ignore_index) continue;
+        const float* q00 = tvf(lo, b, a0, b0); const float* q01 = tvf(lo, b, a0, b1);
+        const float* q10 = tvf(lo, b, a1, b0); const float* q11 = tvf(lo, b, a1, b1);
+        const float c00 = w0 * v0, c01 = w0 * v1, c10 = w1 * v0, c11 = w1 * v1;
+        float z[MAXC];
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < ncls) { z[c] = c00 * q00[c] + c01 * q01[c] + c10 * q10[c] + c11 * q11[c]; m = fmaxf(m, z[c]); }
+        float ssum = 0.f, zt = 0.f;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < ncls) { if (c == (int)t) zt = z[c]; z[c] = __expf(z[c] - m); ssum += z[c]; }
+        const float inv = 1.0f / ssum, wgt = wy * wx;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
+          if (c < ncls) acc[c] += wgt * (z[c] * inv - (c == (int)t ? 1.0f : 0.f));
+        if (a0 == y && b0 == x) loss_local += __logf(ssum) + m - zt;      // this thread owns the pixel's top-left neighbour
+      }
+    }
+    float* d = tvf(dlo, b, y, x);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c)
+      if (c < ncls && acc[c] != 0.f) atomicAdd(d + c, acc[c] * coef);
+  }
+  loss_local = warp_sum(loss_local);
+  if ((threadIdx.x & 31) == 0 && loss_local != 0.f) atomicAdd(loss_sum, loss_local);
+}
+
+__global__ void seg_ce_finalize_kernel(const float* loss_sum, const unsigned long long* n_valid, float* loss_out) {
+  if (loss_out) *loss_out = *n_valid ? *loss_sum / (float)*n_valid : 0.f;     // mean over the valid pixels (F.cross_entropy)
+}
+
+// scratch: 16 bytes (n_valid u64, loss_sum f32).  loss_out (device, nullable) receives the mean CE.
+int launch_seg_ce_fused(const TensorView& lo, int n_cls, const long long* labels, int H, int W, int ignore_index, const TensorView& dlo,
+                        float factor, const float* scale_dev, void* scratch16, float* loss_out, cudaStream_t s) {
+  MYOLO_REQUIRE(lo.dtype == MYOLO_F32 && dlo.dtype == MYOLO_F32 && n_cls >= 1 && n_cls <= 32 && lo.C >= n_cls && labels && scratch16,
+                "seg_ce_fused: fp32 low-resolution logits with <= 32 classes expected");
+  unsigned long long* n_valid = reinterpret_cast<unsigned long long*>(scratch16);
+  float* loss_sum = reinterpret_cast<float*>(n_valid + 1);
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch16, 0, 16, s));
+  const long n = (long)lo.B * H * W;
+  count_valid_kernel<<<grid_for_t(n, 256, 148 * 8), 256, 0, s>>>(labels, n, ignore_index, n_valid);
+  MYOLO_LAUNCH_CHECK();
+  const int rsplit = 4;
+  seg_ce_fused_kernel<32><<<grid_for_t((long)lo.B * lo.H * lo.W * rsplit, 128), 128, 0, s>>>(lo, n_cls, labels, H, W, ignore_index, dlo, factor,
+                                                                                           scale_dev, n_valid, loss_sum, rsplit);
+  MYOLO_LAUNCH_CHECK();
+  seg_ce_finalize_kernel<<<1, 1, 0, s>>>(loss_sum, n_valid, loss_out);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void detect_raw_bwd_kernel(const float* __restrict__ draw, int na, int no, TensorView dconv) {
   const long total = (long)dconv.B * na * dconv.H * dconv.W * no;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {

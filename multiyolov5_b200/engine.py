@@ -202,6 +202,22 @@ class Engine:
         ptrs = (C.c_void_p * 3)(*[_lib.ptr(g) for g in gr])
         _lib.check(_lib.lib().myolo_plan_backward(plan.handle, ptrs, _lib.ptr(gs), _lib.stream_ptr()))
 
+    def train_backward_seg_ce(self, plan, labels, factor=1.0, scale=None, ignore_index=-1):
+        """fused seg loss + backward: mean CE(ignore_index) of the upsampled logits of the last train forward
+        against `labels` (B,H,W) int64; gradients scaled by factor * scale (device scalar tensor).  Returns the mean CE (device scalar)."""
+        assert labels.is_cuda and labels.dtype == torch.int64 and tuple(labels.shape) == (plan.B, plan.H, plan.W)
+        loss = torch.empty((), dtype=torch.float32, device=labels.device)
+        _lib.check(_lib.lib().myolo_plan_backward_seg_ce(plan.handle, _lib.ptr(labels.contiguous()), int(ignore_index), float(factor),
+                                                         _lib.ptr(scale), _lib.ptr(loss), _lib.stream_ptr()))
+        return loss
+
+    def read_grad_view(self, v, plan=None):
+        """debug: NHWC slice of the gradient workspace -> (B,C,H,W) fp32 torch tensor"""
+        p = plan or self.last_plan
+        out = torch.empty((p.B, v.c, v.h, v.w), dtype=torch.float32, device="cuda")
+        _lib.check(_lib.lib().myolo_plan_read_grad_view(p.handle, _lib.View(v.buf.id, v.c_off, v.c), _lib.ptr(out), _lib.stream_ptr()))
+        return out
+
     def launches(self):
         return int(_lib.lib().myolo_plan_last_launch_count(self.last_plan.handle)) if self.last_plan else 0
 

@@ -84,7 +84,7 @@ class Trainer:
     """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
 
     def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
-                 growth_interval=2000, process_group=None, graph_loss=True):
+                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True):
         assert next(model.parameters()).is_cuda, "model.cuda() first"
         self.model, self.hyp, self.batch_size = model, hyp, batch_size
         self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
@@ -106,6 +106,7 @@ class Trainer:
         self.ni = 0
         self.graph_loss = graph_loss        # replay the detection loss (forward + autograd backward, ~700 tiny kernels) as ONE CUDA graph
         self._det_graphs = {}
+        self.fused_seg_loss = fused_seg_loss  # CE + x8 upsample forward/backward in one kernel, no full-resolution logits (plain heads only)
 
     def set_lr(self, lr_bn, lr_weight, lr_bias):
         self.lr = [float(lr_bn), float(lr_weight), float(lr_bias)]
@@ -173,6 +174,11 @@ class Trainer:
         return st.items
 
     def backward_seg(self, segimgs, segtargets):
+        if self.fused_seg_loss:
+            eng = self.model.engine()
+            _, _, plan = eng.train_forward(segimgs, want_seg=False)
+            loss = eng.train_backward_seg_ce(plan, segtargets, factor=self.batch_size * self.seggain, scale=self.scale)
+            return loss * (self.batch_size * self.seggain)
         pred = self.model(segimgs)
         segloss = self.compute_seg_loss(pred[1], segtargets) * self.batch_size * self.seggain   # train.py:385,391
         (segloss * self.scale).backward()

@@ -278,3 +278,35 @@ def test_graphed_det_loss_equals_eager_path():
     named = dict(model.named_parameters())
     assert torch.isfinite(items).all() and float(named["model.25.m.0.weight"].grad.abs().sum()) > 0
     assert float(named["model.24.out.3.weight"].grad.abs().sum()) == 0.0      # det pass leaves the seg head untouched
+
+
+def test_fused_seg_ce_matches_torch_on_the_same_logits():
+    """CE(ignore -1) of the x8 bilinear upsample, forward + backward from the low-resolution logits in one kernel.  On the
+    SAME low-res logits torch gives (interpolate -> cross_entropy -> autograd): loss to 1e-5, d loss / d logits to 1e-4 relative."""
+    from multiyolov5_b200 import _lib
+    model, cfg, sd, x = setup(B=2, H=128, W=256)
+    eng = model.engine()
+    rs = np.random.RandomState(5)
+    labels = torch.from_numpy(rs.randint(-1, 19, (2, 128, 256)).astype(np.int64)).cuda()
+    labels[0, :40] = -1                                               # a block of ignored pixels
+    for it in range(3):                                               # eager, warm, graph replay
+        model.zero_grad(set_to_none=False)
+        _, _, plan = eng.train_forward(x.cuda(), want_seg=False)
+        scale = torch.full((), 8.0, device="cuda")
+        loss = eng.train_backward_seg_ce(plan, labels, factor=0.5, scale=scale)
+        v = [o.in_ for o in plan.pb.ops if o.kind == _lib.OP_SEG_UPSAMPLE][0]
+        lo = eng.read_view(v, plan).clone().requires_grad_(True)
+        dlo = eng.read_grad_view(v, plan)
+        up = torch.nn.functional.interpolate(lo[:, :19], (128, 256), mode="bilinear", align_corners=True)
+        ref = torch.nn.functional.cross_entropy(up, labels, ignore_index=-1)
+        (ref * 0.5 * 8.0).backward()
+        torch.cuda.synchronize()
+        assert abs(float(loss) - float(ref)) < 1e-5 * max(1.0, abs(float(ref))), (it, float(loss), float(ref))
+        assert rel_f(dlo[:, :19].cpu(), lo.grad[:, :19].cpu()) < 1e-4, it
+        named = dict(model.named_parameters())
+        assert float(named["model.24.out.3.weight"].grad.abs().sum()) > 0 and float(named["model.25.m.0.weight"].grad.abs().sum()) == 0.0
+    # all labels ignored: zero loss, zero gradients, no NaN
+    model.zero_grad(set_to_none=False)
+    _, _, plan = eng.train_forward(x.cuda(), want_seg=False)
+    loss = eng.train_backward_seg_ce(plan, torch.full_like(labels, -1))
+    assert float(loss) == 0.0 and float(dict(model.named_parameters())["model.24.out.3.weight"].grad.abs().sum()) == 0.0
