@@ -112,6 +112,8 @@ struct myolo_plan {
   bool bwd_warm[16] = {};
   bool bwd_dirty = false;
   void* ce_scratch = nullptr;      // 16 bytes for the fused seg loss (valid-pixel count, loss sum)
+  float* ce_gbuf = nullptr;        // per-pixel (softmax - onehot), NHWC fp32, of the fused seg loss
+  size_t ce_gbuf_bytes = 0;
 };
 
 static int resolve_view(const myolo_plan* pl, const myolo_view& v, TensorView* out) {
@@ -220,6 +222,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   for (auto& sl : pl->slots) if (sl.dw_packed) cudaFree(sl.dw_packed);
   if (pl->tmp16) cudaFree(pl->tmp16);
   if (pl->ce_scratch) cudaFree(pl->ce_scratch);
+  if (pl->ce_gbuf) cudaFree(pl->ce_gbuf);
   if (pl->spp_scratch) cudaFree(pl->spp_scratch);
   delete pl;
 }
@@ -849,8 +852,16 @@ extern "C" int myolo_plan_backward_seg_ce(myolo_plan* pl, const int64_t* labels,
       TensorView lo, dlo;
       if ((rc = resolve_view(pl, op.in, &lo)) || (rc = grad_view(pl, op.in, &dlo))) return rc;
       live[op.in.buf] = 1;
+      const size_t gb = seg_ce_scratch_bytes(pl->B, pl->H, pl->W, op.aux[0]);
+      if (pl->ce_gbuf_bytes < gb) {
+        if (pl->ce_gbuf) cudaFree(pl->ce_gbuf);
+        pl->ce_gbuf = nullptr;
+        pl->ce_gbuf_bytes = 0;
+        MYOLO_CHECK_CUDA(cudaMalloc(&pl->ce_gbuf, gb));
+        pl->ce_gbuf_bytes = gb;
+      }
       rc = launch_seg_ce_fused(lo, op.aux[0], reinterpret_cast<const long long*>(labels), pl->H, pl->W, ignore_index, dlo, factor, scale_dev,
-                               pl->ce_scratch, loss_out, s);
+                               pl->ce_scratch, pl->ce_gbuf, loss_out, s);
       break;
     }
   if (rc) { if (rc == MYOLO_E_INVALID) set_error("backward_seg_ce: the plan has no segmentation output"); return rc; }

@@ -636,77 +636,104 @@ __global__ void count_valid_kernel(const long long* __restrict__ labels, long n,
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
 
-template <int MAXC>
-__global__ void seg_ce_fused_kernel(TensorView lo, int ncls, const long long* __restrict__ labels, int H, int W, int ignore_index,
-                                    TensorView dlo, float factor, const float* __restrict__ scale_dev,
-                                    const unsigned long long* __restrict__ n_valid, float* loss_sum, int rsplit) {
-  const long total = (long)lo.B * lo.H * lo.W * rsplit;
+// pass 1: one thread per FULL-resolution pixel: interpolated logits from the 4 low-res neighbours -> softmax -> (p - onehot) written as
+// NC_PAD fp32 per pixel (zeros for ignored pixels); the pixel's loss is reduced per warp.
+template <int NC, int NC_PAD>
+__global__ void seg_ce_pixel_kernel(TensorView lo, const long long* __restrict__ labels, int H, int W, int ignore_index, float* __restrict__ g,
+                                    float* loss_sum) {
+  const long total = (long)lo.B * H * W;
+  float loss_local = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W);
+    const int Y = (int)((i / W) % H);
+    const int b = (int)(i / ((long)W * H));
+    const long long t = labels[i];
+    float v[NC_PAD];
+#pragma unroll
+    for (int c = 0; c < NC_PAD; ++c) v[c] = 0.f;
+    if (t != ignore_index) {
+      int a0, a1, b0, b1; float w0, w1, v0, v1;
+      lerp_src(Y, lo.H, H, &a0, &a1, &w0, &w1);
+      lerp_src(X, lo.W, W, &b0, &b1, &v0, &v1);
+      const float* q00 = tvf(lo, b, a0, b0); const float* q01 = tvf(lo, b, a0, b1);
+      const float* q10 = tvf(lo, b, a1, b0); const float* q11 = tvf(lo, b, a1, b1);
+      const float c00 = w0 * v0, c01 = w0 * v1, c10 = w1 * v0, c11 = w1 * v1;
+      float m = -INFINITY, zt = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { v[c] = c00 * q00[c] + c01 * q01[c] + c10 * q10[c] + c11 * q11[c]; m = fmaxf(m, v[c]); }
+      float ssum = 0.f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) { if (c == (int)t) zt = v[c]; v[c] = __expf(v[c] - m); ssum += v[c]; }
+      const float inv = 1.0f / ssum;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) v[c] = v[c] * inv - (c == (int)t ? 1.0f : 0.f);
+      loss_local += __logf(ssum) + m - zt;
+    }
+    float4* dst = reinterpret_cast<float4*>(g + (size_t)i * NC_PAD);
+#pragma unroll
+    for (int c = 0; c < NC_PAD; c += 4) dst[c / 4] = make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]);
+  }
+  loss_local = warp_sum(loss_local);
+  if ((threadIdx.x & 31) == 0 && loss_local != 0.f) atomicAdd(loss_sum, loss_local);
+}
+
+// pass 2: adjoint of the bilinear upsample, gathered per low-res pixel (x a chunk of its footprint rows) from the per-pixel gradients
+template <int NC, int NC_PAD>
+__global__ void seg_ce_gather_kernel(const float* __restrict__ g, int H, int W, TensorView dlo, float factor, const float* __restrict__ scale_dev,
+                                     const unsigned long long* __restrict__ n_valid, int rsplit) {
+  const long total = (long)dlo.B * dlo.H * dlo.W * rsplit;
   const unsigned long long nv = *n_valid;
   const float coef = nv ? factor * (scale_dev ? *scale_dev : 1.0f) / (float)nv : 0.f;
-  float loss_local = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int part = (int)(i % rsplit);
     long p = i / rsplit;
-    const int x = (int)(p % lo.W); p /= lo.W;
-    const int y = (int)(p % lo.H);
-    const int b = (int)(p / lo.H);
+    const int x = (int)(p % dlo.W); p /= dlo.W;
+    const int y = (int)(p % dlo.H);
+    const int b = (int)(p / dlo.H);
     int ylo, yhi, xlo, xhi;
-    dst_range(y, lo.H, H, &ylo, &yhi);
-    dst_range(x, lo.W, W, &xlo, &xhi);
+    dst_range(y, dlo.H, H, &ylo, &yhi);
+    dst_range(x, dlo.W, W, &xlo, &xhi);
     const int rows = yhi - ylo + 1, per = (rows + rsplit - 1) / rsplit;
     const int r0 = ylo + part * per, r1 = min(yhi, r0 + per - 1);
-    float acc[MAXC];
+    float acc[NC_PAD];
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c) acc[c] = 0.f;
+    for (int c = 0; c < NC_PAD; ++c) acc[c] = 0.f;
     for (int Y = r0; Y <= r1; ++Y) {
       int a0, a1; float w0, w1;
-      lerp_src(Y, lo.H, H, &a0, &a1, &w0, &w1);
+      lerp_src(Y, dlo.H, H, &a0, &a1, &w0, &w1);
       const float wy = (a0 == y ? w0 : 0.f) + (a1 == y ? w1 : 0.f);
       if (wy == 0.f) continue;
-      const long long* lab_row = labels + ((size_t)b * H + Y) * W;
+      const float* row = g + ((size_t)b * H + Y) * W * NC_PAD;
       for (int X = xlo; X <= xhi; ++X) {
         int b0, b1; float v0, v1;
-        lerp_src(X, lo.W, W, &b0, &b1, &v0, &v1);
-        const float wx = (b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f);
-        if (wx == 0.f) continue;
-        const long long t = lab_row[X];
-        if (t == ignore_index) continue;
-        const float* q00 = tvf(lo, b, a0, b0); const float* q01 = tvf(lo, b, a0, b1);
-        const float* q10 = tvf(lo, b, a1, b0); const float* q11 = tvf(lo, b, a1, b1);
-        const float c00 = w0 * v0, c01 = w0 * v1, c10 = w1 * v0, c11 = w1 * v1;
-        float z[MAXC];
-        float m = -INFINITY;
+        lerp_src(X, dlo.W, W, &b0, &b1, &v0, &v1);
+        const float wgt = wy * ((b0 == x ? v0 : 0.f) + (b1 == x ? v1 : 0.f));
+        if (wgt == 0.f) continue;
+        const float4* q = reinterpret_cast<const float4*>(row + (size_t)X * NC_PAD);
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-          if (c < ncls) { z[c] = c00 * q00[c] + c01 * q01[c] + c10 * q10[c] + c11 * q11[c]; m = fmaxf(m, z[c]); }
-        float ssum = 0.f, zt = 0.f;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-          if (c < ncls) { if (c == (int)t) zt = z[c]; z[c] = __expf(z[c] - m); ssum += z[c]; }
-        const float inv = 1.0f / ssum, wgt = wy * wx;
-#pragma unroll
-        for (int c = 0; c < MAXC; ++c)
-          if (c < ncls) acc[c] += wgt * (z[c] * inv - (c == (int)t ? 1.0f : 0.f));
-        if (a0 == y && b0 == x) loss_local += __logf(ssum) + m - zt;      // this thread owns the pixel's top-left neighbour
+        for (int c = 0; c < NC_PAD; c += 4) {
+          const float4 u = q[c / 4];
+          acc[c] += wgt * u.x; acc[c + 1] += wgt * u.y; acc[c + 2] += wgt * u.z; acc[c + 3] += wgt * u.w;
+        }
       }
     }
     float* d = tvf(dlo, b, y, x);
 #pragma unroll
-    for (int c = 0; c < MAXC; ++c)
-      if (c < ncls && acc[c] != 0.f) atomicAdd(d + c, acc[c] * coef);
+    for (int c = 0; c < NC; ++c)
+      if (acc[c] != 0.f) atomicAdd(d + c, acc[c] * coef);
   }
-  loss_local = warp_sum(loss_local);
-  if ((threadIdx.x & 31) == 0 && loss_local != 0.f) atomicAdd(loss_sum, loss_local);
 }
 
 __global__ void seg_ce_finalize_kernel(const float* loss_sum, const unsigned long long* n_valid, float* loss_out) {
   if (loss_out) *loss_out = *n_valid ? *loss_sum / (float)*n_valid : 0.f;     // mean over the valid pixels (F.cross_entropy)
 }
 
-// scratch: 16 bytes (n_valid u64, loss_sum f32).  loss_out (device, nullable) receives the mean CE.
+size_t seg_ce_scratch_bytes(int B, int H, int W, int n_cls) { return (size_t)B * H * W * (n_cls <= 20 ? 20 : 32) * sizeof(float); }
+
+// scratch16: 16 bytes (n_valid u64, loss_sum f32); gbuf: seg_ce_scratch_bytes.  loss_out (device, nullable) receives the mean CE.
 int launch_seg_ce_fused(const TensorView& lo, int n_cls, const long long* labels, int H, int W, int ignore_index, const TensorView& dlo,
-                        float factor, const float* scale_dev, void* scratch16, float* loss_out, cudaStream_t s) {
-  MYOLO_REQUIRE(lo.dtype == MYOLO_F32 && dlo.dtype == MYOLO_F32 && n_cls >= 1 && n_cls <= 32 && lo.C >= n_cls && labels && scratch16,
+                        float factor, const float* scale_dev, void* scratch16, float* gbuf, float* loss_out, cudaStream_t s) {
+  MYOLO_REQUIRE(lo.dtype == MYOLO_F32 && dlo.dtype == MYOLO_F32 && n_cls >= 1 && n_cls <= 32 && lo.C >= n_cls && labels && scratch16 && gbuf,
                 "seg_ce_fused: fp32 low-resolution logits with <= 32 classes expected");
   unsigned long long* n_valid = reinterpret_cast<unsigned long long*>(scratch16);
   float* loss_sum = reinterpret_cast<float*>(n_valid + 1);
@@ -715,8 +742,19 @@ int launch_seg_ce_fused(const TensorView& lo, int n_cls, const long long* labels
   count_valid_kernel<<<grid_for_t(n, 256, 148 * 8), 256, 0, s>>>(labels, n, ignore_index, n_valid);
   MYOLO_LAUNCH_CHECK();
   const int rsplit = 4;
-  seg_ce_fused_kernel<32><<<grid_for_t((long)lo.B * lo.H * lo.W * rsplit, 128), 128, 0, s>>>(lo, n_cls, labels, H, W, ignore_index, dlo, factor,
-                                                                                           scale_dev, n_valid, loss_sum, rsplit);
+  const int g1 = grid_for_t(n, 128), g2 = grid_for_t((long)lo.B * lo.H * lo.W * rsplit, 128);
+  if (n_cls == 19) {
+    seg_ce_pixel_kernel<19, 20><<<g1, 128, 0, s>>>(lo, labels, H, W, ignore_index, gbuf, loss_sum);
+    MYOLO_LAUNCH_CHECK();
+    seg_ce_gather_kernel<19, 20><<<g2, 128, 0, s>>>(gbuf, H, W, dlo, factor, scale_dev, n_valid, rsplit);
+  } else if (n_cls <= 20) {
+    MYOLO_REQUIRE(false, "seg_ce_fused: instantiate the kernels for %d classes (19 and 21..32 are built)", n_cls);
+  } else {
+    MYOLO_REQUIRE(n_cls == 32, "seg_ce_fused: instantiate the kernels for %d classes (19 and 32 are built)", n_cls);
+    seg_ce_pixel_kernel<32, 32><<<g1, 128, 0, s>>>(lo, labels, H, W, ignore_index, gbuf, loss_sum);
+    MYOLO_LAUNCH_CHECK();
+    seg_ce_gather_kernel<32, 32><<<g2, 128, 0, s>>>(gbuf, H, W, dlo, factor, scale_dev, n_valid, rsplit);
+  }
   MYOLO_LAUNCH_CHECK();
   seg_ce_finalize_kernel<<<1, 1, 0, s>>>(loss_sum, n_valid, loss_out);
   MYOLO_LAUNCH_CHECK();

@@ -51,8 +51,9 @@ int launch_region_combine_bwd(const TensorView& dbins, const TensorView& datoms,
 int launch_seg_upsample_bwd(const float* dseg, int n_cls, int H, int W, const TensorView& dlo, cudaStream_t s);
 // fused CE(ignore_index) of the bilinear-upsampled low-res logits: seeds d(low-res logits) += factor * (*scale_dev) * d(mean CE)/d(lo)
 // and writes the mean CE to loss_out (device, nullable); scratch16 = 16 bytes of device scratch
+size_t seg_ce_scratch_bytes(int B, int H, int W, int n_cls);
 int launch_seg_ce_fused(const TensorView& lo, int n_cls, const long long* labels, int H, int W, int ignore_index, const TensorView& dlo,
-                        float factor, const float* scale_dev, void* scratch16, float* loss_out, cudaStream_t s);
+                        float factor, const float* scale_dev, void* scratch16, float* gbuf, float* loss_out, cudaStream_t s);
 // Detect: d(conv out fp32 NHWC)[b,y,x,a*no+o] = draw[b,a,y,x,o]
 int launch_detect_raw_bwd(const float* draw, int na, int no, const TensorView& dconv, cudaStream_t s);
 int launch_cast_f32_to_f16(const TensorView& src, const TensorView& dst, cudaStream_t s);
