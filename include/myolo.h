@@ -61,6 +61,7 @@ extern "C" {
 #define MYOLO_OP_BROADCAST 12    /* F.interpolate(nearest) of a 1x1 map (RFB2 global branch), models/common.py:509 */
 #define MYOLO_OP_BN_ACT 14       /* train mode: batch-statistics BatchNorm + activation (+ residual) on a raw conv output; aux[0] = bn slot */
 #define MYOLO_OP_ACT 15          /* train mode: standalone activation (FFM attention SiLU / Sigmoid) so the pre-activation is kept */
+#define MYOLO_OP_DROPOUT 17      /* train mode: out = in * keep / (1-p), keep ~ Bernoulli(1-p) from a counter-based hash of (seed, forward step, op, element); faux[0] = p, aux[0] = op salt.  nn.Dropout(0.1) of the Base / BiSe heads (reference models/yolo.py:65,140) */
 #define MYOLO_OP_CHANNEL_SCALE_OOP 16 /* train mode: out = in * (1 + in2) out of place (in is needed by the backward pass) */
 #define MYOLO_OP_FOCUS_CONV 13   /* whole layer 0 fused: Focus slicing + Conv3x3+BN+SiLU from the NCHW image, models/common.py:542-551 */
 
@@ -130,6 +131,8 @@ int myolo_plan_set_bn(myolo_plan* plan, int bn_slot, int channels, float* gamma,
                       float* d_gamma, float* d_beta, float momentum, float eps);
 /* where the conv parameter gradients are accumulated (fp32, PyTorch layout [Co][Ci][k][k]; d_bias nullable) */
 int myolo_plan_set_conv_grad(myolo_plan* plan, int weight_slot, float* d_weight, float* d_bias);
+/* seed of the train-mode dropout masks (default 0); masks change with every train forward */
+int myolo_plan_set_seed(myolo_plan* plan, uint64_t seed);
 /* train-mode forward: raw[i] (B,na,ny,nx,no) fp32 and seg (B,n_segcls,H,W) fp32, like Model.forward in training (models/yolo.py:225,316) */
 int myolo_plan_train_forward(myolo_plan* plan, const void* x, int x_dtype, float* const* raw, float* seg, void* stream);
 /* backward of the last train forward: grad_raw[i] / grad_seg are dL/d(raw[i]) / dL/d(seg) (fp32, nullable); parameter gradients are

@@ -111,6 +111,8 @@ struct myolo_plan {
   int bwd_ops[16] = {};
   bool bwd_warm[16] = {};
   bool bwd_dirty = false;
+  unsigned long long seed = 0;       // dropout
+  unsigned long long* d_step = nullptr;
   void* ce_scratch = nullptr;      // 16 bytes for the fused seg loss (valid-pixel count, loss sum)
   float* ce_gbuf = nullptr;        // per-pixel (softmax - onehot), NHWC fp32, of the fused seg loss
   size_t ce_gbuf_bytes = 0;
@@ -222,6 +224,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   for (auto& sl : pl->slots) if (sl.dw_packed) cudaFree(sl.dw_packed);
   if (pl->tmp16) cudaFree(pl->tmp16);
   if (pl->ce_scratch) cudaFree(pl->ce_scratch);
+  if (pl->d_step) cudaFree(pl->d_step);
   if (pl->ce_gbuf) cudaFree(pl->ce_gbuf);
   if (pl->spp_scratch) cudaFree(pl->spp_scratch);
   delete pl;
@@ -361,6 +364,10 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
     case MYOLO_OP_ACT:
       if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
       return launch_act_fwd(in, out, op.act, s);
+    case MYOLO_OP_DROPOUT:
+      if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.out, &out))) return rc;
+      MYOLO_REQUIRE(pl->d_step, "op %d: dropout outside a train forward", i);
+      return launch_dropout(in, out, op.faux[0], pl->seed, pl->d_step, (unsigned)op.aux[0], 0, s);
     case MYOLO_OP_CHANNEL_SCALE_OOP:
       if ((rc = resolve_view(pl, op.in, &in)) || (rc = resolve_view(pl, op.in2, &in2)) || (rc = resolve_view(pl, op.out, &out))) return rc;
       return launch_channel_scale_oop(in, in2, out, s);
@@ -598,6 +605,13 @@ extern "C" int myolo_plan_set_bn(myolo_plan* pl, int bn_slot, int channels, floa
   return 0;
 }
 
+extern "C" int myolo_plan_set_seed(myolo_plan* pl, uint64_t seed) {
+  MYOLO_REQUIRE(pl, "set_seed: null plan");
+  if (pl->seed != seed) { pl->graph_dirty = true; pl->bwd_dirty = true; }   // the seed is a kernel argument of the captured graphs
+  pl->seed = seed;
+  return 0;
+}
+
 extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weight, float* d_bias) {
   MYOLO_REQUIRE(pl && slot >= 0 && slot < (int)pl->slots.size(), "set_conv_grad: bad slot %d", slot);
   if (pl->slots[slot].d_w != d_weight || pl->slots[slot].d_bias != d_bias) pl->bwd_dirty = true;
@@ -608,6 +622,14 @@ extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weigh
 
 extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream) {
   MYOLO_REQUIRE(pl && x, "train_forward: null plan / input");
+  if (!pl->d_step) {
+    MYOLO_CHECK_CUDA(cudaMalloc(&pl->d_step, sizeof(unsigned long long)));
+    MYOLO_CHECK_CUDA(cudaMemset(pl->d_step, 0, sizeof(unsigned long long)));
+  }
+  {   // a new dropout mask per forward; the counter lives on the device so that captured graphs see the new value
+    int brc = launch_bump_step(pl->d_step, (cudaStream_t)stream);
+    if (brc) return brc;
+  }
   // same executor as inference: first call in order (lazy allocations / tensor maps), then multi-lane CUDA-graph replay of the internal
   // ops with the input conversion before and the caller-owned outputs (raw x_i, seg logits) after the graph
   int rc = myolo_plan_forward(pl, x, x_dtype, nullptr, raw, seg, MYOLO_F32, nullptr, stream);
@@ -908,6 +930,10 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
       case MYOLO_OP_ACT:
         if ((rc = resolve_view(pl, op.in, &a)) || (rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
         rc = launch_act_bwd(a, b, c, op.act, s);
+        break;
+      case MYOLO_OP_DROPOUT:
+        if ((rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
+        rc = launch_dropout(b, c, op.faux[0], pl->seed, pl->d_step, (unsigned)op.aux[0], 1, s);
         break;
       case MYOLO_OP_CHANNEL_SCALE_OOP: {
         TensorView f, av, gout, gf, ga;

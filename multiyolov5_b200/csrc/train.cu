@@ -320,6 +320,47 @@ int launch_bn_act_bwd(const TensorView& u, const TensorView& dy, const TensorVie
 }
 
 // ------------------------------------------------------------------------------------------------
+// dropout (train mode): keep mask from a counter-based hash - the backward pass regenerates it instead of storing it.
+// (PyTorch's Philox stream cannot be reproduced bit for bit; the mask is Bernoulli(1-p) per element, like nn.Dropout.)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool dropout_keep(unsigned long long seed, unsigned long long step, unsigned salt, unsigned long long idx, float p) {
+  unsigned long long z = seed ^ (step * 0x9E3779B97F4A7C15ull) ^ ((unsigned long long)salt << 48) ^ (idx * 0xD1B54A32D192ED03ull);
+  z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull;          // splitmix64 finaliser
+  z ^= z >> 27; z *= 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f) >= p;
+}
+__global__ void dropout_kernel(TensorView x, TensorView y, float p, unsigned long long seed, const unsigned long long* step, unsigned salt,
+                               int accumulate) {
+  const long total = (long)x.B * x.H * x.W * x.C;
+  const unsigned long long st = *step;
+  const float scale = 1.0f / (1.0f - p);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % x.C);
+    long q = i / x.C;
+    const int xx = (int)(q % x.W); q /= x.W;
+    const int yy = (int)(q % x.H);
+    const int b = (int)(q / x.H);
+    const float v = dropout_keep(seed, st, salt, (unsigned long long)i, p) ? ldv(x, b, yy, xx, c) * scale : 0.f;
+    stv(y, b, yy, xx, c, accumulate ? ldv(y, b, yy, xx, c) + v : v);
+  }
+}
+// forward: y = dropout(x);  backward (accumulate = 1): dx += dropout-mask(dy)  (same seed / step / salt -> same mask)
+int launch_dropout(const TensorView& x, const TensorView& y, float p, unsigned long long seed, const unsigned long long* step, unsigned salt,
+                   int accumulate, cudaStream_t s) {
+  MYOLO_REQUIRE(x.C == y.C && x.H == y.H && x.W == y.W && p >= 0.f && p < 1.f && step, "dropout: bad arguments");
+  dropout_kernel<<<grid_for_t((long)x.B * x.H * x.W * x.C, 256), 256, 0, s>>>(x, y, p, seed, step, salt, accumulate);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void bump_step_kernel(unsigned long long* step) { *step += 1; }
+int launch_bump_step(unsigned long long* step, cudaStream_t s) {
+  bump_step_kernel<<<1, 1, 0, s>>>(step);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // small elementwise ops (generic dtype through ldv/stv: used on tiny maps or fp32 head buffers)
 // ------------------------------------------------------------------------------------------------
 __global__ void act_fwd_kernel(TensorView x, TensorView y, int act) {

@@ -30,6 +30,10 @@ int launch_act_fwd(const TensorView& x, const TensorView& y, int act, cudaStream
 // out = f * (1 + a)   (out-of-place FFM scale for training)
 int launch_channel_scale_oop(const TensorView& f, const TensorView& a, const TensorView& out, cudaStream_t s);
 
+int launch_dropout(const TensorView& x, const TensorView& y, float p, unsigned long long seed, const unsigned long long* step, unsigned salt,
+                   int accumulate, cudaStream_t s);
+int launch_bump_step(unsigned long long* step, cudaStream_t s);
+
 // ---- backward ----
 // dz = dy*act'(z), z = gamma*xhat+beta; du = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)); dgamma += sum(dz*xhat); dbeta += sum(dz)
 // d_res (nullable) += dy.  `scratch` holds 2*C floats.

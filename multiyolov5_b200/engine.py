@@ -162,6 +162,9 @@ class Engine:
         L = _lib.lib()
         sp = _lib.stream_ptr()
         params = self._train_params
+        if not getattr(p, "_seed_set", False):       # dropout masks follow torch's global seed (one hash stream per plan)
+            _lib.check(L.myolo_plan_set_seed(p.handle, C.c_uint64(torch.initial_seed() & 0xFFFFFFFFFFFFFFFF)))
+            p._seed_set = True
         # re-pack the fp16 weights only when the parameters changed (in-place torch updates bump _version; Trainer's fused optimiser
         # writes through raw pointers and sets weights_dirty)
         ver = sum(q._version for q in params)

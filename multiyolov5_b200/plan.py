@@ -18,7 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import (ACT_NONE, ACT_SIGMOID, ACT_SILU, F16, F32, OP_ADD, OP_BILINEAR, OP_BROADCAST, OP_CHANNEL_SCALE, OP_CONV,
-                   OP_ACT, OP_BN_ACT, OP_CHANNEL_SCALE_OOP, OP_DETECT_DECODE, OP_FOCUS_CONV, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
+                   OP_ACT, OP_BN_ACT, OP_CHANNEL_SCALE_OOP, OP_DROPOUT, OP_DETECT_DECODE, OP_FOCUS_CONV, OP_INPUT_FOCUS, OP_REGION_COMBINE, OP_REGION_SUM, OP_SEG_UPSAMPLE, OP_SPP_POOL,
                    OP_UPSAMPLE_NEAREST)
 from .models import common as cm
 
@@ -353,9 +353,21 @@ class PlanBuilder:
         y = self.FFM(m.out[0], cat)
         return self.classifier(m.out[2], y, m.c_out)
 
+    def dropout(self, m: nn.Dropout, x: V) -> V:
+        """nn.Dropout: identity in eval; in train mode OP_DROPOUT (faux[0] = p, aux[0] = per-op salt of the mask hash)"""
+        if not self.train or m.p <= 0:
+            return x
+        out = self.new_buf(x.h, x.w, x.c)
+        rec = OpRec(OP_DROPOUT, x, None, out)
+        rec.aux[0] = len(self.ops) + 1
+        rec.faux[0] = float(m.p)
+        self.emit(rec)
+        return out
+
     def SegMaskBase(self, m, xs: List[V]):
         y = self.C3(m.m[0], xs[0])
         y = self.C3SPP(m.m[1], y)
+        y = self.dropout(m.m[2], y)                    # nn.Dropout(0.1, True), reference models/yolo.py:140
         return self.classifier(m.m[3], y, m.c_out)
 
     # ---- Detect ----

@@ -231,7 +231,9 @@ def SegMaskBase(cx, p, xs, n, shortcut):
     # reference models/yolo.py:129-146
     y = C3(cx, p + ".m.0", xs[0], n, shortcut)
     y = C3SPP(cx, p + ".m.1", y)
-    lo = _classifier(cx, p + ".m.3", y, k=3, bias=False)  # m.2 is Dropout
+    if getattr(cx, "dropout_mask", None) is not None:     # m.2 = nn.Dropout(0.1, True) (reference models/yolo.py:140): active in train mode;
+        y = y * cx.dropout_mask / (1.0 - 0.1)             # the keep mask is an INPUT here (torch's RNG stream is not part of the parity contract)
+    lo = _classifier(cx, p + ".m.3", y, k=3, bias=False)
     cx.taps["seg_lowres"] = lo
     return bilinear(cx, lo, scale=8)
 
@@ -466,11 +468,12 @@ def seg_postprocess(seg: np.ndarray, out_hw) -> np.ndarray:
     return up.argmax(axis=1).astype(np.int64)
 
 
-def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor):
+def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None):
     """`Model.forward` in TRAIN mode (reference models/yolo.py:225,316): returns ([x0,x1,x2] raw head outputs, seg logits) with autograd
     history, so tests can compare hand-written gradients with torch.autograd on the restated graph.  `sd` tensors that should receive
     gradients must be leaf tensors with requires_grad=True."""
     cx = Ctx(sd, quantised=False, train=True)
+    cx.dropout_mask = dropout_mask      # (B,C,h,w) keep mask of the Base head's dropout, or None = identity
     layers = parse_cfg(cfg)
     ys: List[Optional[torch.Tensor]] = []
     x = x.to(torch.float32)

@@ -26,21 +26,36 @@ def setup(tag="s_psp", yml="yolov5s_city_seg.yaml", B=4, H=128, W=256):
     return model, cfg, sd, x
 
 
-def oracle_train(cfg, sd, x, Rs, S):
+def oracle_train(cfg, sd, x, Rs, S, dropout_mask=None):
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "anchor" not in k else v.clone())
            for k, v in sd.items()}
-    raw, seg = restate.model_forward_train(cfg, sdg, x)
+    raw, seg = restate.model_forward_train(cfg, sdg, x, dropout_mask)
     loss = sum((r * R).sum() for r, R in zip(raw, Rs)) + (seg * S).sum()
     loss.backward()
     return raw, seg, sdg
 
 
-def amp_yardstick(cfg, sd, x, Rs, S, ref_raw, ref_seg, ref_sdg):
+def dropout_mask_of(model):
+    """the keep mask our last train forward applied (Base head): read back so that the oracle can apply the same one"""
+    from multiyolov5_b200 import _lib
+    eng = model.engine()
+    ops = [o for o in eng.last_plan.pb.ops if o.kind == _lib.OP_DROPOUT]
+    if not ops:
+        return None
+    xin, xout = eng.read_view(ops[0].in_), eng.read_view(ops[0].out)
+    keep = ((xout != 0) | (xin == 0)).float()
+    frac = float(keep.mean())
+    assert 0.88 < frac < 0.92, frac                                   # Bernoulli(0.9)
+    assert torch.allclose(xout, xin * keep / 0.9, rtol=2e-3, atol=1e-6)   # kept values scaled by 1/(1-p) (fp16 rounding)
+    return keep.cpu()
+
+
+def amp_yardstick(cfg, sd, x, Rs, S, ref_raw, ref_seg, ref_sdg, dropout_mask=None):
     """the SAME restated graph through torch's fp16 autocast on the GPU - what the reference's `amp.autocast` training computes
     (train.py:363) - measured against the fp32 oracle: the error level an fp16-storage path is entitled to."""
     sda = {k: (v.detach().clone().cuda().requires_grad_(True) if v.requires_grad else v.detach().clone().cuda()) for k, v in ref_sdg.items()}
     with torch.autocast("cuda", dtype=torch.float16):
-        araw, aseg = restate.model_forward_train(cfg, sda, x.cuda())
+        araw, aseg = restate.model_forward_train(cfg, sda, x.cuda(), None if dropout_mask is None else dropout_mask.cuda())
     loss = sum((r.float() * R.cuda()).sum() for r, R in zip(araw, Rs)) + (aseg.float() * S.cuda()).sum()
     loss.backward()
     fwd = [rel_f(a.detach().float().cpu(), b.detach()) for a, b in zip(list(araw) + [aseg], list(ref_raw) + [ref_seg])]
@@ -70,8 +85,10 @@ def test_train_forward_and_backward_match_autograd_oracle(tag):
     loss = sum((r * R.cuda()).sum() for r, R in zip(raws, Rs)) + (seg * S.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
-    o_raw, o_seg, sdg = oracle_train(cfg, sd, x, Rs, S)
-    amp_fwd, amp_grd = amp_yardstick(cfg, sd, x, Rs, S, o_raw, o_seg, sdg)
+    dmask = dropout_mask_of(model)
+    assert (dmask is not None) == (tag == "s_base")
+    o_raw, o_seg, sdg = oracle_train(cfg, sd, x, Rs, S, dmask)
+    amp_fwd, amp_grd = amp_yardstick(cfg, sd, x, Rs, S, o_raw, o_seg, sdg, dmask)
     ours_fwd = [rel_f(a.detach().cpu(), b.detach()) for a, b in zip(list(raws) + [seg], list(o_raw) + [o_seg])]
     print("\ntrain forward rel err: ours %s | torch autocast %s" % (np.round(ours_fwd, 4), np.round(amp_fwd, 4)))
     assert max(ours_fwd) < 0.10, ours_fwd
