@@ -25,13 +25,13 @@ CFGS = {"s_psp": ("yolov5s_city_seg.yaml", 29.70e9), "m_lab": ("yolov5m_city_seg
         "m_psp": ("yolov5m_city_seg.yaml", None), "s_bise": ("yolov5s_city_seg_bise.yaml", 32.91e9),
         "s_base": ("yolov5s_city_seg_base.yaml", 30.87e9)}
 H, W = 512, 1024
-# synthetic Detect objectness-bias shifts (per level) calibrated with the oracle so that ~1% of the 32256 anchors pass obj>0.25
+# synthetic Detect objectness-bias shifts (per level) calibrated so that ~1% of the 32256 anchors pass obj>0.25
 # (a realistic O(300) candidates/img NMS load instead of the ~10k the near-critical synthetic weights would give)
 OBJ_BIAS_SHIFT = {"s_psp": (-17.5, -10.5, -18.2), "m_lab": (-5.9, -4.6, -5.2)}
 
 
 def make_weights(tag):
-    from oracle import synth
+    from multiyolov5_b200 import synth
     yml = CFGS[tag][0]
     cfg = synth.load_cfg(yml)
     sd = synth.synth_state_dict(synth.load_manifest(tag if tag in ("s_psp", "m_lab", "m_psp", "s_bise", "s_base") else "s_psp"), cfg, seed=1)

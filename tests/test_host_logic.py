@@ -110,3 +110,42 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("use the oracle for CPU numbers", ""), os.path.join(dp, f)
+
+
+def test_letterbox_geometry_host_logic_matches_restatement():
+    """the product's shape arithmetic for the device letterbox (resized size, padding, offsets) against the restatement of reference
+    utils/datasets.py:818-845 over many frame shapes / options (importing the product module needs no GPU)"""
+    import numpy as np
+    from multiyolov5_b200.utils.datasets import letterbox_geometry
+    from oracle import restate
+    rs = np.random.RandomState(0)
+    for _ in range(300):
+        shape = (int(rs.randint(17, 2200)), int(rs.randint(17, 2200)))
+        new_shape = int(rs.choice([320, 512, 640, 1024])) if rs.rand() < 0.5 else (int(rs.randint(2, 40)) * 32, int(rs.randint(2, 40)) * 32)
+        kw = dict(auto=bool(rs.rand() < 0.5), scaleFill=bool(rs.rand() < 0.2), scaleup=bool(rs.rand() < 0.7), stride=int(rs.choice([32, 64])))
+        a = letterbox_geometry(shape, new_shape, **kw)
+        b = restate.letterbox_geometry(shape, new_shape, **kw)
+        assert a[0] == b[0] and a[3] == b[3] and np.allclose(a[1], b[1]) and np.allclose(a[2], b[2]), (shape, new_shape, kw)
+
+
+def test_trainer_parameter_groups_follow_reference_rules():
+    """pg0 = BatchNorm weights (no decay), pg1 = other weights (decay), pg2 = biases (reference train.py:108-116)"""
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.train import parameter_groups, scale_hyp
+    import torch.nn as nn
+    model = Model("yolov5s_city_seg.yaml")
+    grp = parameter_groups(model)
+    named = dict(model.named_parameters())
+    assert len(grp) == len(named) == 229                          # SURVEY 8 a13: 229 gradient tensors for s/PSP
+    bn_weights = {id(m.weight) for m in model.modules() if isinstance(m, nn.BatchNorm2d)}
+    assert len(bn_weights) > 60
+    for name, p in named.items():
+        g = grp[id(p)]
+        if name.endswith(".bias"):
+            assert g == 2, name
+        elif id(p) in bn_weights:
+            assert g == 0, name
+        else:
+            assert g == 1 and p.dim() == 4, name           # conv weights
+    h = scale_hyp(dict(weight_decay=5e-4, box=0.05, cls=0.5, obj=1.0), nl=3, nc=10, imgsz=1024, total_batch_size=32)
+    assert abs(h["weight_decay"] - 5e-4 * 32 * 2 / 64) < 1e-12 and abs(h["cls"] - 0.5 * 10 / 80) < 1e-12 and abs(h["obj"] - (1024 / 640) ** 2) < 1e-12

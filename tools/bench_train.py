@@ -48,7 +48,7 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    from oracle import synth                     # synthetic weights only (test infrastructure used as a data generator, like bench.py)
+    from multiyolov5_b200 import synth
     from multiyolov5_b200.models.yolo import Model
     from multiyolov5_b200.train import Trainer, scale_hyp
     yml, tag = "yolov5s_city_seg.yaml", "s_psp"
