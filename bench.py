@@ -265,6 +265,38 @@ def main():
     ms_e2e = timed(step_e2e, args.steps, finalize=e2e_tail)
     torch.cuda.synchronize()
 
+    # ---- extra: from RAW camera frames (2048x1024 BGR uint8, pinned host) through the device-side letterbox/pre-process kernel
+    # (replaces cv2.resize + transpose + /255 of utils/datasets.py:185-189 / detect.py:135-137);
+    # same two-deep pipeline, H2D of 6.3 MB per frame inside the timed region
+    from multiyolov5_b200.utils.datasets import preprocess
+    RAW_H, RAW_W = 2 * H, 2 * W
+    raw_host = [torch.randint(0, 256, (B, RAW_H, RAW_W, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    raw_dev = [torch.empty((B, RAW_H, RAW_W, 3), dtype=torch.uint8, device="cuda") for _ in range(2)]
+
+    def step_raw(i):
+        k = i % 2
+        comp = torch.cuda.current_stream()
+        with torch.cuda.stream(s_in):
+            s_in.wait_event(ev_comp[k])
+            raw_dev[k].copy_(raw_host[k], non_blocking=True)
+            ev_in[k].record(s_in)
+        comp.wait_event(ev_in[k])
+        comp.wait_event(ev_out[k])
+        x, _, _ = preprocess(raw_dev[k], (H, W), stride=32, half=not args.fp32_logits)
+        (z, _raw), seg = model(x)
+        det, cnt, cls = post(z, seg, torch.uint8)
+        ev_comp[k].record(comp)
+        keep[k] = (det, cnt, cls, seg, z, x)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ev_comp[k])
+            host_det2[k].copy_(det, non_blocking=True)
+            host_cnt2[k].copy_(cnt, non_blocking=True)
+            host_cls2[k].copy_(cls, non_blocking=True)
+            ev_out[k].record(s_out)
+    ms_raw = timed(step_raw, args.steps, finalize=e2e_tail)
+    torch.cuda.synchronize()
+    del raw_dev, raw_host
+
     # model-only and fused variants (reported as extras)
     def step_model(i):
         model(xs_f32[i % NROT])
@@ -329,6 +361,8 @@ def main():
                         "d2h_bytes_per_step": B * H * W * 1 + B * 300 * 6 * 4 + B * 4,
                         "note": "2-deep software pipeline over 3 streams; class map returned as uint8"},
                 "gpu_launches": launches_per_step * args.steps,
+                "e2e_from_raw_frames": {"value": imgs / (ms_raw * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 3,
+                                        "note": "2048x1024 BGR uint8 frames -> device letterbox/pre-process kernel (bit exact with cv2) -> forward -> post-process"},
                 "model_only_images_per_s": imgs / (ms_model * 1e-3), "fused_argmax_images_per_s": imgs / (ms_fused * 1e-3),
                 "clocks": sampler.summary() if sampler else None, "roofline": roof}
         if not args.no_cpu_baseline and world == 1:

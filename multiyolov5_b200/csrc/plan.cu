@@ -113,6 +113,7 @@ struct myolo_plan {
   bool bwd_dirty = false;
   unsigned long long seed = 0;       // dropout
   unsigned long long* d_step = nullptr;
+  std::vector<cudaEvent_t> bwd_ev;   // per-op completion events of the multi-lane captured backward (+4 join events)
   void* ce_scratch = nullptr;      // 16 bytes for the fused seg loss (valid-pixel count, loss sum)
   float* ce_gbuf = nullptr;        // per-pixel (softmax - onehot), NHWC fp32, of the fused seg loss
   size_t ce_gbuf_bytes = 0;
@@ -223,6 +224,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   if (pl->gws) cudaFree(pl->gws);
   for (auto& sl : pl->slots) if (sl.dw_packed) cudaFree(sl.dw_packed);
   if (pl->tmp16) cudaFree(pl->tmp16);
+  for (auto e : pl->bwd_ev) cudaEventDestroy(e);
   if (pl->ce_scratch) cudaFree(pl->ce_scratch);
   if (pl->d_step) cudaFree(pl->d_step);
   if (pl->ce_gbuf) cudaFree(pl->ce_gbuf);
@@ -821,6 +823,11 @@ static int backward_run(myolo_plan* pl, int mask, std::vector<char>& live, cudaS
   }
   if (!pl->bwd_exec[mask]) {
     if (pl->lanes.empty()) { set_error("backward: forward graph state missing"); return MYOLO_E_INVALID; }
+    if (pl->bwd_ev.size() < pl->ops.size() + 4) {
+      const size_t old_n = pl->bwd_ev.size();
+      pl->bwd_ev.resize(pl->ops.size() + 4);
+      for (size_t k = old_n; k < pl->bwd_ev.size(); ++k) MYOLO_CHECK_CUDA(cudaEventCreateWithFlags(&pl->bwd_ev[k], cudaEventDisableTiming));
+    }
     cudaStream_t cs = pl->lanes[0];
     MYOLO_CHECK_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     rc = backward_walk(pl, live, cs, &n_ops);
@@ -907,6 +914,40 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
   // weight-gradient lane (exists once the forward graph has created the plan's streams / events)
   cudaStream_t side = (side_env && pl->lanes.size() >= 2 && pl->lanes[1] != s && (int)pl->op_ev.size() >= n + 2) ? pl->lanes[1] : s;
   bool used_side = false;
+  // Under capture the chain itself is spread over three lanes: ops are ordered only by real dependencies on the GRADIENT buffers
+  // (reads of grad(out), read-modify-writes of grad(in) / grad(in2)) and on the two shared scratch areas, so the branches of C3 /
+  // SPP / PSP / the three detect levels overlap exactly as they do in the forward graph.
+  static int ml_env = -1;
+  if (ml_env < 0) {
+    const char* e = getenv("MYOLO_BWD_LANES");
+    ml_env = e ? atoi(e) : 1;
+  }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  const bool multi = ml_env && cap == cudaStreamCaptureStatusActive && pl->lanes.size() >= 4 && s == pl->lanes[0] &&
+                     (int)pl->bwd_ev.size() >= n + 4;
+  struct GAcc { int buf, c_lo, c_hi; bool write; };
+  auto acc_of = [&](int i, std::vector<GAcc>& out) {
+    const myolo_op& op = pl->ops[i];
+    out.clear();
+    auto add = [&](const myolo_view& v, bool w) { if (v.buf >= 0) out.push_back(GAcc{v.buf, v.c_off, v.c_off + v.c, w}); };
+    add(op.out, false);
+    add(op.in, true);
+    add(op.in2, true);
+    if (op.kind == MYOLO_OP_CONV && (op.stride == 2 || pl->bufs[op.out.buf].dtype == MYOLO_F32)) out.push_back(GAcc{-2, 0, 1, true});  // tmp16
+    if (op.kind == MYOLO_OP_BILINEAR || op.kind == MYOLO_OP_SPP_POOL) out.push_back(GAcc{-3, 0, 1, true});                          // fp32 scratch
+  };
+  std::vector<int> done;                       // executed ops, in execution order
+  std::vector<std::vector<GAcc>> done_acc;
+  std::vector<int> lane_of(n, -1);
+  const int NLc = 3;
+  cudaStream_t chain[NLc] = {s, multi ? pl->lanes[2] : s, multi ? pl->lanes[3] : s};
+  int lane_last[NLc] = {-1, -1, -1};           // position (in `done`) of the last op of each lane
+  bool lane_used[NLc] = {true, false, false};
+  if (multi) {
+    if (cudaEventRecord(pl->bwd_ev[n], s) != cudaSuccess) { set_error("backward: capture fork failed"); return MYOLO_E_CUDA; }
+  }
+  std::vector<GAcc> cur;
   for (int i = n - 1; i >= 0 && !rc; --i) {
     const myolo_op& op = pl->ops[i];
     TensorView a, b, c, d;
@@ -915,6 +956,39 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
     mark(op.in);
     mark(op.in2);
     ++*n_ops;
+    cudaStream_t s = chain[0];                 // (shadows the origin: the op's lane)
+    int L = 0;
+    if (multi) {
+      acc_of(i, cur);
+      std::vector<int> deps;                   // positions in `done`
+      for (int q = (int)done.size() - 1; q >= 0; --q) {
+        bool hit = false;
+        for (const GAcc& x : cur) {
+          for (const GAcc& y : done_acc[q])
+            if (x.buf == y.buf && (x.write || y.write) && x.c_lo < y.c_hi && y.c_lo < x.c_hi) { hit = true; break; }
+          if (hit) break;
+        }
+        if (hit) deps.push_back(q);
+      }
+      int latest = deps.empty() ? -1 : deps.front();         // deps are in decreasing position order
+      L = -1;
+      if (latest >= 0 && lane_last[lane_of[done[latest]]] == latest) L = lane_of[done[latest]];
+      if (L < 0) {
+        L = 0;
+        for (int k = 1; k < NLc; ++k)
+          if (lane_last[k] < lane_last[L]) L = k;
+      }
+      s = chain[L];
+      if (!lane_used[L]) {
+        if (cudaStreamWaitEvent(s, pl->bwd_ev[n], 0) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+        lane_used[L] = true;
+      }
+      for (int q : deps) {
+        if (lane_of[done[q]] == L) continue;
+        if (cudaStreamWaitEvent(s, pl->bwd_ev[done[q]], 0) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+      }
+      if (rc) break;
+    }
     switch (op.kind) {
       case MYOLO_OP_CONV:
         rc = conv_backward(pl, i, !is_input_buf[op.in.buf], s, side, &used_side);
@@ -967,9 +1041,21 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
         rc = launch_region_bwd(a, b, pl->d_extra + op.aux[0], op.aux[1], pl->d_extra + op.aux[2], op.aux[3], s);
         break;
       default:
-        set_error("backward: op %d of kind %d has no backward (training supports the PSP-head graphs)", i, op.kind);
+        set_error("backward: op %d of kind %d has no backward", i, op.kind);
         rc = MYOLO_E_INVALID;
     }
+    if (multi && !rc) {
+      if (cudaEventRecord(pl->bwd_ev[i], s) != cudaSuccess) { rc = MYOLO_E_CUDA; break; }
+      lane_of[i] = L;
+      done.push_back(i);
+      done_acc.push_back(cur);
+      lane_last[L] = (int)done.size() - 1;
+    }
+  }
+  if (multi) {   // join the chain lanes into the origin
+    for (int k = 1; k < NLc; ++k)
+      if (lane_used[k] && (cudaEventRecord(pl->bwd_ev[n + k], chain[k]) != cudaSuccess || cudaStreamWaitEvent(chain[0], pl->bwd_ev[n + k], 0) != cudaSuccess))
+        if (!rc) { set_error("backward: joining the capture lanes failed"); rc = MYOLO_E_CUDA; }
   }
   if (used_side) {   // join the weight-gradient lane (required to close a capture; in eager mode it orders the optimiser after it)
     if (cudaEventRecord(pl->op_ev[n + 1], side) != cudaSuccess || cudaStreamWaitEvent(s, pl->op_ev[n + 1], 0) != cudaSuccess) {
