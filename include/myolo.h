@@ -138,6 +138,10 @@ int myolo_plan_train_forward(myolo_plan* plan, const void* x, int x_dtype, float
 /* backward of the last train forward: grad_raw[i] / grad_seg are dL/d(raw[i]) / dL/d(seg) (fp32, nullable); parameter gradients are
  * ACCUMULATED into the registered pointers (the reference accumulates the det and the seg pass, train.py:371,392) */
 int myolo_plan_backward(myolo_plan* plan, const float* const* grad_raw, const float* grad_seg, void* stream);
+/* BiSe head in train mode returns three seg outputs [out, aux16, aux32] (reference models/yolo.py:70-79,86): seg[k] / grad_seg[k]
+ * are arrays of three fp32 (B,n_segcls,H,W) pointers (nullable entries; k = 0 is the main output) */
+int myolo_plan_train_forward_multi(myolo_plan* plan, const void* x, int x_dtype, float* const* raw, float* const* seg, void* stream);
+int myolo_plan_backward_multi(myolo_plan* plan, const float* const* grad_raw, const float* const* grad_seg, void* stream);
 /* Fused segmentation loss: mean CrossEntropyLoss(ignore_index) of the bilinear(align_corners) upsample of the
  * last train forward's low-resolution logits against `labels` (B,H,W) int64, WITHOUT materialising the full-resolution logits or their
  * gradient (reference models/yolo.py:163 + utils/loss.py:237 + autograd), followed by the backward pass seeded with

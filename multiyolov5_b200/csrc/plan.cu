@@ -107,9 +107,11 @@ struct myolo_plan {
   std::vector<int> dconv_ready;
   bool train_fwd_done = false;
   // backward replay: one single-lane captured graph per seed mask (bit i = grad_raw[i] given, bit 3 = grad_seg given)
-  cudaGraphExec_t bwd_exec[16] = {};
-  int bwd_ops[16] = {};
-  bool bwd_warm[16] = {};
+  cudaGraphExec_t bwd_exec[64] = {};   // mask bits 0-2: grad_raw[i], bits 3-5: grad_seg[k] (main / aux16 / aux32 of the BiSe head)
+  int bwd_ops[64] = {};
+  bool bwd_warm[64] = {};
+  float* seg_outs[3] = {nullptr, nullptr, nullptr};          // train forward: extra seg outputs (index 1, 2)
+  const float* grad_segs[3] = {nullptr, nullptr, nullptr};   // backward: their gradients
   bool bwd_dirty = false;
   unsigned long long seed = 0;       // dropout
   unsigned long long* d_step = nullptr;
@@ -380,10 +382,15 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
       return launch_detect_decode(in, op.aux[1], op.aux[2], op.faux[0], reinterpret_cast<const float*>(pl->d_extra + op.aux[5]),
                                   raw ? raw[level] : nullptr, z, op.aux[3], op.aux[4], s);
     }
-    case MYOLO_OP_SEG_UPSAMPLE:
+    case MYOLO_OP_SEG_UPSAMPLE: {
       if ((rc = resolve_view(pl, op.in, &in))) return rc;
+      if (op.aux[1] > 0) {     // auxiliary seg outputs of the BiSe head in train mode (reference models/yolo.py:70-79,86): fp32 only
+        float* dst = op.aux[1] < 3 ? pl->seg_outs[op.aux[1]] : nullptr;
+        return dst ? launch_seg_upsample(in, op.aux[0], pl->H, pl->W, dst, MYOLO_F32, nullptr, s) : 0;
+      }
       if (!seg && !seg_argmax) return 0;
       return launch_seg_upsample(in, op.aux[0], pl->H, pl->W, seg, seg_dtype, seg_argmax, s);
+    }
     default:
       set_error("op %d: unknown kind %d", i, op.kind);
       return MYOLO_E_INVALID;
@@ -622,6 +629,14 @@ extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weigh
   return 0;
 }
 
+extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream);
+extern "C" int myolo_plan_train_forward_multi(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* const* seg, void* stream) {
+  MYOLO_REQUIRE(pl, "train_forward: null plan");
+  pl->seg_outs[1] = seg ? seg[1] : nullptr;
+  pl->seg_outs[2] = seg ? seg[2] : nullptr;
+  return myolo_plan_train_forward(pl, x, x_dtype, raw, seg ? seg[0] : nullptr, stream);
+}
+
 extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream) {
   MYOLO_REQUIRE(pl && x, "train_forward: null plan / input");
   if (!pl->d_step) {
@@ -780,10 +795,12 @@ static int backward_seeds(myolo_plan* pl, const float* const* grad_raw, const fl
     const myolo_op& op = pl->ops[i];
     TensorView a;
     int rc;
-    if (op.kind == MYOLO_OP_SEG_UPSAMPLE && grad_seg) {
+    if (op.kind == MYOLO_OP_SEG_UPSAMPLE) {
+      const float* g = op.aux[1] == 0 ? grad_seg : (op.aux[1] < 3 ? pl->grad_segs[op.aux[1]] : nullptr);
+      if (!g) continue;
       if ((rc = grad_view(pl, op.in, &a))) return rc;
       live[op.in.buf] = 1;
-      if ((rc = launch_seg_upsample_bwd(grad_seg, op.aux[0], pl->H, pl->W, a, s))) return rc;
+      if ((rc = launch_seg_upsample_bwd(g, op.aux[0], pl->H, pl->W, a, s))) return rc;
     } else if (op.kind == MYOLO_OP_DETECT_DECODE && grad_raw && grad_raw[op.aux[0]]) {
       if ((rc = grad_view(pl, op.in, &a))) return rc;
       live[op.in.buf] = 1;
@@ -849,12 +866,22 @@ static int backward_run(myolo_plan* pl, int mask, std::vector<char>& live, cudaS
   return 0;
 }
 
+extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream);
+extern "C" int myolo_plan_backward_multi(myolo_plan* pl, const float* const* grad_raw, const float* const* grad_seg, void* stream) {
+  MYOLO_REQUIRE(pl, "backward: null plan");
+  pl->grad_segs[1] = grad_seg ? grad_seg[1] : nullptr;
+  pl->grad_segs[2] = grad_seg ? grad_seg[2] : nullptr;
+  int rc = myolo_plan_backward(pl, grad_raw, grad_seg ? grad_seg[0] : nullptr, stream);
+  pl->grad_segs[1] = pl->grad_segs[2] = nullptr;
+  return rc;
+}
+
 extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream) {
   MYOLO_REQUIRE(pl && pl->train_fwd_done, "backward: call myolo_plan_train_forward first");
   cudaStream_t s = (cudaStream_t)stream;
   if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
   MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->gws, 0, pl->ws_bytes, s));
-  int mask = grad_seg ? 8 : 0;
+  int mask = (grad_seg ? 8 : 0) | (pl->grad_segs[1] ? 16 : 0) | (pl->grad_segs[2] ? 32 : 0);
   for (int i = 0; i < 3; ++i)
     if (grad_raw && grad_raw[i]) mask |= 1 << i;
   // Buffers whose gradient is still all-zero are tracked, and ops that would only propagate zeros are skipped: the det pass of an
@@ -1008,6 +1035,15 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
       case MYOLO_OP_DROPOUT:
         if ((rc = grad_view(pl, op.out, &b)) || (rc = grad_view(pl, op.in, &c))) break;
         rc = launch_dropout(b, c, op.faux[0], pl->seed, pl->d_step, (unsigned)op.aux[0], 1, s);
+        break;
+      case MYOLO_OP_ADD:          // out = in + in2: both inputs receive the output gradient
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b)) || (rc = grad_view(pl, op.in2, &c))) break;
+        if ((rc = launch_grad_add(a, b, s))) break;
+        rc = launch_grad_add(a, c, s);
+        break;
+      case MYOLO_OP_BROADCAST:    // out[b,y,x,c] = in[b,0,0,c]: the 1x1 map receives the per-image spatial sum
+        if ((rc = grad_view(pl, op.out, &a)) || (rc = grad_view(pl, op.in, &b))) break;
+        rc = launch_broadcast_bwd(a, b, s);
         break;
       case MYOLO_OP_CHANNEL_SCALE_OOP: {
         TensorView f, av, gout, gf, ga;

@@ -319,6 +319,47 @@ int launch_bn_act_bwd(const TensorView& u, const TensorView& dy, const TensorVie
   return 0;
 }
 
+// dst += src (any dtype through ldv/stv; used by the ADD backward)
+__global__ void grad_add_kernel(TensorView src, TensorView dst) {
+  const long total = (long)dst.B * dst.H * dst.W * dst.C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dst.C);
+    long q = i / dst.C;
+    const int x = (int)(q % dst.W); q /= dst.W;
+    const int y = (int)(q % dst.H);
+    const int b = (int)(q / dst.H);
+    stv(dst, b, y, x, c, ldv(dst, b, y, x, c) + ldv(src, b, y, x, c));
+  }
+}
+int launch_grad_add(const TensorView& src, const TensorView& dst, cudaStream_t s) {
+  MYOLO_REQUIRE(src.C == dst.C && src.H == dst.H && src.W == dst.W, "grad_add: shape mismatch");
+  grad_add_kernel<<<grid_for_t((long)dst.B * dst.H * dst.W * dst.C, 256), 256, 0, s>>>(src, dst);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+// din[b,0,0,c] += sum_{y,x} dout[b,y,x,c]   (one block per (image, 32 channels))
+__global__ void broadcast_bwd_kernel(TensorView dout, TensorView din) {
+  __shared__ float sh[8][32];
+  const int ncg = (dout.C + 31) / 32;
+  const int cg = blockIdx.x % ncg, b = blockIdx.x / ncg;
+  const int c = cg * 32 + (threadIdx.x & 31), lp = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (c < dout.C)
+    for (int p = lp; p < dout.H * dout.W; p += 8) acc += ldv(dout, b, p / dout.W, p % dout.W, c);
+  sh[lp][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (lp == 0 && c < dout.C) {
+    for (int l = 1; l < 8; ++l) acc += sh[l][threadIdx.x & 31];
+    stv(din, b, 0, 0, c, ldv(din, b, 0, 0, c) + acc);
+  }
+}
+int launch_broadcast_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s) {
+  MYOLO_REQUIRE(din.H == 1 && din.W == 1 && din.C == dout.C, "broadcast_bwd: bad views");
+  broadcast_bwd_kernel<<<dout.B * ceil_div(dout.C, 32), 256, 0, s>>>(dout, din);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dropout (train mode): keep mask from a counter-based hash - the backward pass regenerates it instead of storing it.
 // (PyTorch's Philox stream cannot be reproduced bit for bit; the mask is Bernoulli(1-p) per element, like nn.Dropout.)

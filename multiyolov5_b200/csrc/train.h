@@ -43,6 +43,8 @@ int launch_act_bwd(const TensorView& x, const TensorView& dy, const TensorView& 
 // df += dout*(1+a);  da[b,c] += sum_p dout*f
 int launch_channel_scale_bwd(const TensorView& f, const TensorView& a, const TensorView& dout, const TensorView& df, const TensorView& da,
                              cudaStream_t s);
+int launch_grad_add(const TensorView& src, const TensorView& dst, cudaStream_t s);                    // dst += src
+int launch_broadcast_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s);             // din(1x1) += spatial sum
 int launch_nearest2x_bwd(const TensorView& dout, const TensorView& din, cudaStream_t s);             // din += 2x2 sums
 size_t bilinear_bwd_scratch_bytes(const TensorView& dout, const TensorView& din);
 int launch_bilinear_bwd(const TensorView& dout, const TensorView& din, float* scratch, cudaStream_t s);  // din += adjoint(align_corners)

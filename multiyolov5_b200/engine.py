@@ -193,17 +193,22 @@ class Engine:
             raws = list(out_raws)
         else:
             raws = [torch.empty(sh, dtype=torch.float32, device=x.device) for sh in shapes]
-        seg = torch.empty((B, seg_head.c_out, H, W), dtype=torch.float32, device=x.device) if want_seg else None
+        n_seg = sum(1 for o in p.pb.ops if o.kind == _lib.OP_SEG_UPSAMPLE)        # 3 for the BiSe head (main + two aux outputs)
+        segs = [torch.empty((B, seg_head.c_out, H, W), dtype=torch.float32, device=x.device) if want_seg else None for _ in range(n_seg)]
         raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])
-        _lib.check(L.myolo_plan_train_forward(p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), raw_ptrs, _lib.ptr(seg), sp))
+        seg_ptrs = (C.c_void_p * 3)(*[_lib.ptr(segs[k]) if k < n_seg else None for k in range(3)])
+        _lib.check(L.myolo_plan_train_forward_multi(p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), raw_ptrs, seg_ptrs, sp))
         self.last_plan = p
-        return raws, seg, p
+        return raws, (segs[0] if n_seg == 1 else segs), p
 
     def train_backward(self, plan, grad_raws, grad_seg):
+        """grad_seg: one tensor / None, or a list of up to three (BiSe: main, aux16, aux32)"""
         gr = [g.float().contiguous() if g is not None else None for g in grad_raws]
-        gs = grad_seg.float().contiguous() if grad_seg is not None else None
+        gsl = list(grad_seg) if isinstance(grad_seg, (list, tuple)) else [grad_seg]
+        gsl = [g.float().contiguous() if g is not None else None for g in gsl] + [None] * (3 - len(gsl))
         ptrs = (C.c_void_p * 3)(*[_lib.ptr(g) for g in gr])
-        _lib.check(_lib.lib().myolo_plan_backward(plan.handle, ptrs, _lib.ptr(gs), _lib.stream_ptr()))
+        sptrs = (C.c_void_p * 3)(*[_lib.ptr(g) for g in gsl])
+        _lib.check(_lib.lib().myolo_plan_backward_multi(plan.handle, ptrs, sptrs, _lib.stream_ptr()))
 
     def train_backward_seg_ce(self, plan, labels, factor=1.0, scale=None, ignore_index=-1):
         """fused seg loss + backward: mean CE(ignore_index) of the upsampled logits of the last train forward
@@ -240,11 +245,12 @@ class _TrainFunction(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         raws, seg, plan = engine.train_forward(x)
         ctx.engine, ctx.plan = engine, plan
-        return (*raws, seg)
+        segs = seg if isinstance(seg, list) else [seg]
+        return (*raws, *segs)
 
     @staticmethod
-    def backward(ctx, g0, g1, g2, gseg):
-        ctx.engine.train_backward(ctx.plan, [g0, g1, g2], gseg)   # parameter gradients are accumulated into the flat .grad buffer
+    def backward(ctx, g0, g1, g2, *gsegs):
+        ctx.engine.train_backward(ctx.plan, [g0, g1, g2], list(gsegs))   # parameter gradients are accumulated into the flat .grad buffer
         return None, None, None
 
 
@@ -253,4 +259,4 @@ def train_forward(model, x):
     if not hasattr(eng, "_anchor"):
         eng._anchor = torch.zeros((), device=x.device, requires_grad=True)
     out = _TrainFunction.apply(eng._anchor, eng, x)
-    return [list(out[:3]), out[3]]
+    return [list(out[:3]), out[3] if len(out) == 4 else list(out[3:])]     # BiSe: seg = [out, aux16, aux32] (models/yolo.py:86)

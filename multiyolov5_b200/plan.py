@@ -309,10 +309,11 @@ class PlanBuilder:
         self.emit(OpRec(OP_CHANNEL_SCALE, feat, a.sub(0, feat.c), None))
         return feat
 
-    def classifier(self, conv: nn.Conv2d, x: V, n_cls: int):
+    def classifier(self, conv: nn.Conv2d, x: V, n_cls: int, out_index: int = 0):
         lo = self.conv(x, conv, None, ACT_NONE, out_dtype=F32, name="seg.classifier")
-        rec = OpRec(OP_SEG_UPSAMPLE, lo, None, None)   # aux = [n_cls]
+        rec = OpRec(OP_SEG_UPSAMPLE, lo, None, None)   # aux = [n_cls, output index (0 main; 1, 2: BiSe aux heads in train mode)]
         rec.aux[0] = n_cls
+        rec.aux[1] = out_index
         self.emit(rec)
         return lo
 
@@ -349,9 +350,14 @@ class PlanBuilder:
         self.emit(OpRec(OP_ADD, f2, f3, s))
         cat = self.new_buf(h, w, 256)
         self.Conv(m.m8[0], xs[0], cat.sub(0, 128))
-        self.bilinear(self.Conv(m.up16[0], s), h, w, cat.sub(128, 128))
+        f2 = self.bilinear(self.Conv(m.up16[0], s), h, w, cat.sub(128, 128))
         y = self.FFM(m.out[0], cat)
-        return self.classifier(m.out[2], y, m.c_out)
+        y = self.dropout(m.out[1], y)                  # nn.Dropout(0.1), reference models/yolo.py:65
+        lo = self.classifier(m.out[2], y, m.c_out)
+        if self.train:                                 # auxiliary heads, training only (reference models/yolo.py:70-79,86)
+            self.classifier(m.aux16[1], self.Conv(m.aux16[0], f2), m.c_out, out_index=1)
+            self.classifier(m.aux32[1], self.Conv(m.aux32[0], f3), m.c_out, out_index=2)
+        return lo
 
     def dropout(self, m: nn.Dropout, x: V) -> V:
         """nn.Dropout: identity in eval; in train mode OP_DROPOUT (faux[0] = p, aux[0] = per-op salt of the mask hash)"""

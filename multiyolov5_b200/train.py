@@ -92,7 +92,9 @@ class Trainer:
         model.hyp, model.gr = hyp, getattr(model, "gr", 1.0)
         model.train()
         self.compute_loss = ComputeLoss(model)
-        self.compute_seg_loss = SegmentationLosses(ignore_index=-1)
+        self.n_seg_outputs = 3 if type(model.model[-2]).__name__ == "SegMaskBiSe" else 1
+        # BiSe returns [out, aux16, aux32]: loss1 + 1.5*aux_weight*loss2 + 0.5*aux_weight*loss3 (reference train.py:387-388, utils/loss.py:239-244)
+        self.compute_seg_loss = SegmentationLosses(ignore_index=-1, aux=self.n_seg_outputs == 3, aux_num=2)
         self.flat = FlatState(model)
         dev = self.flat.param.device
         self.lr = [hyp["lr0"]] * 3
@@ -174,13 +176,14 @@ class Trainer:
         return st.items
 
     def backward_seg(self, segimgs, segtargets):
-        if self.fused_seg_loss:
+        if self.fused_seg_loss and self.n_seg_outputs == 1:
             eng = self.model.engine()
             _, _, plan = eng.train_forward(segimgs, want_seg=False)
             loss = eng.train_backward_seg_ce(plan, segtargets, factor=self.batch_size * self.seggain, scale=self.scale)
             return loss * (self.batch_size * self.seggain)
         pred = self.model(segimgs)
-        segloss = self.compute_seg_loss(pred[1], segtargets) * self.batch_size * self.seggain   # train.py:385,391
+        outs = pred[1] if isinstance(pred[1], list) else [pred[1]]
+        segloss = self.compute_seg_loss(*outs, segtargets) * self.batch_size * self.seggain   # train.py:385-391
         (segloss * self.scale).backward()
         return segloss.detach()
 

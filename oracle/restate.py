@@ -216,15 +216,22 @@ def SegMaskLab(cx, p, xs, c_hid, n):
 
 
 def SegMaskBiSe(cx, p, xs):
-    # reference models/yolo.py:30-86 (eval branch: returns self.out(feat1) only)
+    # reference models/yolo.py:30-86 (eval: returns self.out(feat1); train: [out, aux16(feat2), aux32(feat3)])
     f3 = RFB2(cx, p + ".m32.0", xs[2], d=(2, 3), has_globel=True)
     f3 = cx.q(bilinear(cx, Conv(cx, p + ".up32.0", f3, 3), scale=2))
     f2 = cx.q(RFB2(cx, p + ".m16.0", xs[1], d=(2, 3)) + f3)
     f2 = cx.q(bilinear(cx, Conv(cx, p + ".up16.0", f2, 3), scale=2))
     y = FFM(cx, p + ".out.0", torch.cat([Conv(cx, p + ".m8.0", xs[0], 1), f2], 1), 3)
-    lo = _classifier(cx, p + ".out.2", y)  # out.1 is Dropout (identity in eval)
+    if getattr(cx, "dropout_mask", None) is not None:     # out.1 = nn.Dropout(0.1), active in train mode; keep mask is an input
+        y = y * cx.dropout_mask / (1.0 - 0.1)
+    lo = _classifier(cx, p + ".out.2", y)
     cx.taps["seg_lowres"] = lo
-    return bilinear(cx, lo, scale=8)
+    out = bilinear(cx, lo, scale=8)
+    if not getattr(cx, "train", False):
+        return out
+    a16 = bilinear(cx, _classifier(cx, p + ".aux16.1", Conv(cx, p + ".aux16.0", f2, 3)), scale=8)      # models/yolo.py:70-74
+    a32 = bilinear(cx, _classifier(cx, p + ".aux32.1", Conv(cx, p + ".aux32.0", f3, 3)), scale=16)     # models/yolo.py:75-79
+    return [out, a16, a32]
 
 
 def SegMaskBase(cx, p, xs, n, shortcut):
@@ -500,6 +507,8 @@ def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor,
             x = seg = SegMaskLab(cx, p, inp, sp["c_hid"], sp["n"])
         elif t == "SegMaskBase":
             x = seg = SegMaskBase(cx, p, inp, sp["n"], sp["shortcut"])
+        elif t == "SegMaskBiSe":
+            x = seg = SegMaskBiSe(cx, p, inp)          # train mode: [out, aux16, aux32]
         elif t == "Detect":
             raw = []
             no = sp["nc"] + 5

@@ -30,9 +30,10 @@ def oracle_train(cfg, sd, x, Rs, S, dropout_mask=None):
     sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "anchor" not in k else v.clone())
            for k, v in sd.items()}
     raw, seg = restate.model_forward_train(cfg, sdg, x, dropout_mask)
-    loss = sum((r * R).sum() for r, R in zip(raw, Rs)) + (seg * S).sum()
+    segs = seg if isinstance(seg, list) else [seg]
+    loss = sum((r * R).sum() for r, R in zip(raw, Rs)) + sum((g * Sk).sum() for g, Sk in zip(segs, S))
     loss.backward()
-    return raw, seg, sdg
+    return raw, segs, sdg
 
 
 def dropout_mask_of(model):
@@ -56,15 +57,17 @@ def amp_yardstick(cfg, sd, x, Rs, S, ref_raw, ref_seg, ref_sdg, dropout_mask=Non
     sda = {k: (v.detach().clone().cuda().requires_grad_(True) if v.requires_grad else v.detach().clone().cuda()) for k, v in ref_sdg.items()}
     with torch.autocast("cuda", dtype=torch.float16):
         araw, aseg = restate.model_forward_train(cfg, sda, x.cuda(), None if dropout_mask is None else dropout_mask.cuda())
-    loss = sum((r.float() * R.cuda()).sum() for r, R in zip(araw, Rs)) + (aseg.float() * S.cuda()).sum()
+    asegs = aseg if isinstance(aseg, list) else [aseg]
+    loss = sum((r.float() * R.cuda()).sum() for r, R in zip(araw, Rs)) + sum((g.float() * Sk.cuda()).sum() for g, Sk in zip(asegs, S))
     loss.backward()
-    fwd = [rel_f(a.detach().float().cpu(), b.detach()) for a, b in zip(list(araw) + [aseg], list(ref_raw) + [ref_seg])]
+    fwd = [rel_f(a.detach().float().cpu(), b.detach()) for a, b in zip(list(araw) + asegs, list(ref_raw) + list(ref_seg))]
     grd = {n: rel_f(v.grad.float().cpu(), ref_sdg[n].grad) for n, v in sda.items()
            if v.requires_grad and ref_sdg[n].grad is not None and ref_sdg[n].grad.norm() > 1e-8}
     return fwd, grd
 
 
-TRAIN_CASES = {"s_psp": "yolov5s_city_seg.yaml", "m_lab": "yolov5m_city_seg_lab.yaml", "s_base": "yolov5s_city_seg_base.yaml"}
+TRAIN_CASES = {"s_psp": "yolov5s_city_seg.yaml", "m_lab": "yolov5m_city_seg_lab.yaml", "s_base": "yolov5s_city_seg_base.yaml",
+               "s_bise": "yolov5s_city_seg_bise.yaml"}
 
 
 @pytest.mark.parametrize("tag", list(TRAIN_CASES))
@@ -79,17 +82,20 @@ def test_train_forward_and_backward_match_autograd_oracle(tag):
     gen = torch.Generator().manual_seed(11)
     out = model(x.cuda())
     raws, seg = out
-    assert len(raws) == 3 and raws[0].shape == (x.shape[0], 3, 16, 32, 15) and seg.shape == (x.shape[0], 19, 128, 256) and seg.requires_grad
+    segs = seg if isinstance(seg, list) else [seg]          # BiSe: [out, aux16, aux32] (reference models/yolo.py:86)
+    assert len(segs) == (3 if tag == "s_bise" else 1)
+    assert len(raws) == 3 and raws[0].shape == (x.shape[0], 3, 16, 32, 15)
+    assert all(g.shape == (x.shape[0], 19, 128, 256) and g.requires_grad for g in segs)
     Rs = [torch.randn(r.shape, generator=gen) * 4.0 for r in raws]
-    S = torch.randn(seg.shape, generator=gen) * 0.05
-    loss = sum((r * R.cuda()).sum() for r, R in zip(raws, Rs)) + (seg * S.cuda()).sum()
+    S = [torch.randn(g.shape, generator=gen) * 0.05 for g in segs]
+    loss = sum((r * R.cuda()).sum() for r, R in zip(raws, Rs)) + sum((g * Sk.cuda()).sum() for g, Sk in zip(segs, S))
     loss.backward()
     torch.cuda.synchronize()
     dmask = dropout_mask_of(model)
-    assert (dmask is not None) == (tag == "s_base")
+    assert (dmask is not None) == (tag in ("s_base", "s_bise"))
     o_raw, o_seg, sdg = oracle_train(cfg, sd, x, Rs, S, dmask)
     amp_fwd, amp_grd = amp_yardstick(cfg, sd, x, Rs, S, o_raw, o_seg, sdg, dmask)
-    ours_fwd = [rel_f(a.detach().cpu(), b.detach()) for a, b in zip(list(raws) + [seg], list(o_raw) + [o_seg])]
+    ours_fwd = [rel_f(a.detach().cpu(), b.detach()) for a, b in zip(list(raws) + segs, list(o_raw) + list(o_seg))]
     print("\ntrain forward rel err: ours %s | torch autocast %s" % (np.round(ours_fwd, 4), np.round(amp_fwd, 4)))
     assert max(ours_fwd) < 0.10, ours_fwd
     assert all(o <= 1.25 * a + 2e-3 for o, a in zip(ours_fwd, amp_fwd)), (ours_fwd, amp_fwd)
@@ -327,3 +333,23 @@ def test_fused_seg_ce_matches_torch_on_the_same_logits():
     _, _, plan = eng.train_forward(x.cuda(), want_seg=False)
     loss = eng.train_backward_seg_ce(plan, torch.full_like(labels, -1))
     assert float(loss) == 0.0 and float(dict(model.named_parameters())["model.24.out.3.weight"].grad.abs().sum()) == 0.0
+
+
+def test_trainer_bise_head_three_outputs():
+    """BiSe in train mode returns [out, aux16, aux32]; the step uses SegmentationLosses(aux=True, aux_num=2) (reference train.py:387-388)"""
+    from multiyolov5_b200.train import Trainer, scale_hyp
+    model, cfg, sd, _ = setup("s_bise", "yolov5s_city_seg_bise.yaml", B=2, H=128, W=256)
+    hyp = dict(lr0=0.01, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
+    tr = Trainer(model, scale_hyp(hyp, nl=3, nc=cfg["nc"], imgsz=256, total_batch_size=4), batch_size=2, init_scale=2.0 ** 10)
+    assert tr.n_seg_outputs == 3
+    rs = np.random.RandomState(0)
+    imgs = synth.synth_image(2, 128, 256, seed=1).cuda()
+    t = np.zeros((6, 6), np.float32)
+    t[:, 0] = rs.randint(0, 2, 6); t[:, 1] = rs.randint(0, cfg["nc"], 6)
+    t[:, 2:4] = rs.uniform(0.1, 0.9, (6, 2)); t[:, 4:6] = rs.uniform(0.05, 0.4, (6, 2))
+    mask = torch.from_numpy(rs.randint(-1, 19, (2, 1, 16, 32)).astype(np.int64)).cuda().repeat_interleave(8, 2).repeat_interleave(8, 3)[:, 0].contiguous()
+    hist = [tr.step(imgs, torch.from_numpy(t).cuda(), imgs, mask) for _ in range(25)]
+    first, last = float(hist[0][1]), float(hist[-1][1])
+    assert np.isfinite([float(h[1]) for h in hist]).all() and last < 0.85 * first, (first, last)
+    named = dict(model.named_parameters())
+    assert float(named["model.24.aux16.1.weight"].abs().sum()) > 0
