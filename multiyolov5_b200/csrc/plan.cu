@@ -447,7 +447,12 @@ static void compute_deps(myolo_plan* pl) {
 
 static int build_graph(myolo_plan* pl) {
   const int n = (int)pl->ops.size();
-  const int NL = 4;
+  static int nl_env = -1;
+  if (nl_env < 0) {
+    const char* e = getenv("MYOLO_LANES");
+    nl_env = e ? std::max(4, std::min(16, atoi(e))) : 4;      // >= 4: the captured backward uses lanes 0-3
+  }
+  const int NL = nl_env;
   if (pl->deps.empty()) compute_deps(pl);
   if (pl->lanes.empty()) {
     pl->lanes.resize(NL);
