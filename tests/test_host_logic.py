@@ -149,3 +149,29 @@ def test_trainer_parameter_groups_follow_reference_rules():
             assert g == 1 and p.dim() == 4, name           # conv weights
     h = scale_hyp(dict(weight_decay=5e-4, box=0.05, cls=0.5, obj=1.0), nl=3, nc=10, imgsz=1024, total_batch_size=32)
     assert abs(h["weight_decay"] - 5e-4 * 32 * 2 / 64) < 1e-12 and abs(h["cls"] - 0.5 * 10 / 80) < 1e-12 and abs(h["obj"] - (1024 / 640) ** 2) < 1e-12
+
+
+def test_train_plans_build_for_every_head_and_only_use_differentiable_ops():
+    """planner, train=True: all five shipped configs lower to op kinds that the backward walk implements (csrc/plan.cu: backward_walk),
+    nothing aliases, BiSe exposes its three seg outputs with indices 0/1/2 and the Base / BiSe dropout becomes an op"""
+    from multiyolov5_b200 import _lib, plan as P
+    from multiyolov5_b200.models.yolo import Model
+    differentiable = {_lib.OP_CONV, _lib.OP_BN_ACT, _lib.OP_ACT, _lib.OP_DROPOUT, _lib.OP_CHANNEL_SCALE_OOP, _lib.OP_UPSAMPLE_NEAREST,
+                      _lib.OP_BILINEAR, _lib.OP_SPP_POOL, _lib.OP_REGION_COMBINE, _lib.OP_REGION_SUM, _lib.OP_ADD, _lib.OP_BROADCAST}
+    seeds = {_lib.OP_INPUT_FOCUS, _lib.OP_DETECT_DECODE, _lib.OP_SEG_UPSAMPLE}
+    for yml, n_seg, n_drop in (("yolov5s_city_seg.yaml", 1, 0), ("yolov5m_city_seg_lab.yaml", 1, 0), ("yolov5s_city_seg_base.yaml", 1, 1),
+                               ("yolov5s_city_seg_bise.yaml", 3, 1), ("yolov5m_city_seg.yaml", 1, 0)):
+        pb = P.build_plan(Model(yml), 2, 128, 256, train=True)
+        kinds = [o.kind for o in pb.ops]
+        assert set(kinds) <= differentiable | seeds, (yml, set(kinds) - differentiable - seeds)
+        segs = [o for o in pb.ops if o.kind == _lib.OP_SEG_UPSAMPLE]
+        assert sorted(o.aux[1] for o in segs) == list(range(n_seg)), yml
+        assert kinds.count(_lib.OP_DROPOUT) == n_drop and kinds.count(_lib.OP_DETECT_DECODE) == 3, yml
+        assert len(pb.bn_slots) == kinds.count(_lib.OP_BN_ACT) > 60, yml
+        # train plans keep every buffer: no two buffers share workspace bytes
+        spans = sorted((b.offset, b.offset + 2 * b.h * b.w * b.c * (1 if b.dtype == _lib.F16 else 2) * 2) for b in pb.bufs)
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), yml
+        # eval plans of the same model have a single seg output and no train-only ops
+        pe = P.build_plan(Model(yml), 2, 128, 256)
+        ke = [o.kind for o in pe.ops]
+        assert ke.count(_lib.OP_SEG_UPSAMPLE) == 1 and not ({_lib.OP_BN_ACT, _lib.OP_DROPOUT, _lib.OP_ACT} & set(ke)), yml
