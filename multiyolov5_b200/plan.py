@@ -10,10 +10,12 @@ Design points
   * aux[] conventions per op kind are documented next to each emit_* helper.
 """
 import math
+import os
 import struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
 
+import torch
 import torch.nn as nn
 
 from . import _lib
@@ -82,6 +84,35 @@ class OpRec:
     tag: str = ""
 
 
+class _CatConv:
+    """two convolutions of the same input as one: duck-types the nn.Conv2d attributes the planner / weight upload read"""
+
+    def __init__(self, a: nn.Conv2d, b: nn.Conv2d):
+        assert (a.kernel_size, a.stride, a.dilation, a.padding, a.groups, a.in_channels) == \
+               (b.kernel_size, b.stride, b.dilation, b.padding, b.groups, b.in_channels) and a.bias is None and b.bias is None
+        self.a, self.b = a, b
+        self.kernel_size, self.stride, self.dilation, self.padding, self.groups = a.kernel_size, a.stride, a.dilation, a.padding, a.groups
+        self.in_channels, self.out_channels, self.bias = a.in_channels, a.out_channels + b.out_channels, None
+
+    @property
+    def weight(self):
+        return torch.cat([self.a.weight.detach(), self.b.weight.detach()], 0)
+
+
+class _CatBN:
+    def __init__(self, a: nn.BatchNorm2d, b: nn.BatchNorm2d):
+        assert a.eps == b.eps
+        self.a, self.b, self.eps, self.num_features = a, b, a.eps, a.num_features + b.num_features
+
+    def _cat(self, name):
+        return torch.cat([getattr(self.a, name).detach(), getattr(self.b, name).detach()], 0)
+
+    weight = property(lambda self: self._cat("weight"))
+    bias = property(lambda self: self._cat("bias"))
+    running_mean = property(lambda self: self._cat("running_mean"))
+    running_var = property(lambda self: self._cat("running_var"))
+
+
 def adaptive_bins(n_in: int, k: int):
     """AdaptiveAvgPool2d bin edges: start=floor(i*n/k), end=ceil((i+1)*n/k)  (ATen adaptive pooling index math)."""
     return [(math.floor(i * n_in / k), math.ceil((i + 1) * n_in / k)) for i in range(k)]
@@ -91,6 +122,7 @@ class PlanBuilder:
     def __init__(self, B: int, H: int, W: int, train: bool = False):
         self.B, self.H, self.W = B, H, W
         self.train = train                      # train mode: raw conv -> batch-stat BN + act ops, nothing in place, no aliasing
+        self.fuse_c3 = os.environ.get("MYOLO_FUSE_C3") == "1"
         self.bn_slots: List[nn.BatchNorm2d] = []
         self.bufs: List[Buf] = []
         self.ops: List[OpRec] = []
@@ -215,8 +247,19 @@ class PlanBuilder:
 
     def C3(self, m: cm.C3, x: V, dst=None) -> V:
         c_ = m.cv1.conv.out_channels
-        cat = self.new_buf(x.h, x.w, 2 * c_)
         n = len(m.m)
+        if self.fuse_c3 and not self.train and n >= 1:
+            # EXPERIMENTAL (MYOLO_FUSE_C3=1, off by default, not yet validated on the GPU): cv1 and cv2 read the same input, so they
+            # run as ONE 1x1 conv with concatenated output channels writing [cv1_out | cv2_out]; the last bottleneck then overwrites
+            # the (by then dead) cv1 half with the m-chain output, which is exactly the concat cv3 reads.  One launch and one read
+            # of x less per C3; no kernel change.
+            both = self.new_buf(x.h, x.w, 2 * c_)
+            self.conv(x, _CatConv(m.cv1.conv, m.cv2.conv), _CatBN(m.cv1.bn, m.cv2.bn), ACT_SILU, both, name="c3.cv1+cv2")
+            y = both.sub(0, c_)
+            for i, bt in enumerate(m.m):
+                y = self.Bottleneck(bt, y, both.sub(0, c_) if i == n - 1 else None)
+            return self.Conv(m.cv3, both, dst)
+        cat = self.new_buf(x.h, x.w, 2 * c_)
         y = self.Conv(m.cv1, x, cat.sub(0, c_) if n == 0 else None)
         for i, bt in enumerate(m.m):
             y = self.Bottleneck(bt, y, cat.sub(0, c_) if i == n - 1 else None)
