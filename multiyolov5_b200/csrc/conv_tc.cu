@@ -35,8 +35,10 @@ static constexpr int kTileRing = 32;
 
 #ifdef MYOLO_TIMELINE
 #define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
+#define DBG_STAMP0(slot) do { if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[(slot)] = clock64(); } while (0)
 #else
 #define DBG_STAMP(slot) do { } while (0)
+#define DBG_STAMP0(slot) do { } while (0)
 #endif
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int kc, uint32_t base_offset) {
@@ -105,6 +107,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b_sub_bytes = p.BN * p.kc * 2;
+  DBG_STAMP0(11);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA0);
@@ -128,6 +131,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  DBG_STAMP0(12);
   if (p.ws_mode && warp == 0 && lane == 0) {
     // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
     mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
@@ -135,6 +139,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
   // ... and wait here until every predecessor grid has completed and flushed (activations / residual come from them)
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  DBG_STAMP0(13);
 
   const int a_sub_bytes = kTileM * p.kc * 2;
   const int row_bytes = p.kc * 2;
@@ -446,6 +451,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tcgen05_fence_before();
   __syncthreads();
+  DBG_STAMP0(14);
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);

@@ -1229,7 +1229,8 @@ extern "C" int myolo_conv_bn_silu(const void* x, int B, int H, int W, int ci, co
         cudaStreamSynchronize(s);
         std::vector<long long> h(64 * 16);
         cudaMemcpy(h.data(), dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost);
-        const long long t0 = h[0];
+        const long long t0 = h[11] ? h[11] : h[0];
+        printf("# prologue: entry 0 | setup done %lld | dependency wait done %lld | teardown %lld   (cycles since kernel entry of CTA0)\n", h[12] - t0, h[13] - t0, h[14] - t0);
         printf("# conv timeline CTA0: grid %d tiles %d BN %d kc %d kstages %d S %d ws %d n_stg %d smem %d\n", c.grid, c.p.total_tiles, c.p.BN, c.p.kc,
                c.p.n_kstages, c.p.num_stages, c.p.ws_mode, c.p.n_stg, c.smem);
         printf("# it: P_begin P_issued | M_begin M_tempty M_full0 M_commit | E_begin E_tfull E_stgready E_done E_store   (cycles since first stamp)\n");

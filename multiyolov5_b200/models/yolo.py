@@ -196,7 +196,7 @@ class Model(nn.Module):
 
     # ---- plan / engine ---------------------------------------------------------------------------------------------
     def invalidate_weights(self):
-        if self._engine is not None:
+        if getattr(self, "_engine", None) is not None:
             self._engine.weights_dirty = True
 
     def load_state_dict(self, *a, **k):
@@ -210,8 +210,19 @@ class Model(nn.Module):
             self._engine.weights_dirty = True
         return r
 
+    # ---- pickling / deepcopy (reference train.py:485 `deepcopy(model).half()`, utils/torch_utils.py:282 ModelEMA, torch.save of the
+    # whole module): the compiled plans hold device handles and are rebuilt lazily, they never travel with the module ----
+    def __getstate__(self):
+        d = dict(self.__dict__)
+        d["_engine"] = None
+        return d
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        object.__setattr__(self, "_engine", None)
+
     def engine(self):
-        if self._engine is None:
+        if getattr(self, "_engine", None) is None:
             from ..engine import Engine
             object.__setattr__(self, "_engine", Engine(self))
         return self._engine
@@ -223,7 +234,19 @@ class Model(nn.Module):
             raise NotImplementedError("TTA (augment=True) is broken in the reference fork itself (SURVEY.md section 2 #18)")
         if self.training:
             # train mode: `[[x0,x1,x2], seg]` with batch-statistics BatchNorm and a hand-written backward behind torch.autograd
-            # (reference models/yolo.py:225,316; train.py:363-392).  PSP / Lab / Base heads; BiSe's aux outputs are not built.
+            # (reference models/yolo.py:225,316; train.py:363-392).  All four heads; BiSe returns seg = [out, aux16, aux32] (models/yolo.py:86).
             from ..engine import train_forward
             return train_forward(self, x)
+        if profile:
+            # reference models/yolo.py:300-309 prints ms per top-level layer; here: device time of every op of the plan (CUDA events around
+            # each op, eager launches), summed per yaml layer
+            eng = self.engine()
+            out = eng.forward(x, seg_argmax=seg_argmax, profile=True)
+            per_layer = {}
+            for o, ms in zip(eng.last_plan.pb.ops, eng.last_profile):
+                per_layer[o.tag] = per_layer.get(o.tag, 0.0) + ms
+            for tag, ms in per_layer.items():
+                print(f"{ms:10.3f} ms  {tag}")
+            print(f"{sum(per_layer.values()):10.3f} ms  total (device time, {len(eng.last_profile)} kernels)")
+            return out
         return self.engine().forward(x, seg_argmax=seg_argmax)

@@ -17,6 +17,65 @@ def xywh2xyxy(x):  # reference utils/general.py:265-272 (host-side helper kept f
     return y
 
 
+def xyxy2xywh(x):  # reference utils/general.py:254-262
+    y = x.clone()
+    y[:, 0] = (x[:, 0] + x[:, 2]) / 2
+    y[:, 1] = (x[:, 1] + x[:, 3]) / 2
+    y[:, 2] = x[:, 2] - x[:, 0]
+    y[:, 3] = x[:, 3] - x[:, 1]
+    return y
+
+
+def clip_coords(boxes, img_shape):
+    """in place, like the reference (utils/general.py:334-340): xyxy boxes clipped to (height, width)"""
+    boxes[:, 0].clamp_(0, img_shape[1])
+    boxes[:, 1].clamp_(0, img_shape[0])
+    boxes[:, 2].clamp_(0, img_shape[1])
+    boxes[:, 3].clamp_(0, img_shape[0])
+
+
+def scale_coords(img1_shape, coords, img0_shape, ratio_pad=None):
+    """xyxy boxes from the letterboxed network input back to the original frame, IN PLACE on the caller's tensor (reference
+    utils/general.py:319-331, called on NMS output rows at detect.py:169; the rows returned by non_max_suppression are ordinary
+    writable tensors for exactly this reason)."""
+    if ratio_pad is None:
+        gain = min(img1_shape[0] / img0_shape[0], img1_shape[1] / img0_shape[1])
+        pad = (img1_shape[1] - img0_shape[1] * gain) / 2, (img1_shape[0] - img0_shape[0] * gain) / 2
+    else:
+        gain, pad = ratio_pad[0][0], ratio_pad[1]
+    coords[:, [0, 2]] -= pad[0]
+    coords[:, [1, 3]] -= pad[1]
+    coords[:, :4] /= gain
+    clip_coords(coords, img0_shape)
+    return coords
+
+
+def box_iou(box1, box2):
+    """(N,4) x (M,4) xyxy -> (N,M) IoU (reference utils/general.py:388-410)"""
+    area1 = (box1[:, 2] - box1[:, 0]) * (box1[:, 3] - box1[:, 1])
+    area2 = (box2[:, 2] - box2[:, 0]) * (box2[:, 3] - box2[:, 1])
+    inter = (torch.min(box1[:, None, 2:], box2[:, 2:]) - torch.max(box1[:, None, :2], box2[:, :2])).clamp(0).prod(2)
+    return inter / (area1[:, None] + area2 - inter)
+
+
+def strip_optimizer(f="best.pt", s=""):
+    """reference utils/general.py:512-525: finalise a training checkpoint - EMA becomes the model, optimiser state dropped, fp16, frozen"""
+    import os
+    from ..models.experimental import load_checkpoint
+    x = load_checkpoint(f, map_location=torch.device("cpu"))
+    if x.get("ema"):
+        x["model"] = x["ema"]
+    for k in ("optimizer", "training_results", "wandb_id", "ema", "updates"):
+        x[k] = None
+    x["epoch"] = -1
+    x["model"].half()
+    for p in x["model"].parameters():
+        p.requires_grad = False
+    torch.save(x, s or f)
+    mb = os.path.getsize(s or f) / 1e6
+    print(f"Optimizer stripped from {f},{(' saved as %s,' % s) if s else ''} {mb:.1f}MB")
+
+
 def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False, labels=(),
                         max_det=300, return_padded=False):
     """reference utils/general.py:421-509.  prediction: (B,A,5+nc) fp32 CUDA.  Returns list[(n,6)] like the reference

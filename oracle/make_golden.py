@@ -239,6 +239,40 @@ def gen_consumers():
     print("consumers", int(correct), int(labeled), inter[:4], union[:4])
 
 
+def gen_ckpt(ref_yolo):
+    """a checkpoint exactly as the reference's train.py:482-494 writes it (whole pickled reference `Model` in half precision inside a
+    dict), for a quarter-width yolov5s_city_seg so the fixture stays small, plus what the reference's own `attempt_load` recipe
+    (`ckpt['model'].float().fuse().eval()`, models/experimental.py:119) computes from it on a small input."""
+    import copy
+    cfg = synth.load_cfg("yolov5s_city_seg.yaml")
+    cfg["width_multiple"] = 0.25
+    torch.manual_seed(7)
+    model = build_reference_model(ref_yolo, cfg)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) * 0.4 + 0.8)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+            elif isinstance(m, torch.nn.Conv2d):
+                fan_in = m.weight.shape[1] * m.weight.shape[2] * m.weight.shape[3]
+                m.weight.copy_(torch.randn(m.weight.shape, generator=g) * (2.0 / fan_in) ** 0.5)
+    model.names = [f"cls{i}" for i in range(cfg["nc"])]
+    ckpt = {"epoch": 3, "best_fitness": 0.5, "training_results": "synthetic", "model": copy.deepcopy(model).half(), "ema": None, "updates": 0,
+            "optimizer": None, "wandb_id": None}
+    path = os.path.join(GOLD, "ref_ckpt_tiny.pt")
+    torch.save(ckpt, path)
+    m2 = torch.load(path, weights_only=False)["model"].float().fuse().eval()     # the reference's own loading recipe
+    x = synth.synth_image(1, 64, 64, seed=5)
+    with torch.no_grad():
+        (z, raw), seg = m2(x)
+    np.savez_compressed(os.path.join(GOLD, "ref_ckpt_tiny_out.npz"), z=z.numpy(), seg=seg.numpy(), raw0=raw[0].numpy(),
+                        names=np.array(model.names), stride=model.stride.numpy())
+    print("ckpt", os.path.getsize(path) / 1e6, "MB", z.shape, seg.shape)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     cwd = os.getcwd()
@@ -256,3 +290,5 @@ if __name__ == "__main__":
         gen_letterbox()
     if not only or "consumers" in only:
         gen_consumers()
+    if not only or "ckpt" in only:
+        gen_ckpt(ref_yolo)
