@@ -711,9 +711,14 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
-__global__ void count_valid_kernel(const long long* __restrict__ labels, long n, int ignore_index, unsigned long long* out) {
+// labels outside [0, n_cls) other than ignore_index would make torch's CrossEntropyLoss raise; here they count as ignored pixels
+// (no device-side exception exists on this path; the python wrapper documents it)
+__global__ void count_valid_kernel(const long long* __restrict__ labels, long n, int ignore_index, int n_cls, unsigned long long* out) {
   unsigned int c = 0;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) c += labels[i] != ignore_index;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long long t = labels[i];
+    c += (t != ignore_index) && t >= 0 && t < n_cls;
+  }
   c = __reduce_add_sync(0xFFFFFFFFu, c);
   if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, (unsigned long long)c);
 }
@@ -733,7 +738,7 @@ __global__ void seg_ce_pixel_kernel(TensorView lo, const long long* __restrict__
     float v[NC_PAD];
 #pragma unroll
     for (int c = 0; c < NC_PAD; ++c) v[c] = 0.f;
-    if (t != ignore_index) {
+    if (t != ignore_index && t >= 0 && t < NC) {
       int a0, a1, b0, b1; float w0, w1, v0, v1;
       lerp_src(Y, lo.H, H, &a0, &a1, &w0, &w1);
       lerp_src(X, lo.W, W, &b0, &b1, &v0, &v1);
@@ -821,7 +826,7 @@ int launch_seg_ce_fused(const TensorView& lo, int n_cls, const long long* labels
   float* loss_sum = reinterpret_cast<float*>(n_valid + 1);
   MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch16, 0, 16, s));
   const long n = (long)lo.B * H * W;
-  count_valid_kernel<<<grid_for_t(n, 256, 148 * 8), 256, 0, s>>>(labels, n, ignore_index, n_valid);
+  count_valid_kernel<<<grid_for_t(n, 256, 148 * 8), 256, 0, s>>>(labels, n, ignore_index, n_cls, n_valid);
   MYOLO_LAUNCH_CHECK();
   const int rsplit = 4;
   const int g1 = grid_for_t(n, 128), g2 = grid_for_t((long)lo.B * lo.H * lo.W * rsplit, 128);

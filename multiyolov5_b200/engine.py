@@ -73,6 +73,10 @@ class Engine:
         if key not in self.plans:
             self.plans[key] = CompiledPlan(self.model, B, H, W, self.noalias)
         p = self.plans[key]
+        ver = sum(q._version for q in self.model.parameters()) + sum(q._version for q in self.model.buffers())
+        if getattr(self, "_infer_version", None) != ver:      # in-place edits of parameters / buffers bump torch's version counters
+            self._infer_version = ver
+            self.weights_dirty = True
         if self.weights_dirty:
             for q in self.plans.values():
                 q.weights_uploaded = False
@@ -198,11 +202,25 @@ class Engine:
         raw_ptrs = (C.c_void_p * 3)(*[_lib.ptr(r) for r in raws])
         seg_ptrs = (C.c_void_p * 3)(*[_lib.ptr(segs[k]) if k < n_seg else None for k in range(3)])
         _lib.check(L.myolo_plan_train_forward_multi(p.handle, _lib.ptr(x), _lib.torch_dtype_code(x.dtype), raw_ptrs, seg_ptrs, sp))
+        # activations / batch statistics / dropout step of THIS forward live in the plan's single workspace: a backward is only valid
+        # for the most recent train forward of the plan (the reference's order forward, backward, forward, backward - train.py:364-392)
+        p.fwd_generation = getattr(p, "fwd_generation", 0) + 1
+        # running_mean / running_var moved (raw pointers): every inference plan's BN-folded weights are stale now
+        for q in self.plans.values():
+            if not q.train:
+                q.weights_uploaded = False
         self.last_plan = p
         return raws, (segs[0] if n_seg == 1 else segs), p
 
-    def train_backward(self, plan, grad_raws, grad_seg):
+    def _check_generation(self, plan, generation):
+        if generation is not None and generation != getattr(plan, "fwd_generation", 0):
+            raise _lib.MyoloError("backward of a stale train-mode forward: another forward of the same (B,H,W) ran in between and overwrote the "
+                                  "saved activations (one outstanding forward per shape; run forward, backward, forward, backward like "
+                                  "reference train.py:364-392)")
+
+    def train_backward(self, plan, grad_raws, grad_seg, generation=None):
         """grad_seg: one tensor / None, or a list of up to three (BiSe: main, aux16, aux32)"""
+        self._check_generation(plan, generation)
         gr = [g.float().contiguous() if g is not None else None for g in grad_raws]
         gsl = list(grad_seg) if isinstance(grad_seg, (list, tuple)) else [grad_seg]
         gsl = [g.float().contiguous() if g is not None else None for g in gsl] + [None] * (3 - len(gsl))
@@ -244,13 +262,13 @@ class _TrainFunction(torch.autograd.Function):
     def forward(ctx, anchor, engine, x):
         ctx.set_materialize_grads(False)
         raws, seg, plan = engine.train_forward(x)
-        ctx.engine, ctx.plan = engine, plan
+        ctx.engine, ctx.plan, ctx.generation = engine, plan, plan.fwd_generation
         segs = seg if isinstance(seg, list) else [seg]
         return (*raws, *segs)
 
     @staticmethod
     def backward(ctx, g0, g1, g2, *gsegs):
-        ctx.engine.train_backward(ctx.plan, [g0, g1, g2], list(gsegs))   # parameter gradients are accumulated into the flat .grad buffer
+        ctx.engine.train_backward(ctx.plan, [g0, g1, g2], list(gsegs), generation=ctx.generation)   # parameter gradients are accumulated into the flat .grad buffer
         return None, None, None
 
 

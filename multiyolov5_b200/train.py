@@ -126,7 +126,11 @@ class Trainer:
     def _det_graph(self, shapes, nt_pad, dev):
         """static inputs (head outputs, padded targets) -> static outputs (d loss / d head outputs, loss items), captured once per
         (grid shapes, padded target count).  Padding rows are all-zero targets: zero width/height never matches an anchor."""
-        key = (tuple(shapes), nt_pad)
+        # every scalar the captured kernels bake in is part of the key: changing hyp / gains / gr / autobalance state re-captures
+        cl = self.compute_loss
+        key = (tuple(shapes), nt_pad, self.detgain, self.world_size, self.rank, float(getattr(self.model, "gr", 1.0)),
+               tuple(sorted((k, float(v)) for k, v in self.hyp.items() if isinstance(v, (int, float)))),
+               tuple(float(b) for b in getattr(cl, "balance", ())), bool(getattr(cl, "autobalance", False)))
         st = self._det_graphs.get(key)
         if st is not None:
             return st
@@ -173,10 +177,11 @@ class Trainer:
         _, _, plan = eng.train_forward(imgs, out_raws=st.p, want_seg=False)       # head outputs land in the graph's static inputs
         st.graph.replay()
         eng.train_backward(plan, [q.grad for q in st.p], None)
-        return st.items
+        return st.items.clone()                                                   # the static tensor is overwritten by the next replay
 
     def backward_seg(self, segimgs, segtargets):
-        if self.fused_seg_loss and self.n_seg_outputs == 1:
+        # the fused kernels are instantiated for 19 (Cityscapes) and 32 classes; any other n_segcls takes the autograd path below
+        if self.fused_seg_loss and self.n_seg_outputs == 1 and self.model.model[-2].c_out in (19, 32):
             eng = self.model.engine()
             _, _, plan = eng.train_forward(segimgs, want_seg=False)
             loss = eng.train_backward_seg_ce(plan, segtargets, factor=self.batch_size * self.seggain, scale=self.scale)
