@@ -31,7 +31,7 @@ static constexpr int kTmemCols = 256;     // 2 accumulator rounds x 128 columns
 static constexpr int kAccStride = 128;
 static constexpr int kMaxWsBytes = 40 * 1024;
 static constexpr int kSmemPerCta = 112 * 1024;   // two CTAs per SM: their epilogues / TMA latencies overlap
-static constexpr int kTileRing = 32;
+static constexpr int kBiasBytes = 4096;         // bias vector of the layer in shared memory (<= 1024 output channels)
 
 #ifdef MYOLO_TIMELINE
 #define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)
@@ -81,7 +81,81 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
   t.n0 = n_tile * p.BN;
   return t;
 }
+// tile g of a vertical round (MODE 2): G consecutive output rows of one full-row column block
+__device__ __forceinline__ TileCoord decode_vround(const ConvTcParams& p, int round, int g) {
+  TileCoord t;
+  t.b = round / p.rounds_per_img;
+  const int r = round - t.b * p.rounds_per_img;
+  const int tyg = r / p.tiles_x;
+  t.x0 = (r - tyg * p.tiles_x) * p.tw;
+  t.y0 = tyg * p.G + g;
+  t.n0 = 0;
+  return t;
+}
 
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// one 16-column chunk of the epilogue: accumulators + bias -> activation (+ residual) -> fp16 staging / fp32 global
+__device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint32_t* v, const float* bias_s, int nb, const uint4& rr0,
+                                               const uint4& rr1, bool has_res, int ci, uint32_t stg, int sub_bytes, int sw, bool pix_ok,
+                                               size_t pix) {
+  const float4* bp = reinterpret_cast<const float4*>(bias_s + nb);       // shared memory, same address for the whole warp: broadcast
+  const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+  float f[16];
+  f[0] = __uint_as_float(v[0]) + b0.x;   f[1] = __uint_as_float(v[1]) + b0.y;
+  f[2] = __uint_as_float(v[2]) + b0.z;   f[3] = __uint_as_float(v[3]) + b0.w;
+  f[4] = __uint_as_float(v[4]) + b1.x;   f[5] = __uint_as_float(v[5]) + b1.y;
+  f[6] = __uint_as_float(v[6]) + b1.z;   f[7] = __uint_as_float(v[7]) + b1.w;
+  f[8] = __uint_as_float(v[8]) + b2.x;   f[9] = __uint_as_float(v[9]) + b2.y;
+  f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
+  f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y;
+  f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
+  if (p.act == MYOLO_ACT_SILU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
+  } else if (p.act == MYOLO_ACT_SIGMOID) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
+  }
+  if (has_res) {
+    const __half2* r0 = reinterpret_cast<const __half2*>(&rr0);
+    const __half2* r1 = reinterpret_cast<const __half2*>(&rr1);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 fa = __half22float2(r0[e]), fb = __half22float2(r1[e]);
+      f[2 * e] += fa.x;     f[2 * e + 1] += fa.y;
+      f[8 + 2 * e] += fb.x; f[8 + 2 * e + 1] += fb.y;
+    }
+  }
+  if (p.out_mode == 0) {
+    const int ch = ci << 4;
+    const int sub = ch >> p.log2_ow;
+    const int u0 = (ch & (p.ow - 1)) >> 3;
+    const uint32_t srow = stg + sub * sub_bytes;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 o;
+      __half2* o2 = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(f[h * 8 + 2 * e], f[h * 8 + 2 * e + 1]);
+      sts128(srow + (((u0 + h) ^ sw) << 4), o);
+    }
+  } else if (pix_ok) {
+    float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      if (nb + 4 * e < p.out_f32_ctot)
+        *reinterpret_cast<float4*>(op + 4 * e) = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
+    }
+  }
+}
+
+// MODE 0: one TMA box per filter tap (1x1, stride 2, partial-row tiles, very wide dilations)
+// MODE 1: strip mode (3x3 stride 1, full-row tiles): one strip per (filter row, channel block) feeds the three kx taps
+// MODE 2: strip mode + vertical rounds (weights resident): the G tiles of a round are G consecutive rows sharing G+2 strips
+template <int MODE, bool RES>
 __global__ void __launch_bounds__(kNumThreads, 2)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmA3,
@@ -95,51 +169,55 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint8_t* smem_o = smem_b + (p.ws_mode ? p.b_res_bytes : S * p.b_stage_bytes);
   const int sub_bytes = 32 * p.ow * 2;                            // one warp sub-box: 32 rows x ow channels
   const int stg_warp_bytes = p.n_sub * sub_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_o + kEpiWarps * p.n_stg * stg_warp_bytes);
+  float* bias_s = reinterpret_cast<float*>(smem_o + kEpiWarps * p.n_stg * stg_warp_bytes);   // [n_tiles_n * BN] fp32
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bias_s) + kBiasBytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + S;
   uint64_t* tfull_bar = bars + 2 * S;
   uint64_t* tempty_bar = bars + 2 * S + 2;
   uint64_t* bres_bar = bars + 2 * S + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 5);
-  int4* tile_ring = reinterpret_cast<int4*>(bars + 2 * S + 6);    // {b, y0, x0, n0} per tile, written by the producer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int b_sub_bytes = p.BN * p.kc * 2;
   DBG_STAMP0(11);
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA0);
-    tma_prefetch_desc(&tmB);
-    if (p.out_mode == 0) tma_prefetch_desc(&tmO);
-    for (int i = 0; i < S; ++i) {
-      mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], kEpiWarps);
-    }
-    mbar_init(bres_bar, 1);
-    fence_mbar_init();
-  }
-  // Programmatic dependent launch: let the next kernel of the stream start its own prologue now ...
+  // ---- set-up.  Warp 0 (the TMA producer) only ARRIVES at the set-up barrier: it initialises the mbarriers and then starts fetching
+  // while warp 1 allocates TMEM and the epilogue warps copy the bias vector (a weight constant) into shared memory. ----
+  // Programmatic dependent launch: let the next kernel of the stream start its own prologue as early as possible.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  DBG_STAMP0(12);
-  if (p.ws_mode && warp == 0 && lane == 0) {
-    // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
-    mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
-    for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA0);
+      tma_prefetch_desc(&tmB);
+      if (p.out_mode == 0) tma_prefetch_desc(&tmO);
+      for (int i = 0; i < S; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], kEpiWarps);
+      }
+      mbar_init(bres_bar, 1);
+      fence_mbar_init();
+      __threadfence_block();
+    }
+    __syncwarp();
+    named_bar_arrive(1, kNumThreads);
+  } else {
+    if (warp == 1) {
+      tmem_alloc(tmem_slot, kTmemCols);
+    } else {
+      const int nb_tot = p.n_tiles_n * p.BN;
+      for (int i = threadIdx.x - 64; i < nb_tot; i += kEpiWarps * 32) bias_s[i] = __ldg(p.bias + i);
+    }
+    tcgen05_fence_before();
+    named_bar_sync(1, kNumThreads);
+    tcgen05_fence_after();
   }
-  // ... and wait here until every predecessor grid has completed and flushed (activations / residual come from them)
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  DBG_STAMP0(13);
+  DBG_STAMP0(12);
 
   const int a_sub_bytes = kTileM * p.kc * 2;
   const int row_bytes = p.kc * 2;
@@ -147,36 +225,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer =====================
+    if (p.ws_mode) {
+      // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
+      mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
+      for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
+    }
+    // ... wait here until every predecessor grid has completed and flushed (activations / residual come from them)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    DBG_STAMP0(13);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
-      if (p.vround) {
+      if (MODE == 2) {
         // G vertically adjacent full-row tiles: rows y0 .. y0+n_valid-1 need input rows y0-1 .. y0+n_valid -> n_valid+2 strips
-        const int b = round / p.rounds_per_img;
-        const int r = round - b * p.rounds_per_img;
-        const int tyg = r / p.tiles_x;
-        const int x0 = (r - tyg * p.tiles_x) * p.tw, y0 = tyg * p.G;
-        const int n_valid = min(p.G, p.Ho - y0);
-        for (int g = 0; g < n_valid; ++g) tile_ring[(it + g) & (kTileRing - 1)] = make_int4(b, y0 + g, x0, 0);
-        it += n_valid;
+        const TileCoord t = decode_vround(p, round, 0);
+        const int n_valid = min(p.G, p.Ho - t.y0);
+        DBG_STAMP(0);
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int s = 0; s < n_valid + 2; ++s) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2) * row_bytes);
-            tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, x0 - 1, y0 - 1 + s, b);
+            tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - 1, t.y0 - 1 + s, t.b);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
+        DBG_STAMP(1);
+        it += n_valid;
         continue;
       }
       for (int g = 0; g < p.G; ++g) {
         const int tile = round * p.G + g;
         if (tile >= p.total_tiles) break;
         const TileCoord t = decode_tile(p, tile, tiles_per_img);
-        // the epilogue reads this slot only after tfull of the same round, i.e. long after this write (mbarrier chain)
-        tile_ring[it & (kTileRing - 1)] = make_int4(t.b, t.y0, t.x0, t.n0);
         DBG_STAMP(0);
-        if (p.strip) {
+        if (MODE == 1) {
           for (int ky = 0; ky < 3; ++ky)
             for (int cb = 0; cb < p.cblocks; ++cb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -213,6 +295,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp == 1 && lane == 0) {
     // ===================== MMA issuer (single thread) =====================
+    const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = (1u << 4)                       // D format: fp32
                            | (0u << 7) | (0u << 10)        // A, B format: fp16
                            | (0u << 15) | (0u << 16)       // A, B K-major
@@ -233,7 +316,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       mbar_wait(&tempty_bar[as], aphase ^ 1);
       tcgen05_fence_after();
       DBG_STAMP(3);
-      if (p.vround) {
+      if (MODE == 2) {
         const int r = round % p.rounds_per_img;
         const int n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
         for (int cb = 0; cb < p.cblocks; ++cb)
@@ -257,51 +340,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             umma_commit(&empty_bar[stage]);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
-      } else
-      for (int g = 0; g < p.G; ++g) {
-        if (round * p.G + g >= p.total_tiles) break;
-        const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
-        if (p.strip) {
-          uint32_t first = 0;
-          for (int ky = 0; ky < 3; ++ky)
-            for (int cb = 0; cb < p.cblocks; ++cb) {
+      } else {
+        for (int g = 0; g < p.G; ++g) {
+          if (round * p.G + g >= p.total_tiles) break;
+          const uint32_t tmem_d = tmem_base + as * kAccStride + g * p.BN;
+          if (MODE == 1) {
+            uint32_t first = 0;
+            for (int ky = 0; ky < 3; ++ky)
+              for (int cb = 0; cb < p.cblocks; ++cb) {
+                mbar_wait(&full_bar[stage], phase);
+                tcgen05_fence_after();
+                const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
+                uint32_t lb = p.ws_mode ? lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16)
+                                        : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
+                const uint32_t lb_step = p.ws_mode ? (uint32_t)(p.cblocks * bsub16) : (uint32_t)bsub16;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  const uint32_t lak = la + kx * p.dil * row16;          // same strip, shifted by kx*dil pixels
+                  for (int k = 0; k < kmma; ++k) {
+                    umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, first);
+                    first = 1;
+                  }
+                  lb += lb_step;
+                }
+                umma_commit(&empty_bar[stage]);
+                if (++stage == S) { stage = 0; phase ^= 1; }
+              }
+          } else {
+            int q = 0;
+            for (int ks = 0; ks < p.n_kstages; ++ks) {
               mbar_wait(&full_bar[stage], phase);
               tcgen05_fence_after();
-              const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
-              uint32_t lb = p.ws_mode ? lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16)
-                                      : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
-              const uint32_t lb_step = p.ws_mode ? (uint32_t)(p.cblocks * bsub16) : (uint32_t)bsub16;
-#pragma unroll
-              for (int kx = 0; kx < 3; ++kx) {
-                const uint32_t lak = la + kx * p.dil * row16;          // same strip, shifted by kx*dil pixels
+              if (ks == 0) DBG_STAMP(4);
+              const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+              uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
+              uint32_t lb = p.ws_mode ? lb_res + (uint32_t)(q * bsub16) : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
+              for (int j = 0; j < nch; ++j, ++q) {
                 for (int k = 0; k < kmma; ++k) {
-                  umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, first);
-                  first = 1;
+                  // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
+                  umma_f16_ss(tmem_d, desc_join(la + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((ks | j | k) != 0));
                 }
-                lb += lb_step;
+                la += asub16;
+                lb += bsub16;
               }
-              umma_commit(&empty_bar[stage]);
+              umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
-        } else {
-          int q = 0;
-          for (int ks = 0; ks < p.n_kstages; ++ks) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            if (ks == 0) DBG_STAMP(4);
-            const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-            uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
-            uint32_t lb = p.ws_mode ? lb_res + (uint32_t)(q * bsub16) : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
-            for (int j = 0; j < nch; ++j, ++q) {
-              for (int k = 0; k < kmma; ++k) {
-                // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
-                umma_f16_ss(tmem_d, desc_join(la + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((ks | j | k) != 0));
-              }
-              la += asub16;
-              lb += bsub16;
-            }
-            umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
-            if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -312,6 +396,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
   } else if (warp >= 2) {
     // ===================== epilogue: 8 autonomous warps =====================
+    const uint32_t tmem_base = *tmem_slot;
     const int quarter = warp & 3;                  // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;           // tile row == pixel index inside the tw x th rectangle
@@ -325,30 +410,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int g_first = p.ep_split_cols ? 0 : half;
     const int g_step = p.ep_split_cols ? 1 : 2;
     const bool idle_half = (!p.ep_split_cols && p.G == 1 && half == 1);
+    constexpr bool has_res = RES;
     int as = 0;
     uint32_t aphase = 0;
     int sbuf = 0;
-    int ring_base = 0;
     int it = 0;
+    // the predecessor's output (the residual) is only read after the dependency wait
+    if (has_res) asm volatile("griddepcontrol.wait;" ::: "memory");
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
       int n_valid;
-      if (p.vround) {
+      if (MODE == 2) {
         const int r = round % p.rounds_per_img;
         n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
       } else {
         n_valid = min(p.G, p.total_tiles - round * p.G);
       }
       if (warp == 2 && lane == 0) DBG_STAMP(6);
-      mbar_wait(&tfull_bar[as], aphase);
-      tcgen05_fence_after();
-      if (warp == 2 && lane == 0) DBG_STAMP(7);
+      bool waited = false;
       if (!idle_half) {
         for (int g = g_first; g < n_valid; g += g_step) {
-          const int4 ti = tile_ring[(ring_base + g) & (kTileRing - 1)];
-          const int tb = ti.x, ty0 = ti.y, tx0 = ti.z, tn0 = ti.w;
-          const int py = ty0 + ry, px = tx0 + rx;
+          const TileCoord tc = MODE == 2 ? decode_vround(p, round, g) : decode_tile(p, round * p.G + g, tiles_per_img);
+          const int py = tc.y0 + ry, px = tc.x0 + rx;
           const bool pix_ok = (py < p.Ho) && (px < p.Wo);
-          const size_t pix = ((size_t)tb * p.Ho + py) * p.Wo + px;
+          const size_t pix = ((size_t)tc.b * p.Ho + py) * p.Wo + px;
+          // residual of the first column pair: issued before the accumulator wait so that its latency hides behind the MMAs
+          uint4 rr[4];
+          rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0, 0, 0, 0);
+          const __half* rp = has_res ? p.residual + pix * p.res_ctot + tc.n0 + c_lo * 16 : nullptr;
+          if (has_res && pix_ok) {
+            const int nb = tc.n0 + c_lo * 16;
+            if (nb < p.Co) rr[0] = __ldg(reinterpret_cast<const uint4*>(rp));
+            if (nb + 8 < p.Co) rr[1] = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+            if (nchunks_w > 1) {
+              if (nb + 16 < p.Co) rr[2] = __ldg(reinterpret_cast<const uint4*>(rp + 16));
+              if (nb + 24 < p.Co) rr[3] = __ldg(reinterpret_cast<const uint4*>(rp + 24));
+            }
+          }
           if (p.out_mode == 0) {
             // my staging buffer was handed to the TMA engine n_stg stores ago: it must have been read by now
             if (lane == 0) {
@@ -357,79 +454,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             }
             __syncwarp();
           }
+          if (!waited) {
+            mbar_wait(&tfull_bar[as], aphase);
+            tcgen05_fence_after();
+            waited = true;
+            if (warp == 2 && lane == 0) DBG_STAMP(7);
+          }
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride + g * p.BN;
           const uint32_t stg = stg0 + sbuf * stg_warp_bytes;
-          for (int ci = 0; ci < nchunks_w; ++ci) {
-            const int c = c_lo + ci;
-            const int nb = tn0 + c * 16;
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(taddr + c * 16, v);
-            uint4 rr0 = make_uint4(0, 0, 0, 0), rr1 = make_uint4(0, 0, 0, 0);
-            if (p.residual != nullptr && pix_ok) {
-              const __half* rp = p.residual + pix * p.res_ctot + nb;
-              if (nb < p.Co) rr0 = __ldg(reinterpret_cast<const uint4*>(rp));
-              if (nb + 8 < p.Co) rr1 = __ldg(reinterpret_cast<const uint4*>(rp + 8));
+          for (int cp = 0; cp < nchunks_w; cp += 2) {
+            const bool two = cp + 1 < nchunks_w;
+            const int c = c_lo + cp;
+            const int nb = tc.n0 + c * 16;
+            uint32_t v[32];
+            tmem_ld_32x32b_x16(taddr + c * 16, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            if (two) tmem_ld_32x32b_x16(taddr + c * 16 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            if (cp > 0 && has_res && pix_ok) {
+              const __half* rq = rp + cp * 16;
+              rr[0] = rr[1] = rr[2] = rr[3] = make_uint4(0, 0, 0, 0);
+              if (nb < p.Co) rr[0] = __ldg(reinterpret_cast<const uint4*>(rq));
+              if (nb + 8 < p.Co) rr[1] = __ldg(reinterpret_cast<const uint4*>(rq + 8));
+              if (two) {
+                if (nb + 16 < p.Co) rr[2] = __ldg(reinterpret_cast<const uint4*>(rq + 16));
+                if (nb + 24 < p.Co) rr[3] = __ldg(reinterpret_cast<const uint4*>(rq + 24));
+              }
             }
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + nb);
-            const float4 b0 = __ldg(bp), b1 = __ldg(bp + 1), b2 = __ldg(bp + 2), b3 = __ldg(bp + 3);
             tmem_ld_wait();
-            float f[16];
-            f[0] = __uint_as_float(v[0]) + b0.x;   f[1] = __uint_as_float(v[1]) + b0.y;
-            f[2] = __uint_as_float(v[2]) + b0.z;   f[3] = __uint_as_float(v[3]) + b0.w;
-            f[4] = __uint_as_float(v[4]) + b1.x;   f[5] = __uint_as_float(v[5]) + b1.y;
-            f[6] = __uint_as_float(v[6]) + b1.z;   f[7] = __uint_as_float(v[7]) + b1.w;
-            f[8] = __uint_as_float(v[8]) + b2.x;   f[9] = __uint_as_float(v[9]) + b2.y;
-            f[10] = __uint_as_float(v[10]) + b2.z; f[11] = __uint_as_float(v[11]) + b2.w;
-            f[12] = __uint_as_float(v[12]) + b3.x; f[13] = __uint_as_float(v[13]) + b3.y;
-            f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
-            if (p.act == MYOLO_ACT_SILU) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
-            } else if (p.act == MYOLO_ACT_SIGMOID) {
-#pragma unroll
-              for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
-            }
-            if (p.residual != nullptr) {
-              const __half2* r0 = reinterpret_cast<const __half2*>(&rr0);
-              const __half2* r1 = reinterpret_cast<const __half2*>(&rr1);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 fa = __half22float2(r0[e]), fb = __half22float2(r1[e]);
-                f[2 * e] += fa.x;     f[2 * e + 1] += fa.y;
-                f[8 + 2 * e] += fb.x; f[8 + 2 * e + 1] += fb.y;
-              }
-            }
-            if (p.out_mode == 0) {
-              const int ch = ci << 4;
-              const int sub = ch >> p.log2_ow;
-              const int u0 = (ch & (p.ow - 1)) >> 3;
-              const uint32_t srow = stg + sub * sub_bytes;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                uint4 o;
-                __half2* o2 = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) o2[e] = __floats2half2_rn(f[h * 8 + 2 * e], f[h * 8 + 2 * e + 1]);
-                sts128(srow + (((u0 + h) ^ sw) << 4), o);
-              }
-            } else if (pix_ok) {
-              float* op = p.out_f32 + pix * p.out_f32_ctot + nb;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (nb + 4 * e < p.out_f32_ctot)
-                  *reinterpret_cast<float4*>(op + 4 * e) = make_float4(f[4 * e], f[4 * e + 1], f[4 * e + 2], f[4 * e + 3]);
-              }
-            }
+            epilogue_chunk(p, &v[0], bias_s, nb, rr[0], rr[1], has_res, cp, stg, sub_bytes, sw, pix_ok, pix);
+            if (two) epilogue_chunk(p, &v[16], bias_s, nb + 16, rr[2], rr[3], has_res, cp + 1, stg, sub_bytes, sw, pix_ok, pix);
           }
           if (p.out_mode == 0) {
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              const int nbase = tn0 + c_lo * 16;
+              const int nbase = tc.n0 + c_lo * 16;
               for (int s = 0; s < p.n_sub; ++s) {
                 if (nbase + s * p.ow < p.Co)
                   tma_store_4d(&tmO, smem_o + (warp - 2) * p.n_stg * stg_warp_bytes + sbuf * stg_warp_bytes + s * sub_bytes,
-                               nbase + s * p.ow, tx0 + wx, ty0 + wy, tb);
+                               nbase + s * p.ow, tc.x0 + wx, tc.y0 + wy, tc.b);
               }
               tma_store_commit();
             }
@@ -437,16 +499,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
       }
+      if (!waited) {   // idle half / no tile for this warp in a partial round: still take part in the accumulator hand-shake
+        mbar_wait(&tfull_bar[as], aphase);
+        tcgen05_fence_after();
+      }
       // all TMEM reads of this warp for the round are complete (every tcgen05.ld was waited on): release the accumulators
       tcgen05_fence_before();
       __syncwarp();
       if (warp == 2 && lane == 0) DBG_STAMP(9);
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
-      ring_base += n_valid;
       ++it;
     }
-    if (p.out_mode == 0 && lane == 0) tma_store_wait_all();
+    // shared memory must stay valid until the bulk stores have READ it; global visibility is given at grid completion
+    if (p.out_mode == 0 && lane == 0) tma_store_wait_read<0>();
   }
 
   tcgen05_fence_before();
@@ -454,7 +520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   DBG_STAMP0(14);
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    tmem_dealloc(*tmem_slot, kTmemCols);
   }
 }
 
@@ -542,6 +608,7 @@ bool conv_tc_eligible(const ConvOp& op) {
   }
   // tiny maps run on the generic kernel (TMA boxes larger than the tensor are avoided on purpose)
   if (op.out.W < 8 || op.out.H < 2 || op.out.W * op.out.H < 128) return false;
+  if (align_up(op.Co, 16) * 4 + 512 > kBiasBytes) return false;   // the bias vector lives in shared memory
   return true;
 }
 
@@ -660,24 +727,37 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     p.a_stage_bytes = kTileM * kKStage * 2;
     p.b_stage_bytes = p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024);
   }
-  // shared memory budget: two co-resident CTAs per SM (<= 112 KB each); fall back to one big CTA otherwise
+  // shared memory budget: two co-resident CTAs per SM (<= 112 KB each, their epilogues / TMA latencies overlap) for multi-wave layers;
+  // ONE CTA per SM with a deep operand ring when the layer has at most `one_cta_x100`/100 rounds per SM (P4/P5 maps: the pipeline depth,
+  // i.e. bytes in flight per SM, is what bounds those launches) or when two CTAs would leave fewer than 2 stages
   const int stage_bytes = p.a_stage_bytes + p.b_stage_bytes;
   const int stg1 = kEpiWarps * p.n_sub * 32 * p.ow * 2;     // one staging buffer for each of the 8 warps
-  const int misc = 2048 /*barriers + tile ring*/ + 1024 /*alignment slack*/;
-  int ctas_per_sm = 2;
-  p.n_stg = p.out_mode == 0 ? 2 : 0;
-  int S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
-  if (S < 3 && p.n_stg == 2) {
-    p.n_stg = 1;
-    S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+  const int misc = 1024 /*barriers*/ + kBiasBytes + 1024 /*alignment slack*/;
+  static int one_cta_x100 = -1;
+  if (one_cta_x100 < 0) {
+    const char* e = getenv("MYOLO_ONE_CTA_X100");
+    one_cta_x100 = e ? atoi(e) : 100;
   }
-  if (S < 2) {
-    ctas_per_sm = 1;
+  int ctas_per_sm = ((long)p.total_rounds * 100 <= (long)one_cta_x100 * num_sms) ? 1 : 2;
+  int S = 0;
+  if (ctas_per_sm == 2) {
     p.n_stg = p.out_mode == 0 ? 2 : 0;
+    S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+    if (S < 3 && p.n_stg == 2) {
+      p.n_stg = 1;
+      S = (kSmemPerCta - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+    }
+    if (S < 2) ctas_per_sm = 1;
+  }
+  if (ctas_per_sm == 1) {
+    // a CTA that runs a single round in which every epilogue warp stores at most one tile never reuses its staging buffer
+    const bool single_use = p.total_rounds <= num_sms && (p.G == 1 || (p.G == 2 && !p.ep_split_cols));
+    p.n_stg = p.out_mode == 0 ? (single_use ? 1 : 2) : 0;
     S = (220 * 1024 - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
   }
   if (S > 8) S = 8;
   MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");
+  MYOLO_REQUIRE(p.n_tiles_n * p.BN * 4 <= kBiasBytes, "conv_tc: %d output channels exceed the shared-memory bias buffer", p.n_tiles_n * p.BN);
   p.num_stages = S;
   op.smem = S * stage_bytes + p.b_res_bytes + p.n_stg * stg1 + misc;
   const int cta_cap = num_sms * ctas_per_sm;
@@ -726,7 +806,12 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   return 0;
@@ -748,7 +833,11 @@ int conv_tc_launch(const ConvOp& op, cudaStream_t stream) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  MYOLO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, op.tmA[0], op.tmA[1], op.tmA[2], op.tmA[3], op.tmB, op.tmO, op.p));
+  const bool res = op.p.residual != nullptr;
+  auto kern = op.p.vround ? (res ? conv_tc_kernel<2, true> : conv_tc_kernel<2, false>)
+              : op.p.strip ? (res ? conv_tc_kernel<1, true> : conv_tc_kernel<1, false>)
+                           : (res ? conv_tc_kernel<0, true> : conv_tc_kernel<0, false>);
+  MYOLO_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, op.tmA[0], op.tmA[1], op.tmA[2], op.tmA[3], op.tmB, op.tmO, op.p));
   g_launch_count++;
   return 0;
 }

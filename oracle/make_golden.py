@@ -239,6 +239,107 @@ def gen_consumers():
     print("consumers", int(correct), int(labeled), inter[:4], union[:4])
 
 
+# tcgen05-sized inference fixtures: every backbone / neck / head conv of these inputs runs on conv_tc_kernel (the 64x96 fixtures above
+# put every map below P2 on the CUDA-core kernel).  Stored compactly: z fp32, raw x_i fp16, low-resolution seg logits fp32, two taps.
+BIG_CASES = {
+    "s_psp_256x512": ("s_psp", "yolov5s_city_seg.yaml", 1, 256, 512, 3),
+    "m_lab_256x512": ("m_lab", "yolov5m_city_seg_lab.yaml", 1, 256, 512, 3),
+    "s_psp_512x1024": ("s_psp", "yolov5s_city_seg.yaml", 1, 512, 1024, 7),
+}
+
+
+def gen_nets_big(ref_yolo):
+    for name, (tag, yml, B, H, W, seed) in BIG_CASES.items():
+        cfg = synth.load_cfg(yml)
+        torch.manual_seed(0)
+        model = build_reference_model(ref_yolo, cfg)
+        sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1)
+        model.load_state_dict(sd)
+        model.fuse().eval()
+        x = synth.synth_image(B, H, W, seed=seed)       # NOT stored: re-created from the seed by the tests (checksum below)
+        feats, lowres = {}, {}
+        hooks = [model.model[i].register_forward_hook(lambda m, a, o, i=i: feats.__setitem__(i, o.detach().clone())) for i in (9, 23)]
+        seg_head = model.model[24]
+        seq = seg_head.out if hasattr(seg_head, "out") else (seg_head.decoder if hasattr(seg_head, "decoder") else seg_head.m)
+        hooks.append(seq[-1].register_forward_hook(lambda m, a, o: lowres.__setitem__("x", a[0].detach().clone())))
+        with torch.no_grad():
+            (z, raw), seg = model(x)
+        for h in hooks:
+            h.remove()
+        arrs = dict(x_sum=np.float64(x.double().sum().item()), z=z.numpy(), seg_lowres=lowres["x"].numpy(),
+                    seg_argmax=seg.argmax(1).numpy().astype(np.uint8), seed=np.int64(seed), shape=np.array([B, H, W]))
+        for i, r in enumerate(raw):
+            arrs[f"raw{i}"] = r.numpy().astype(np.float16)
+            arrs[f"raw{i}_absmax"] = np.float32(r.abs().max().item())
+        for i, t in feats.items():
+            arrs[f"layer{i}"] = t.numpy().astype(np.float16)
+        np.savez_compressed(os.path.join(GOLD, f"netbig_{name}.npz"), **arrs)
+        print(name, {k: getattr(v, "shape", None) for k, v in arrs.items()}, os.path.getsize(os.path.join(GOLD, f"netbig_{name}.npz")) / 1e6, "MB")
+
+
+TRAIN_CASES = {"s_psp": "yolov5s_city_seg.yaml", "s_bise": "yolov5s_city_seg_bise.yaml", "m_lab": "yolov5m_city_seg_lab.yaml",
+               "s_base": "yolov5s_city_seg_base.yaml"}
+
+
+from oracle.digest import grad_digest, train_probe_tensors  # noqa: E402
+
+
+def gen_train(ref_yolo):
+    """the reference's own TRAIN-mode `Model` (batch-statistics BatchNorm, active Dropout) + torch.autograd on a small input: head outputs,
+    the gradient of every parameter (digest), and the BatchNorm running statistics after the forward.  Pins
+    oracle.restate.model_forward_train (tests/test_oracle_golden.py)."""
+    for tag, yml in TRAIN_CASES.items():
+        cfg = synth.load_cfg(yml)
+        torch.manual_seed(0)
+        model = build_reference_model(ref_yolo, cfg)
+        sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1, gain=1.0)
+        model.load_state_dict(sd)
+        model.train()
+        x = synth.synth_image(2, 64, 96, seed=5)
+        masks, pre = [], []
+        hooks = []
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):    # the Base head's Dropout is in place (models/yolo.py:140): keep a copy of its input
+                hooks.append(m.register_forward_pre_hook(lambda mod, a: pre.append(a[0].detach().clone())))
+                hooks.append(m.register_forward_hook(lambda mod, a, o: masks.append(((o != 0) | (pre[-1] == 0)).detach().clone())))
+        torch.manual_seed(123)
+        out = model(x)
+        for h in hooks:
+            h.remove()
+        raws, seg = out
+        segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
+        Rs, Ss = train_probe_tensors([tuple(r.shape) for r in raws], [tuple(g.shape) for g in segs])
+        loss = sum((r * R).sum() for r, R in zip(raws, Rs)) + sum((g * S).sum() for g, S in zip(segs, Ss))
+        loss.backward()
+        arrs = {"loss": np.float64(loss.item())}
+        for i, r in enumerate(raws):
+            arrs[f"raw{i}"] = r.detach().numpy()
+        for k, g in enumerate(segs):
+            arrs[f"seg{k}_sub"] = g.detach()[:, :, ::3, ::3].numpy()
+        names, digests = [], []
+        for n, p_ in model.named_parameters():
+            if p_.grad is not None:
+                names.append(n)
+                digests.append(grad_digest(p_.grad))
+        arrs["grad_names"] = np.array(names)
+        arrs["grad_digest"] = np.stack(digests)
+        rn, rm, rv = [], [], []
+        for n, m in model.named_modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                rn.append(n)
+                rm.append(m.running_mean.numpy().copy())
+                rv.append(m.running_var.numpy().copy())
+        arrs["bn_names"] = np.array(rn)
+        arrs["bn_mean"] = np.concatenate(rm)
+        arrs["bn_var"] = np.concatenate(rv)
+        if masks:
+            assert len(masks) == 1
+            arrs["dropout_keep_bits"] = np.packbits(masks[0].numpy().astype(np.uint8).reshape(-1))
+            arrs["dropout_shape"] = np.array(masks[0].shape)
+        np.savez_compressed(os.path.join(GOLD, f"train_{tag}.npz"), **arrs)
+        print("train", tag, "loss", float(loss), len(names), "grads", len(rn), "BN layers", os.path.getsize(os.path.join(GOLD, f"train_{tag}.npz")) / 1e6, "MB")
+
+
 def gen_ckpt(ref_yolo):
     """a checkpoint exactly as the reference's train.py:482-494 writes it (whole pickled reference `Model` in half precision inside a
     dict), for a quarter-width yolov5s_city_seg so the fixture stays small, plus what the reference's own `attempt_load` recipe
@@ -292,3 +393,7 @@ if __name__ == "__main__":
         gen_consumers()
     if not only or "ckpt" in only:
         gen_ckpt(ref_yolo)
+    if not only or "netsbig" in only:
+        gen_nets_big(ref_yolo)
+    if not only or "train" in only:
+        gen_train(ref_yolo)

@@ -23,6 +23,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+BN_MOMENTUM = 0.03  # reference utils/torch_utils.py:151
 BN_EPS = 1e-3  # reference utils/torch_utils.py:150 (initialize_weights sets eps=1e-3 on every BN instance)
 
 
@@ -68,6 +69,14 @@ def conv_bn_act(cx: Ctx, x, wkey: str, bnp: Optional[str], k: int, s: int = 1, d
     pad = d * (k // 2)
     if bnp is not None and cx.train:
         y = F.conv2d(x, w, None, s, pad, d)
+        if getattr(cx, "new_running", None) is not None:
+            # nn.BatchNorm2d's running-statistics update in train mode: momentum 0.03 (reference utils/torch_utils.py:150-152), batch mean and
+            # UNBIASED batch variance
+            with torch.no_grad():
+                n = y.numel() // y.shape[1]
+                bm, bv = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=False)
+                cx.new_running[bnp] = ((1 - BN_MOMENTUM) * cx.sd[bnp + ".running_mean"] + BN_MOMENTUM * bm,
+                                       (1 - BN_MOMENTUM) * cx.sd[bnp + ".running_var"] + BN_MOMENTUM * bv * n / max(n - 1, 1))
         y = F.batch_norm(y, None, None, cx.sd[bnp + ".weight"], cx.sd[bnp + ".bias"], training=True, momentum=0.0, eps=BN_EPS)
         if act:
             y = y * torch.sigmoid(y)
@@ -475,11 +484,15 @@ def seg_postprocess(seg: np.ndarray, out_hw) -> np.ndarray:
     return up.argmax(axis=1).astype(np.int64)
 
 
-def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None):
+def model_forward_train(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, dropout_mask: Optional[torch.Tensor] = None,
+                        new_running: Optional[dict] = None):
     """`Model.forward` in TRAIN mode (reference models/yolo.py:225,316): returns ([x0,x1,x2] raw head outputs, seg logits) with autograd
     history, so tests can compare hand-written gradients with torch.autograd on the restated graph.  `sd` tensors that should receive
-    gradients must be leaf tensors with requires_grad=True."""
+    gradients must be leaf tensors with requires_grad=True.  `new_running`: optional dict that receives {bn prefix: (running_mean,
+    running_var)} as nn.BatchNorm2d would leave them after this forward.  Pinned against the reference's own train-mode Model + autograd
+    by tests/golden/train_*.npz (tests/test_oracle_golden.py)."""
     cx = Ctx(sd, quantised=False, train=True)
+    cx.new_running = new_running
     cx.dropout_mask = dropout_mask      # (B,C,h,w) keep mask of the Base head's dropout, or None = identity
     layers = parse_cfg(cfg)
     ys: List[Optional[torch.Tensor]] = []

@@ -150,3 +150,87 @@ def test_seg_consumer_restatements_match_reference():
     c, l, inter, union = restate.seg_metrics_np(g["m_out"], g["m_tgt"], 19)
     assert (c, l) == (int(g["m_correct"]), int(g["m_labeled"]))
     assert np.array_equal(inter, g["m_inter"]) and np.array_equal(union, g["m_union"])
+
+
+TRAIN_NETS = {"s_psp": "yolov5s_city_seg.yaml", "s_bise": "yolov5s_city_seg_bise.yaml", "m_lab": "yolov5m_city_seg_lab.yaml",
+              "s_base": "yolov5s_city_seg_base.yaml"}
+
+
+@pytest.mark.parametrize("tag", list(TRAIN_NETS))
+def test_train_restatement_pinned_by_reference_train_mode(tag):
+    """oracle.restate.model_forward_train vs the reference's own train-mode `Model` + torch.autograd (tests/golden/train_<tag>.npz, written
+    by oracle/make_golden.py gen_train): head outputs, the gradient of EVERY parameter (norm / sum / 64 samples each) and the BatchNorm
+    running statistics after the forward.  This is the pin of the truth the GPU training tests are judged against."""
+    from oracle.digest import grad_digest, train_probe_tensors
+    cfg = synth.load_cfg(TRAIN_NETS[tag])
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1, gain=1.0)
+    g = np.load(os.path.join(GOLD, f"train_{tag}.npz"))
+    x = synth.synth_image(2, 64, 96, seed=5)
+    mask = None
+    if "dropout_keep_bits" in g:
+        shp = tuple(int(v) for v in g["dropout_shape"])
+        mask = torch.from_numpy(np.unpackbits(g["dropout_keep_bits"])[:int(np.prod(shp))].reshape(shp).astype(np.float32))
+    sdg = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k and "anchor" not in k else v.clone())
+           for k, v in sd.items()}
+    new_running = {}
+    raws, seg = restate.model_forward_train(cfg, sdg, x, mask, new_running=new_running)
+    segs = list(seg) if isinstance(seg, (list, tuple)) else [seg]
+    Rs, Ss = train_probe_tensors([tuple(r.shape) for r in raws], [tuple(s.shape) for s in segs])
+    loss = sum((r * R).sum() for r, R in zip(raws, Rs)) + sum((s * S).sum() for s, S in zip(segs, Ss))
+    loss.backward()
+    for i, r in enumerate(raws):
+        assert relmax(r.detach().numpy(), g[f"raw{i}"]) < 1e-4, (i, relmax(r.detach().numpy(), g[f"raw{i}"]))
+    for k, s in enumerate(segs):
+        assert relmax(s.detach()[:, :, ::3, ::3].numpy(), g[f"seg{k}_sub"]) < 1e-4
+    assert abs(float(loss) - float(g["loss"])) < 1e-3 * max(1.0, abs(float(g["loss"])))
+    # every gradient the reference produced exists here, under the same name, with the same digest
+    names = [str(n) for n in g["grad_names"]]
+    dig = g["grad_digest"]
+    norm_errs = []
+    for n, d in zip(names, dig):
+        assert sdg[n].grad is not None, n
+        mine = grad_digest(sdg[n].grad)
+        scale = max(d[0] / np.sqrt(sdg[n].numel()), 1e-12)       # RMS magnitude of the tensor
+        err_norm = abs(mine[0] - d[0]) / max(d[0], 1e-12)
+        err_samples = float(np.abs(mine[2:] - d[2:]).max() / scale)
+        norm_errs.append(err_norm)
+        assert err_norm < 2e-3, (n, mine[0], d[0])
+        # single entries relative to the tensor's RMS.  The Base head's C3SPP max-pools an 8x12 map with 9x9 / 13x13 windows: two candidates
+        # that tie to 1e-7 route the whole window gradient to a different pixel (same d gamma / d beta, different d W upstream) - measured
+        # 1e-2 Frobenius on those tensors between the reference and this restatement, both fp32 torch
+        assert err_samples < (0.15 if tag == "s_base" else 2e-2), (n, err_samples)
+    assert float(np.median(norm_errs)) < (3e-3 if tag == "s_base" else 1e-4), float(np.median(norm_errs))
+    assert len(names) == sum(1 for v in sdg.values() if v.requires_grad and v.grad is not None)
+    # running statistics (momentum 0.03, unbiased variance)
+    off = 0
+    for n in [str(v) for v in g["bn_names"]]:
+        rm, rv = new_running[n]
+        c = rm.numel()
+        assert np.allclose(rm.numpy(), g["bn_mean"][off:off + c], rtol=1e-4, atol=1e-6), n
+        assert np.allclose(rv.numpy(), g["bn_var"][off:off + c], rtol=1e-4, atol=1e-6), n
+        off += c
+    assert off == g["bn_mean"].size
+
+
+BIG = {"s_psp_256x512": ("s_psp", "yolov5s_city_seg.yaml"), "m_lab_256x512": ("m_lab", "yolov5m_city_seg_lab.yaml")}
+
+
+@pytest.mark.parametrize("name", list(BIG))
+def test_forward_restatement_matches_reference_at_tensor_core_sizes(name):
+    """the tcgen05-sized reference fixtures (netbig_*.npz) also pin the restatement (fp32 CPU both sides)"""
+    tag, yml = BIG[name]
+    cfg = synth.load_cfg(yml)
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1)
+    g = np.load(os.path.join(GOLD, f"netbig_{name}.npz"))
+    B, H, W = [int(v) for v in g["shape"]]
+    x = synth.synth_image(B, H, W, seed=int(g["seed"]))
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6 * float(g["x_sum"])
+    out = restate.model_forward(cfg, sd, x, keep=(9, 23))
+    assert relmax(out["z"].numpy(), g["z"]) < 2e-4
+    assert relmax(out["seg_lowres"].numpy(), g["seg_lowres"]) < 2e-4
+    for i in range(3):
+        assert relmax(out["raw"][i].numpy(), g[f"raw{i}"].astype(np.float32)) < 1e-3      # stored as fp16
+    for i in (9, 23):
+        assert relmax(out["layers"][i].numpy(), g[f"layer{i}"].astype(np.float32)) < 2e-3
+    agree = float((out["seg"].argmax(1).numpy() == g["seg_argmax"]).mean())
+    assert agree > 0.9999, agree
