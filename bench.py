@@ -79,7 +79,7 @@ class ClockSampler(threading.Thread):
 def cpu_reference_line(args, tag, steps, warmup, as_main):
     """the reference's CPU implementation of the path (oracle port: torch fp32 CPU + torchvision nms), one image per step."""
     from oracle import synth
-    from oracle.cpu_pipeline import CpuPipeline
+    from oracle.cpu_pipeline import make_cpu_pipeline, reference_root
     yml, cfg, sd = make_weights(tag)
     x = synth.synth_image(1, H, W, seed=0)
     # the reference would run with torch's default (= all cores); small-batch convs often run faster with fewer threads, so give the
@@ -87,12 +87,12 @@ def cpu_reference_line(args, tag, steps, warmup, as_main):
     ncpu = os.cpu_count() or 1
     best = None
     for th in sorted({t for t in (8, 16, 32, 64, ncpu) if t <= ncpu}):
-        pipe = CpuPipeline(cfg, sd, threads=th)
+        pipe, kind = make_cpu_pipeline(cfg, sd, threads=th)
         pipe(x)
         t0 = time.perf_counter(); pipe(x); dt = time.perf_counter() - t0
         if best is None or dt < best[0]:
             best = (dt, th)
-    pipe = CpuPipeline(cfg, sd, threads=best[1])
+    pipe, kind = make_cpu_pipeline(cfg, sd, threads=best[1])
     for _ in range(warmup):
         pipe(x)
     ts, parts = [], []
@@ -102,7 +102,9 @@ def cpu_reference_line(args, tag, steps, warmup, as_main):
         ts.append(time.perf_counter() - t0)
         parts.append(tm)
     med = float(np.median(ts))
-    info = {"value": 1.0 / med, "unit": "images/s", "cores": pipe.threads, "kind": "port",
+    info = {"value": 1.0 / med, "unit": "images/s", "cores": pipe.threads, "kind": kind,
+            "code": (f"unmodified reference tree at {reference_root()} (import-only stubs, oracle/ref_shims.py)" if kind == "reference" else
+                     "oracle port of the detect.py job (oracle/cpu_pipeline.py): the reference is not an installable package and its tree is not on this box"),
             "sample": f"{steps} steps x 1 image 3x{H}x{W} fp32 (model {np.median([p['model'] for p in parts]) * 1e3:.1f} ms, nms "
                       f"{np.median([p['nms'] for p in parts]) * 1e3:.1f} ms, seg upsample+argmax {np.median([p['segpost'] for p in parts]) * 1e3:.1f} ms), "
                       f"os.cpu_count()={os.cpu_count()}, torch threads={pipe.threads} (fastest of 8/16/32/64/all)"}
@@ -116,12 +118,95 @@ def cpu_reference_line(args, tag, steps, warmup, as_main):
             "gpu_launches": 0}
 
 
+def reference_gpu_infer(tag, B, steps, warmup):
+    """detect.py job through torch's fp16 + cuDNN kernels on this GPU (oracle/gpu_pipeline.py): resident fp16 inputs, NROT batches > L2"""
+    try:
+        from oracle.gpu_pipeline import TorchHalfPipeline
+        yml, cfg, sd = make_weights(tag)
+        pipe = TorchHalfPipeline(cfg, sd)
+        gen = torch.Generator(device="cuda").manual_seed(4321)
+        xs = [torch.rand((B, 3, H, W), device="cuda", generator=gen).half() for _ in range(4)]
+        for i in range(max(3, warmup)):
+            pipe(xs[i % 4])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            pipe(xs[i % 4])
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        e0.record()
+        for i in range(steps):
+            if pipe.model is not None:
+                pipe.model(xs[i % 4])
+            else:
+                from oracle import restate
+                with torch.no_grad():
+                    restate.model_forward(cfg, pipe.sd, xs[i % 4], half=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_model = e0.elapsed_time(e1)
+        return {"images_per_s": B * steps / (ms * 1e-3), "ms_per_step": ms / steps, "model_only_images_per_s": B * steps / (ms_model * 1e-3),
+                "steps": steps, "kind": pipe.kind, "note": "python-loop NMS (torchvision.ops.nms per image) and per-image upsample+argmax as detect.py does"}
+    except Exception as e:        # a baseline arm must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
+def infer_record(tag, B, steps, warmup, world, min_seconds=1.0):
+    """sub-record for another inference config (BASELINE.json configs[2]: yolov5m + Lab head, batch 8): same step as the headline"""
+    import torch.distributed as dist
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.utils.general import non_max_suppression, seg_argmax
+    yml, cfg, sd = make_weights(tag)
+    model = Model(yml)
+    model.load_state_dict(sd)
+    model.cuda().eval().half()
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    xs = [torch.rand((B, 3, H, W), device="cuda", generator=gen).half() for _ in range(4)]
+
+    def step(i):
+        (z, _), seg = model(xs[i % 4])
+        non_max_suppression(z, 0.25, 0.45, return_padded=True)
+        seg_argmax(seg, (H, W))
+
+    def run(n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            step(i)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    for i in range(max(3, warmup)):
+        step(i)
+    ms = run(steps)
+    n_long = max(steps, int(min_seconds * 1e3 / (ms / steps)) + 1)
+    ms_long = run(n_long)
+    rec = {"workload": f"{yml} inference, batch {B}x3x{H}x{W} per GPU, half mode: Model.forward + NMS(0.25,0.45) + seg argmax", "n_gpus": world, "steps": steps,
+           "ms_per_step": ms / steps, "images_per_s": B * world * steps / (ms * 1e-3),
+           "sustained": {"steps": n_long, "seconds": ms_long * 1e-3, "images_per_s": B * world * n_long / (ms_long * 1e-3)},
+           "gflop_per_image": (CFGS[tag][1] or 0) / 1e9}
+    del model, xs
+    torch.cuda.empty_cache()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the train / m_lab / reference-gpu sub-records (quick runs, ncu captures)")
     ap.add_argument("--cfg", default="s_psp", choices=list(CFGS))
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -136,6 +221,19 @@ def main():
     if args.impl == "reference":
         if rank == 0:
             print(json.dumps(cpu_reference_line(args, args.cfg, max(3, min(args.steps, 30)), min(warmup, 3), True)), flush=True)
+        return
+    if args.impl == "reference-gpu":
+        # the reference's own GPU configuration (torch fp16 + cuDNN, cudnn.benchmark; detect.py:96-103,124) on ONE B200: a baseline arm
+        if rank == 0:
+            torch.cuda.set_device(local)
+            B = args.batch or (16 if args.cfg.startswith("s_") else 8)
+            rec = reference_gpu_infer(args.cfg, B, max(5, min(args.steps, 20)), warmup)
+            line = {"metric": "images/sec @1024x512 (det+seg fwd)", "value": rec.get("images_per_s"), "unit": "images/s", "n_gpus": 1,
+                    "steps": rec.get("steps"), "warmup": warmup, "ms_per_step": rec.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f16 (torch / cuDNN)", "data": "synthetic", "impl": "reference-gpu",
+                    "config": {"workload": f"{CFGS[args.cfg][0]} detect.py job, batch {B}x3x{H}x{W}, inputs resident in HBM"}, "detail": rec,
+                    "gpu_launches": 0}
+            print(json.dumps(line), flush=True)
         return
 
     import torch.distributed as dist
@@ -255,6 +353,14 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total = timed(step_resident, args.steps, sampler)
+    # the same step for >= 1 s (the driver's `steps` make a ~50 ms region: a burst figure; this one runs at sustained clocks / power)
+    n_long = max(args.steps, int(1000.0 / (ms_total / args.steps)) + 1)
+    sampler_long = ClockSampler(local) if rank == 0 else None
+    if sampler_long:
+        sampler_long.start()
+    ms_long = timed(step_resident, n_long)
+    if sampler_long:
+        sampler_long.stop_flag = True
     det, cnt, cls = step_resident(0)
     torch.cuda.synchronize()
     n_cand = float(cnt.float().mean().item())
@@ -319,13 +425,23 @@ def main():
         per_op = acc / reps
         pb = eng.last_plan.pb
         from multiyolov5_b200 import _lib
-        conv_ms = sum(per_op[i] for i, o in enumerate(pb.ops) if o.kind == _lib.OP_CONV)
-        n_conv = sum(1 for o in pb.ops if o.kind == _lib.OP_CONV)
-        flops = 0.0
+        import ctypes as C
+        conv_ms = simt_ms = 0.0
+        n_conv = n_simt = 0
+        flops = simt_flops = 0.0
+        info = (C.c_int32 * 12)()
+        conv_table = []
         for i, o in enumerate(pb.ops):
             if o.kind == _lib.OP_CONV:
                 s = pb.slots[o.slot].conv
-                flops += 2.0 * B * o.out.h * o.out.w * s.out_channels * s.in_channels * s.kernel_size[0] * s.kernel_size[1]
+                f = 2.0 * B * o.out.h * o.out.w * s.out_channels * s.in_channels * s.kernel_size[0] * s.kernel_size[1]
+                _lib.check(_lib.lib().myolo_plan_conv_info(eng.last_plan.handle, i, info))
+                if info[0]:      # tcgen05 kernel
+                    conv_ms += per_op[i]; n_conv += 1; flops += f
+                else:            # CUDA-core kernel (maps < one 128-pixel tile: PPM bins, FFM attention FCs)
+                    simt_ms += per_op[i]; n_simt += 1; simt_flops += f
+                conv_table.append((i, o.tag, f"{s.in_channels}->{s.out_channels} k{s.kernel_size[0]}s{s.stride[0]}d{s.dilation[0]} @{o.out.h}x{o.out.w}",
+                                   list(info), per_op[i] * 1e3, f))
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -341,12 +457,17 @@ def main():
         except Exception:
             pass
         roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                "kernel": "conv_tc_kernel (all fused Conv+BN+SiLU launches of one forward)", "launches": n_conv, "avg_launch_ms": conv_ms / n_conv,
+                "kernel": "conv_tc_kernel (the tcgen05 Conv+BN+SiLU launches of one forward; CUDA-core conv launches are listed separately)",
+                "launches": n_conv, "avg_launch_ms": conv_ms / n_conv, "simt_conv_launches": n_simt, "simt_conv_ms": simt_ms,
+                "simt_conv_flops_per_step": simt_flops,
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
                 "conv_share_of_forward": conv_ms / float(per_op.sum())}
         if args.profile_ops:
             for i, o in enumerate(pb.ops):
                 print(f"{i:3d} kind={o.kind:2d} {o.tag:24s} {per_op[i] * 1e3:9.1f} us", file=sys.stderr)
+            print("# conv launches: op, layer, shape, [tc, grid, smem, BN, stages, mode, ws, G, tiles, ntn, kc, cta/sm], us, TFLOP/s", file=sys.stderr)
+            for (i, tg, shp, inf, us, f) in conv_table:
+                print(f"#conv {i:3d} {tg:16s} {shp:30s} {inf} {us:8.1f} us {f / (us * 1e-6) / 1e12:7.1f} TF/s", file=sys.stderr)
 
     if rank == 0:
         imgs = B * world * args.steps
@@ -364,7 +485,28 @@ def main():
                 "e2e_from_raw_frames": {"value": imgs / (ms_raw * 1e-3), "unit": "images/s", "h2d_bytes_per_step": B * 4 * H * W * 3,
                                         "note": "2048x1024 BGR uint8 frames -> device letterbox/pre-process kernel (bit exact with cv2) -> forward -> post-process"},
                 "model_only_images_per_s": imgs / (ms_model * 1e-3), "fused_argmax_images_per_s": imgs / (ms_fused * 1e-3),
-                "clocks": sampler.summary() if sampler else None, "roofline": roof}
+                "clocks": sampler.summary() if sampler else None, "roofline": roof,
+                "sustained": {"steps": n_long, "seconds": ms_long * 1e-3, "ms_per_step": ms_long / n_long,
+                              "value": B * world * n_long / (ms_long * 1e-3), "clocks": sampler_long.summary() if sampler_long else None,
+                              "note": "same resident step as `value`, timed for >= 1 s"}}
+        line["e2e"]["d2h_note"] = "class map returned as uint8 (19 classes); the reference's .cpu() moves the same map as int64, 8x the bytes"
+    # ---- sub-records for the other BASELINE.json configs (every rank takes part: the train step contains the path's one collective)
+    extras = {}
+    if not args.no_extras and tag == "s_psp" and args.batch is None:
+        del xs_u8, xs_f32, dev_in2, keep
+        model = eng = None
+        torch.cuda.empty_cache()
+        from tools.bench_train import train_record
+        extras["train"] = train_record(world, rank, steps=max(6, args.steps // 2), warmup=warmup, B=4, with_reference_gpu=(world == 1))
+        extras["m_lab"] = infer_record("m_lab", 8, args.steps, warmup, world)
+        if rank == 0 and world == 1:
+            extras["reference_gpu"] = reference_gpu_infer(tag, B, 10, warmup)
+    if rank == 0:
+        line.update(extras)
+        if "reference_gpu" in extras and extras["reference_gpu"].get("images_per_s"):
+            line["reference_gpu"]["ours_over_torch"] = line["value"] / extras["reference_gpu"]["images_per_s"]
+        if "train" in extras and isinstance(extras["train"].get("reference_gpu"), dict) and extras["train"]["reference_gpu"].get("ms_per_step"):
+            extras["train"]["reference_gpu"]["ours_over_torch"] = extras["train"]["reference_gpu"]["ms_per_step"] / extras["train"]["ms_per_step"]
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_reference_line(args, tag, 8, 2, False)
         print(json.dumps(line), flush=True)

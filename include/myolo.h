@@ -120,6 +120,9 @@ int myolo_plan_forward(myolo_plan* plan, const void* x, int x_dtype, float* z, f
 int myolo_plan_read_view(myolo_plan* plan, myolo_view view, float* dst_nchw, void* stream);
 /* number of kernels the last myolo_plan_forward launched (bench.py's gpu_launches) */
 int64_t myolo_plan_last_launch_count(const myolo_plan* plan);
+/* which kernel conv op `op_index` takes and its tiling: info[12] = {1 tcgen05 / 0 CUDA-core, grid, smem bytes, BN, stages, mode (0 taps /
+ * 1 strip / 2 vertical rounds), weights-stationary, G, tiles, N tiles, kc, CTAs per SM}.  Feeds bench.py's roofline record and profiles/. */
+int myolo_plan_conv_info(myolo_plan* plan, int op_index, int32_t* info);
 /* per-op device time of the next forward (CUDA events around every op; host array of n_ops floats, ms) */
 int myolo_plan_profile(myolo_plan* plan, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
                        int64_t* seg_argmax, float* host_ms_per_op, void* stream);
@@ -163,6 +166,12 @@ int myolo_grads_check_finite(const float* grad, int64_t n, int32_t* found_inf /*
 int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr,
                    const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale /* device */,
                    const int32_t* found_inf /* device, nullable */, int zero_grad, void* stream);
+
+/* The path's ONE exchange step (reference train.py:243-245 wraps the model in DistributedDataParallel): in-place
+ * SUM all-reduce of the flat fp32 gradient buffer over the ranks of `nccl_comm` (an ncclComm_t; averaging is folded into myolo_sgd_step's
+ * inv_scale), enqueued on `stream`.  The library does not link NCCL: it binds ncclAllReduce from the libnccl the host process has already
+ * loaded (torch's); MYOLO_E_INVALID if no NCCL is loaded.  Python binding: parallel.allreduce_flat_grads. */
+int myolo_allreduce_grads(float* flat_grad, int64_t n, void* nccl_comm, void* stream);
 
 /* ---- pre-process ----
  * `letterbox` of reference utils/datasets.py:818-848 (cv2.resize INTER_LINEAR to resized_w x resized_h, constant border) on uint8 HWC

@@ -30,6 +30,7 @@ static constexpr int kNumThreads = 64 + kEpiWarps * 32;
 static constexpr int kTmemCols = 256;     // 2 accumulator rounds x 128 columns
 static constexpr int kAccStride = 128;
 static constexpr int kMaxWsBytes = 40 * 1024;
+static constexpr int kMaxWsBytesBig = 100 * 1024;
 static constexpr int kSmemPerCta = 112 * 1024;   // two CTAs per SM: their epilogues / TMA latencies overlap
 static constexpr int kBiasBytes = 4096;         // bias vector of the layer in shared memory (<= 1024 output channels)
 
@@ -681,22 +682,28 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     strip_env = e ? atoi(e) : 1;   // 1: shifted start addresses (the UMMA swizzle is a function of the absolute smem address - verified on B200)
   }
   p.strip = (strip_env > 0 && op.k == 3 && op.stride == 1 && p.th == 1 && p.tw + 2 * op.dil <= 256) ? strip_env : 0;
-  // accumulator rounds: G tiles share one TMEM stage when the layer is big enough to keep every CTA busy
-  p.G = 1;
-  if (p.n_tiles_n == 1) {
-    for (int g = 4; g >= 2; g >>= 1)
-      if (g * p.BN <= kAccStride && p.total_tiles / g >= 2 * max_ctas) { p.G = g; break; }
-  }
-  p.total_rounds = ceil_div(p.total_tiles, p.G);
-  // weights-stationary mode: one N tile and the whole [BN x K] weight tile fits next to the A ring
-  static int ws_kb = -1;
+  // weights-stationary mode: one N tile and the whole [BN x K] weight tile stays resident in shared memory.  Up to kMaxWsBytes two CTAs
+  // share an SM; larger tiles (up to kMaxWsBytesBig: 3x3 64->64, 1x1 256->128, 384->64 ...) take the SM alone - shared-memory fill
+  // bandwidth (measured: 40 B/clk per SM) is what bounds these layers, so not re-fetching the weights per M tile is worth the lost co-residency
+  static int ws_kb = -1, ws_big_kb = -1;
   if (ws_kb < 0) {
     const char* e = getenv("MYOLO_WS_KB");
     ws_kb = e ? atoi(e) : kMaxWsBytes / 1024;
+    const char* e2 = getenv("MYOLO_WS_BIG_KB");
+    ws_big_kb = e2 ? atoi(e2) : kMaxWsBytesBig / 1024;
   }
   const int w_bytes = p.n_chunks * p.BN * p.kc * 2;
-  p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= ws_kb * 1024) ? 1 : 0;
+  p.ws_mode = (p.n_tiles_n == 1 && w_bytes <= (ws_big_kb > ws_kb ? ws_big_kb : ws_kb) * 1024) ? 1 : 0;
+  const bool ws_big = p.ws_mode && w_bytes > ws_kb * 1024;       // forces one CTA per SM
   p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
+  // accumulator rounds: G tiles share one TMEM stage when the layer is big enough to keep every CTA busy
+  const int cta_budget = ws_big ? num_sms : max_ctas;
+  p.G = 1;
+  if (p.n_tiles_n == 1) {
+    for (int g = 4; g >= 2; g >>= 1)
+      if (g * p.BN <= kAccStride && p.total_tiles / g >= 2 * cta_budget) { p.G = g; break; }
+  }
+  p.total_rounds = ceil_div(p.total_tiles, p.G);
   // vertical rounds: the G tiles of a round are G consecutive image rows, so G+2 strips feed 3*G (row, filter-row) pairs
   static int vr_env = -1;
   if (vr_env < 0) {
@@ -738,7 +745,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     const char* e = getenv("MYOLO_ONE_CTA_X100");
     one_cta_x100 = e ? atoi(e) : 100;
   }
-  int ctas_per_sm = ((long)p.total_rounds * 100 <= (long)one_cta_x100 * num_sms) ? 1 : 2;
+  int ctas_per_sm = (ws_big || (long)p.total_rounds * 100 <= (long)one_cta_x100 * num_sms) ? 1 : 2;
   int S = 0;
   if (ctas_per_sm == 2) {
     p.n_stg = p.out_mode == 0 ? 2 : 0;

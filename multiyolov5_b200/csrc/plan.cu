@@ -582,6 +582,25 @@ extern "C" int myolo_plan_profile(myolo_plan* pl, const void* x, int x_dtype, fl
 
 extern "C" int64_t myolo_plan_last_launch_count(const myolo_plan* pl) { return pl ? pl->last_launches : 0; }
 
+// which kernel a conv op of the plan takes and how it is tiled (valid after the first forward): info[0..11] =
+// {1 tcgen05 / 0 CUDA-core, grid, dynamic smem bytes, BN, pipeline stages, mode (0 taps, 1 strip, 2 vertical rounds), weights-stationary,
+//  G, total tiles, n tiles in N, kc, CTAs per SM}
+extern "C" int myolo_plan_conv_info(myolo_plan* pl, int op_index, int32_t* info) {
+  MYOLO_REQUIRE(pl && info && op_index >= 0 && op_index < (int)pl->ops.size(), "conv_info: bad arguments");
+  MYOLO_REQUIRE(pl->ops[op_index].kind == MYOLO_OP_CONV, "conv_info: op %d is not a conv", op_index);
+  int rc;
+  if (!pl->conv_ready[op_index] && (rc = prepare_conv(pl, op_index))) return rc;
+  const ConvOp& c = pl->convs[op_index];
+  for (int i = 0; i < 12; ++i) info[i] = 0;
+  info[0] = c.use_tc ? 1 : 0;
+  if (c.use_tc) {
+    info[1] = c.grid; info[2] = c.smem; info[3] = c.p.BN; info[4] = c.p.num_stages; info[5] = c.p.vround ? 2 : (c.p.strip ? 1 : 0);
+    info[6] = c.p.ws_mode; info[7] = c.p.G; info[8] = c.p.total_tiles; info[9] = c.p.n_tiles_n; info[10] = c.p.kc;
+    info[11] = c.smem > 113 * 1024 ? 1 : 2;
+  }
+  return 0;
+}
+
 extern "C" int myolo_plan_read_view(myolo_plan* pl, myolo_view view, float* dst, void* stream) {
   MYOLO_REQUIRE(pl && dst, "read_view: null argument");
   TensorView v;
@@ -1169,6 +1188,29 @@ extern "C" int myolo_sgd_step(float* param, float* grad, float* momentum_buf, co
   if (rc) return rc;
   return launch_sgd_step(param, grad, momentum_buf, group, (long)n, lr, weight_decay, n_groups, momentum, nesterov, inv_scale, found_inf,
                          zero_grad, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gradient exchange: NCCL all-reduce of the flat gradient buffer, bound at run time from the libnccl already in the process
+// ------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
+extern "C" int myolo_allreduce_grads(float* flat_grad, int64_t n, void* nccl_comm, void* stream) {
+  MYOLO_REQUIRE(flat_grad && n > 0 && nccl_comm, "allreduce_grads: bad arguments");
+  static PFN_ncclAllReduce fn = nullptr;
+  if (!fn) {
+    void* sym = dlsym(RTLD_DEFAULT, "ncclAllReduce");
+    if (!sym) {
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+      if (h) sym = dlsym(h, "ncclAllReduce");
+    }
+    MYOLO_REQUIRE(sym, "allreduce_grads: no NCCL library is loaded in this process (torch.distributed with the nccl backend loads it)");
+    fn = reinterpret_cast<PFN_ncclAllReduce>(sym);
+  }
+  const int rc = fn(flat_grad, flat_grad, (size_t)n, 7 /* ncclFloat32 */, 0 /* ncclSum */, nccl_comm, (cudaStream_t)stream);
+  MYOLO_REQUIRE(rc == 0, "allreduce_grads: ncclAllReduce failed with ncclResult_t %d", rc);
+  g_launch_count++;
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------

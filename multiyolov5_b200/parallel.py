@@ -23,13 +23,32 @@ def aggregate_throughput(images_local: int, ms_local: float, device=None) -> flo
     return float(n.item() / (t.item() * 1e-3))
 
 
-def allreduce_flat_grads(flat_grad: torch.Tensor, group=None) -> int:
+def nccl_comm_ptr(group=None, device=None):
+    """the raw ncclComm_t of the process group's NCCL backend (what the C ABI's myolo_allreduce_grads takes), or None (gloo / no comm yet)"""
+    try:
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        be = pg._get_backend(device or torch.device("cuda", torch.cuda.current_device()))
+        ptr = int(be._comm_ptr())
+        return ptr or None
+    except Exception:
+        return None
+
+
+def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, stream=None) -> int:
     """ONE collective per optimiser step over the contiguous gradient buffer (31 MB fp32 for s/PSP): SUM over ranks, in place.
     Averaging (DDP semantics) is folded into the optimiser's unscale factor, 1 / (loss scale x world size), so no extra pass over the
-    buffer is needed.  Returns the world size used."""
+    buffer is needed.  On the NCCL backend the call goes through the library's own entry point (`myolo_allreduce_grads`: ncclAllReduce on
+    the communicator torch created, enqueued on `stream` or the current stream); gloo (CPU tests) uses torch.distributed.
+    Returns the world size used."""
     if not (dist.is_available() and dist.is_initialized()):
         return 1
     world = dist.get_world_size(group)
     if world > 1:
-        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        comm = nccl_comm_ptr(group, flat_grad.device) if flat_grad.is_cuda and dist.get_backend(group) == "nccl" else None
+        if comm is not None:
+            from . import _lib
+            sp = stream.cuda_stream if stream is not None else _lib.stream_ptr()
+            _lib.check(_lib.lib().myolo_allreduce_grads(_lib.ptr(flat_grad), flat_grad.numel(), comm, sp))
+        else:
+            dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     return world

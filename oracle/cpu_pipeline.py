@@ -62,3 +62,61 @@ class CpuPipeline:
                            for b in range(x.shape[0])])
         t3 = time.perf_counter()
         return dets, cls, dict(model=t1 - t0, nms=t2 - t1, segpost=t3 - t2)
+
+
+class ReferencePipeline:
+    """The UNMODIFIED reference tree (MYOLO_REFERENCE_ROOT, `baseline/_ref`, or /root/reference - whichever exists) imported through
+    oracle/ref_shims.py and driven exactly like detect.py:144-148,191-193.  The tree cannot travel to the GPU box (it is not an installable
+    package: `pip install /root/reference` fails with "Neither 'setup.py' nor 'pyproject.toml' found"), so this class is what
+    bench.py uses in the build container and CpuPipeline (the port) is what it uses where the tree is absent."""
+
+    def __init__(self, cfg, sd, threads=None):
+        import copy
+        from . import ref_shims
+        ref_yolo, ref_general = ref_shims.import_reference()
+        if threads:
+            torch.set_num_threads(threads)
+        self.threads = torch.get_num_threads()
+        torch.manual_seed(0)
+        self.model = ref_yolo.Model(copy.deepcopy(cfg))
+        self.model.load_state_dict(sd)
+        self.model.fuse().eval()
+        self.nms = ref_general.non_max_suppression
+
+    def __call__(self, x: torch.Tensor, conf=0.25, iou=0.45):
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            out = self.model(x)
+            t1 = time.perf_counter()
+            dets = self.nms(out[0][0], conf, iou)
+            t2 = time.perf_counter()
+            H, W = x.shape[2:]
+            seg = out[1]
+            cls = torch.stack([F.interpolate(seg[b:b + 1], (H, W), mode="bilinear", align_corners=True)[0].max(0)[1] for b in range(x.shape[0])])
+            t3 = time.perf_counter()
+        return dets, cls, dict(model=t1 - t0, nms=t2 - t1, segpost=t3 - t2)
+
+
+def reference_root():
+    """first existing location of the unmodified reference tree, or None"""
+    import os
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.environ.get("MYOLO_REFERENCE_ROOT"), os.path.join(here, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "models", "yolo.py")):
+            return cand
+    return None
+
+
+def make_cpu_pipeline(cfg, sd, threads=None):
+    """(pipeline, kind): the unmodified reference when its tree is present, the port otherwise"""
+    root = reference_root()
+    if root is not None:
+        import os
+        os.environ["MYOLO_REFERENCE_ROOT"] = root
+        from . import ref_shims
+        ref_shims.REF_ROOT = root
+        try:
+            return ReferencePipeline(cfg, sd, threads), "reference"
+        except Exception:       # an incomplete tree: fall back to the port rather than fail the bench
+            pass
+    return CpuPipeline(cfg, sd, threads), "port"

@@ -42,7 +42,10 @@ def q16(t: torch.Tensor) -> torch.Tensor:
 
 
 class Ctx:
-    def __init__(self, sd: Dict[str, torch.Tensor], quantised: bool = False, train: bool = False):
+    def __init__(self, sd: Dict[str, torch.Tensor], quantised: bool = False, train: bool = False, half: bool = False):
+        # half: the reference's CUDA configuration (detect.py:96-103,136): `model.fuse()` folds BN in fp32, `model.half()` rounds the
+        # folded weights / biases to fp16, activations are fp16 tensors end to end (torch fp16 kernels, cuDNN convolutions)
+        self.half = half
         self.train = train   # train mode: BatchNorm uses batch statistics (reference train.py runs model.train()); tensors keep autograd
         self.sd = sd if train else {k: v.detach().to(torch.float32) if v.is_floating_point() else v for k, v in sd.items()}
         self.quantised = quantised
@@ -80,6 +83,15 @@ def conv_bn_act(cx: Ctx, x, wkey: str, bnp: Optional[str], k: int, s: int = 1, d
         y = F.batch_norm(y, None, None, cx.sd[bnp + ".weight"], cx.sd[bnp + ".bias"], training=True, momentum=0.0, eps=BN_EPS)
         if act:
             y = y * torch.sigmoid(y)
+        return y if residual is None else residual + y
+    if getattr(cx, "half", False):
+        if bnp is not None:
+            scale, shift = _bn_affine(cx, bnp)
+            y = F.conv2d(x, (w * scale.view(-1, 1, 1, 1)).half(), shift.half(), s, pad, d)
+        else:
+            y = F.conv2d(x, w.half(), cx.sd[bias_key].half() if bias_key is not None else None, s, pad, d)
+        if act:
+            y = F.silu(y)
         return y if residual is None else residual + y
     if bnp is not None:
         scale, shift = _bn_affine(cx, bnp)
@@ -185,9 +197,9 @@ def FFM(cx, p, x, k):
     feat = Conv(cx, p + ".convblk", x, k)
     a = F.adaptive_avg_pool2d(feat, 1)
     wa, wb = cx.sd[p + ".channel_attention.1.weight"], cx.sd[p + ".channel_attention.3.weight"]
-    a = F.conv2d(a, wa)
+    a = F.conv2d(a, wa.to(a.dtype))
     a = a * torch.sigmoid(a)
-    a = torch.sigmoid(F.conv2d(a, wb))
+    a = torch.sigmoid(F.conv2d(a, wb.to(a.dtype)))
     return cx.q(feat * a + feat)
 
 
@@ -269,9 +281,9 @@ def Detect(cx, p, xs, nc, anchors_px: Sequence[Sequence[float]], strides: Sequen
         y = y.view(bs, na, no, ny, nx).permute(0, 1, 3, 4, 2).contiguous()
         raw.append(y)
         s = y.sigmoid()
-        yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing="ij")
-        grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()
-        ag = torch.tensor(anchors_px[i], dtype=torch.float32).view(1, na, 1, 1, 2)
+        yv, xv = torch.meshgrid([torch.arange(ny, device=y.device), torch.arange(nx, device=y.device)], indexing="ij")
+        grid = torch.stack((xv, yv), 2).view(1, 1, ny, nx, 2).float()          # `_make_grid` result: fp32 even under model.half()
+        ag = torch.tensor(anchors_px[i], dtype=torch.float32, device=y.device).view(1, na, 1, 1, 2).to(y.dtype)   # buffer: follows .half()
         s[..., 0:2] = (s[..., 0:2] * 2.0 - 0.5 + grid) * strides[i]
         s[..., 2:4] = (s[..., 2:4] * 2) ** 2 * ag
         z.append(s.view(bs, -1, no))
@@ -332,13 +344,17 @@ def parse_cfg(cfg: dict):
 
 
 def model_forward(cfg: dict, sd: Dict[str, torch.Tensor], x: torch.Tensor, quantised: bool = False,
-                  keep: Sequence[int] = ()):
+                  keep: Sequence[int] = (), half: bool = False):
     """`Model.forward_once` (reference models/yolo.py:293-316) in eval mode.
-    Returns dict(z, raw=[x0,x1,x2], seg, seg_lowres, layers={i: tensor})."""
-    cx = Ctx(sd, quantised)
+    Returns dict(z, raw=[x0,x1,x2], seg, seg_lowres, layers={i: tensor}).
+    half=True (CUDA tensors): the same graph the way the reference runs it on a GPU - BN folded in fp32, weights and activations fp16,
+    torch/cuDNN kernels (detect.py:96-103) - the precision yardstick of the GPU parity tests and the `reference-gpu` bench arm."""
+    cx = Ctx(sd, quantised, half=half)
     layers = parse_cfg(cfg)
     ys: List[Optional[torch.Tensor]] = []
-    x = x.to(torch.float32)
+    x = x.to(torch.float16 if half else torch.float32)
+    if half:
+        assert x.is_cuda and not quantised, "half=True is the torch fp16 CUDA yardstick (the reference's own GPU configuration)"
     det = seg = None
     strides = []
     with torch.no_grad():

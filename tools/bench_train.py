@@ -22,6 +22,119 @@ H, W = 512, 1024
 GFLOP_FWD_PER_IMG = 29.70          # SURVEY.md section 8d (Conv2d MACs x 2, s/PSP)
 
 
+def make_workload(world, rank, B):
+    """model, Trainer and NROT rotating synthetic batches of BASELINE.json configs[3]'s per-GPU slice"""
+    from multiyolov5_b200 import synth
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.train import Trainer, scale_hyp
+    yml, tag = "yolov5s_city_seg.yaml", "s_psp"
+    cfg = synth.load_cfg(yml)
+    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1, gain=1.0)
+    model = Model(yml)
+    model.load_state_dict(sd)
+    model.cuda().train()
+    hyp = dict(lr0=0.0015, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
+    hyp = scale_hyp(hyp, nl=3, nc=cfg["nc"], imgsz=W, total_batch_size=B * world)      # data/hyp.scratch.yaml values
+    tr = Trainer(model, hyp, batch_size=B, world_size=world, rank=rank if world > 1 else -1, init_scale=2.0 ** 10)
+    gen = torch.Generator(device="cuda").manual_seed(77 + rank)
+    NROT = 3
+    imgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+    segimgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+    rs = np.random.RandomState(5 + rank)
+    tg = []
+    for _ in range(NROT):
+        t = np.zeros((20 * B, 6), np.float32)
+        t[:, 0] = np.repeat(np.arange(B), 20)
+        t[:, 1] = rs.randint(0, 10, 20 * B)
+        t[:, 2:4] = rs.uniform(0.1, 0.9, (20 * B, 2))
+        t[:, 4:6] = rs.uniform(0.02, 0.22, (20 * B, 2))
+        tg.append(torch.from_numpy(t).cuda())
+    masks = [torch.randint(-1, 19, (B, H, W), device="cuda", generator=gen) for _ in range(NROT)]
+    return dict(yml=yml, cfg=cfg, sd=sd, hyp=hyp, model=model, tr=tr, imgs=imgs, segimgs=segimgs, tg=tg, masks=masks, NROT=NROT)
+
+
+def timed_steps(step, steps, world):
+    """EXACTLY `steps` calls bracketed by barrier + synchronize, CUDA events on the launching stream, max over ranks (ms)"""
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def train_record(world, rank, steps=10, warmup=3, B=4, min_seconds=1.0, with_reference_gpu=False):
+    """the `train` sub-record of bench.py's JSON line (BASELINE.json configs[3]): step time, whole-job images/s, the all-reduce's own time,
+    and a >= min_seconds sustained run next to the short one"""
+    wl = make_workload(world, rank, B)
+    tr, NROT = wl["tr"], wl["NROT"]
+
+    def step(i):
+        k = i % NROT
+        return tr.step(wl["imgs"][k], wl["tg"][k], wl["segimgs"][k], wl["masks"][k])
+
+    for i in range(max(warmup, 3)):
+        step(i)
+    ms = timed_steps(step, steps, world)
+    n_long = max(steps, int(min_seconds * 1e3 / (ms / steps)) + 1)
+    ms_long = timed_steps(step, n_long, world)
+    # the exchange on its own: the flat fp32 gradient buffer through ONE all-reduce (what every optimiser step contains)
+    ar_ms = 0.0
+    if world > 1:
+        def ar(i):
+            tr.allreduce()
+        ar(0)
+        ar_ms = timed_steps(ar, 20, world) / 20
+        tr.flat.grad.zero_()
+    flops = 3.0 * GFLOP_FWD_PER_IMG * 1e9 * 2 * B * world
+    rec = {"workload": f"{wl['yml']} train step (det fwd+bwd, seg fwd+bwd, ONE flat-gradient all-reduce, fused SGD; reference train.py:363-401), per GPU "
+                       f"{B} det + {B} seg images 3x{H}x{W}, 20 boxes/img, global batch {2 * B * world}",
+           "n_gpus": world, "steps": steps, "ms_per_step": ms / steps, "images_per_s": 2 * B * world * steps / (ms * 1e-3),
+           "sustained": {"steps": n_long, "seconds": ms_long * 1e-3, "ms_per_step": ms_long / n_long,
+                         "images_per_s": 2 * B * world * n_long / (ms_long * 1e-3)},
+           "allreduce_ms": ar_ms, "allreduce_mbytes": tr.flat.n * 4 / 1e6, "allreduce_share_of_step": ar_ms / (ms / steps) if world > 1 else 0.0,
+           "collective": "NCCL all-reduce (sum) of the flat fp32 gradient buffer, averaging folded into the optimiser" if world > 1 else "none (1 GPU)",
+           "conv_tflops_algorithmic": flops / (ms / steps * 1e-3) / 1e12, "dtype": "f16 storage / f32 accumulate, fp32 master weights",
+           "loss_scale": float(tr.scale)}
+    if with_reference_gpu and rank == 0:
+        rec["reference_gpu"] = reference_gpu_train(wl, B)
+    del wl, tr
+    torch.cuda.empty_cache()
+    return rec
+
+
+def reference_gpu_train(wl, B, steps=6):
+    """torch autocast + cuDNN step of the same graph on this GPU (reference train.py:363-401): the reference's own GPU path as a baseline"""
+    try:
+        from oracle.gpu_pipeline import TorchAutocastTrainStep
+        from multiyolov5_b200.models.yolo import Model
+        shell = Model(wl["yml"]).cuda()
+        ref = TorchAutocastTrainStep(wl["cfg"], wl["sd"], shell, wl["hyp"], B)
+        NROT = wl["NROT"]
+
+        def step(i):
+            k = i % NROT
+            ref.step(wl["imgs"][k], wl["tg"][k], wl["segimgs"][k], wl["masks"][k])
+        for i in range(3):
+            step(i)
+        ms = timed_steps(step, steps, 1)
+        return {"ms_per_step": ms / steps, "images_per_s": 2 * B * steps / (ms * 1e-3), "kind": "torch autocast(fp16) + cuDNN (cudnn.benchmark) + "
+                "GradScaler + torch SGD on the restated train graph, 1 GPU", "steps": steps}
+    except Exception as e:   # a baseline must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=10)
@@ -48,33 +161,9 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
-    from multiyolov5_b200 import synth
-    from multiyolov5_b200.models.yolo import Model
-    from multiyolov5_b200.train import Trainer, scale_hyp
-    yml, tag = "yolov5s_city_seg.yaml", "s_psp"
-    cfg = synth.load_cfg(yml)
-    sd = synth.synth_state_dict(synth.load_manifest(tag), cfg, seed=1, gain=1.0)
-    model = Model(yml)
-    model.load_state_dict(sd)
-    model.cuda().train()
+    wl = make_workload(world, rank, args.batch)
+    yml, model, tr, NROT, imgs, segimgs, tg, masks = wl["yml"], wl["model"], wl["tr"], wl["NROT"], wl["imgs"], wl["segimgs"], wl["tg"], wl["masks"]
     B = args.batch
-    hyp = dict(lr0=0.0015, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
-    hyp = scale_hyp(hyp, nl=3, nc=cfg["nc"], imgsz=W, total_batch_size=B * world)      # data/hyp.scratch.yaml values
-    tr = Trainer(model, hyp, batch_size=B, world_size=world, rank=rank if world > 1 else -1, init_scale=2.0 ** 10)
-    gen = torch.Generator(device="cuda").manual_seed(77 + rank)
-    NROT = 3
-    imgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
-    segimgs = [torch.rand((B, 3, H, W), device="cuda", generator=gen) for _ in range(NROT)]
-    rs = np.random.RandomState(5 + rank)
-    tg = []
-    for _ in range(NROT):
-        t = np.zeros((20 * B, 6), np.float32)
-        t[:, 0] = np.repeat(np.arange(B), 20)
-        t[:, 1] = rs.randint(0, 10, 20 * B)
-        t[:, 2:4] = rs.uniform(0.1, 0.9, (20 * B, 2))
-        t[:, 4:6] = rs.uniform(0.02, 0.22, (20 * B, 2))
-        tg.append(torch.from_numpy(t).cuda())
-    masks = [torch.randint(-1, 19, (B, H, W), device="cuda", generator=gen) for _ in range(NROT)]
 
     def step(i):
         k = i % NROT

@@ -1,5 +1,10 @@
 """Turns gpurun_out ncu artefacts into the small, committed summaries under profiles/.
-    python tools/summarize_profiles.py <tag> <launches.csv> [<full.ncu-rep>]
+    python tools/summarize_profiles.py <tag> <launches.csv> [<full.ncu-rep>]   # from the raw `ncu --csv --log-file` launch list
+    python tools/summarize_profiles.py regen <tag>                               # re-derive launches_<tag>.md and ncu_traffic.json from the
+                                                                                 # TRACKED compact per-launch table profiles/launches_<tag>.csv
+The launch list comes from (B200_PROFILING.md):
+    ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
+        --clock-control none -s <warm-up launches> -c <launches of one step> --csv --log-file gpurun_out/launches.csv python bench.py --no-extras ...
 """
 import collections
 import csv
@@ -24,6 +29,30 @@ def launches(path, out):
             d["rd"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1)
         elif r[mi].startswith("dram__bytes_write"):
             d["wr"] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[ui], 1)
+        elif r[mi].startswith("sm__pipe_tensor_cycles_active"):
+            d["tc"] = v
+    # the compact per-launch table is what gets committed: everything below can be regenerated from it (`regen`)
+    compact = out.replace(".md", ".csv")
+    with open(compact, "w") as f:
+        f.write("launch,kernel,duration_us,dram_read_bytes,dram_write_bytes,tensor_pipe_pct\n")
+        for n, d in enumerate(per.values()):
+            f.write(f"{n},{d['k'].replace(', ', ';').replace(',', ';')},{d.get('us', 0):.3f},{d.get('rd', -1):.0f},{d.get('wr', -1):.0f},{d.get('tc', -1):.2f}\n")
+    summarize(per, out, compact)
+
+
+def regen(tag):
+    per = collections.OrderedDict()
+    for r in csv.DictReader(open(f"profiles/launches_{tag}.csv")):
+        d = {"k": r["kernel"], "us": float(r["duration_us"])}
+        if float(r["dram_read_bytes"]) >= 0:
+            d["rd"], d["wr"] = float(r["dram_read_bytes"]), float(r["dram_write_bytes"])
+        if float(r["tensor_pipe_pct"]) >= 0:
+            d["tc"] = float(r["tensor_pipe_pct"])
+        per[r["launch"]] = d
+    summarize(per, f"profiles/launches_{tag}.md", f"profiles/launches_{tag}.csv")
+
+
+def summarize(per, out, path):
     agg, tot = collections.OrderedDict(), 0.0
     for d in per.values():
         a = agg.setdefault(d["k"], [0, 0.0, 0.0]); a[0] += 1; a[1] += d.get("us", 0.0); a[2] += d.get("rd", 0.0) + d.get("wr", 0.0)
@@ -34,8 +63,9 @@ def launches(path, out):
         f.write("| kernel | launches | total us | share |" + (" dram MB (rd+wr) |" if has_dram else "") + "\n|---|---:|---:|---:|" + ("---:|" if has_dram else "") + "\n")
         for k, (n, t, by) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write(f"| {k} | {n} | {t:.1f} | {100 * t / tot:.1f}% |" + (f" {by / 1e6:.1f} |" if has_dram else "") + "\n")
-        f.write("\nper-launch durations in stream order (us):\n\n")
-        f.write(" ".join(f"{d['k'][:12]}:{d.get('us', 0):.1f}" for d in per.values()) + "\n")
+        f.write("\nper-launch durations in stream order (us" + (", tensor-pipe % in brackets" if any("tc" in d for d in per.values()) else "") + "):\n\n")
+        f.write(" ".join(f"{d['k'][:12]}:{d.get('us', 0):.1f}" + (f"[{d['tc']:.0f}]" if d.get("tc", -1) >= 0 and d["k"].startswith("conv_tc") else "")
+                         for d in per.values()) + "\n")
     if has_dram:
         import json
         conv = [d for d in per.values() if d["k"].startswith("conv_tc")]
@@ -70,6 +100,9 @@ def full(rep, out):
 
 
 if __name__ == "__main__":
+    if sys.argv[1] == "regen":
+        regen(sys.argv[2])
+        sys.exit(0)
     tag = sys.argv[1]
     launches(sys.argv[2], f"profiles/launches_{tag}.md")
     if len(sys.argv) > 3:
