@@ -441,15 +441,34 @@ template <> struct Pack4<__half> {
 // every thread then produces 4 consecutive pixels for all classes with 2 shared loads + 1 lerp per value and 16-byte stores
 // (per class a warp writes 512 contiguous bytes).  (Vertical-then-horizontal association differs from ATen's
 // horizontal-then-vertical by <= 1 ulp; the bit-exact-vs-ATen path is myolo_seg_upsample_argmax / myolo_bilinear_nchw.)
-template <typename TOut>
+template <typename TOut> struct Pack8;       // 8 consecutive outputs with 16-byte stores
+template <> struct Pack8<float> {
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+};
+template <> struct Pack8<__half> {
+  static __device__ __forceinline__ void store(__half* p, const float* v) {
+    uint4 u;
+    __half2* h = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) h[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+
+// PPT consecutive pixels per thread (8 on the aligned fast path: one 16-byte store per class for fp16 logits, two for fp32; 4 otherwise);
+// AMAX compiles the running arg-max in only when a class map is requested.
+template <typename TOut, int PPT, bool AMAX>
 __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int ncls, int H, int W, TOut* seg, int64_t* amax) {
   extern __shared__ float sup_smem[];
-  const int segs = (W + 4 * blockDim.x - 1) / (4 * blockDim.x);
+  const int segs = (W + PPT * blockDim.x - 1) / (PPT * blockDim.x);
   const int sx = blockIdx.x % segs;
   const int y = (blockIdx.x / segs) % H;
   const int b = blockIdx.x / (segs * H);
-  const int xbeg = sx * 4 * blockDim.x;
-  const int xend = min(W, xbeg + 4 * (int)blockDim.x);
+  const int xbeg = sx * PPT * blockDim.x;
+  const int xend = min(W, xbeg + PPT * (int)blockDim.x);
   const Lerp ly = lerp_axis(y, in.H, H);
   const int c0 = lerp_axis(xbeg, in.W, W).i0;
   const int c1 = lerp_axis(xend - 1, in.W, W).i1;
@@ -469,47 +488,64 @@ __global__ void __launch_bounds__(256) seg_upsample_kernel(TensorView in, int nc
       if (c4 * 4 + k < ncls) d[(c4 * 4 + k) * pitch] = vv[k];
   }
   __syncthreads();
-  const int x0 = xbeg + 4 * threadIdx.x;
+  const int x0 = xbeg + PPT * threadIdx.x;
   if (x0 >= W) return;
-  int i0[4], i1[4];
-  float l0[4], l1[4];
+  int i0[PPT], i1[PPT];
+  float l0[PPT], l1[PPT];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < PPT; ++j) {
     const Lerp lx = lerp_axis(min(x0 + j, W - 1), in.W, W);
     i0[j] = lx.i0 - c0; i1[j] = lx.i1 - c0; l0[j] = lx.l0; l1[j] = lx.l1;
   }
-  float best[4] = {0.f, 0.f, 0.f, 0.f};
-  int bi[4] = {0, 0, 0, 0};
-  const bool full = (x0 + 3 < W) && (W % 4 == 0);
+  float best[PPT];
+  int bi[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) { best[j] = 0.f; bi[j] = 0; }
+  const bool full = (x0 + PPT - 1 < W) && (W % PPT == 0);
   for (int c = 0; c < ncls; ++c) {
     const float* r = sv + c * pitch;
-    float v[4];
+    float v[PPT];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PPT; ++j) {
       v[j] = fmaf(l1[j], r[i1[j]], l0[j] * r[i0[j]]);
-      if (c == 0 || v[j] > best[j]) { best[j] = v[j]; bi[j] = c; }
+      if (AMAX && (c == 0 || v[j] > best[j])) { best[j] = v[j]; bi[j] = c; }
     }
     if (seg) {
       TOut* o = seg + (((size_t)b * ncls + c) * H + y) * W + x0;
-      if (full) Pack4<TOut>::store(o, v[0], v[1], v[2], v[3]);
-      else
-        for (int j = 0; j < 4 && x0 + j < W; ++j) o[j] = (TOut)v[j];
+      if (full) {
+        if (PPT == 8) Pack8<TOut>::store(o, v);
+        else Pack4<TOut>::store(o, v[0], v[1], v[2], v[3]);
+      } else {
+        for (int j = 0; j < PPT && x0 + j < W; ++j) o[j] = (TOut)v[j];
+      }
     }
   }
-  if (amax) {
+  if (AMAX) {
     int64_t* o = amax + ((size_t)b * H + y) * W + x0;
-    for (int j = 0; j < 4 && x0 + j < W; ++j) o[j] = bi[j];
+    for (int j = 0; j < PPT && x0 + j < W; ++j) o[j] = bi[j];
+  }
+}
+template <typename TOut>
+static void launch_seg_upsample_t(const TensorView& in, int n_cls, int H, int W, TOut* seg, int64_t* argmax, size_t smem, cudaStream_t s) {
+  const bool wide = (W % 8 == 0) && W >= 256 && (reinterpret_cast<uintptr_t>(seg) & 15) == 0;
+  if (wide) {
+    const int threads = W >= 1024 ? 128 : (W >= 512 ? 64 : 32);
+    const long blocks = (long)in.B * H * ceil_div(W, 8 * threads);
+    if (argmax) seg_upsample_kernel<TOut, 8, true><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, seg, argmax);
+    else seg_upsample_kernel<TOut, 8, false><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, seg, argmax);
+  } else {
+    const int threads = W >= 1024 ? 256 : (W >= 512 ? 128 : 64);
+    const long blocks = (long)in.B * H * ceil_div(W, 4 * threads);
+    if (argmax) seg_upsample_kernel<TOut, 4, true><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, seg, argmax);
+    else seg_upsample_kernel<TOut, 4, false><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, seg, argmax);
   }
 }
 int launch_seg_upsample(const TensorView& in, int n_cls, int H, int W, void* seg, int seg_dtype, int64_t* argmax, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.ctot % 4 == 0 && in.ctot >= ((n_cls + 3) / 4) * 4, "seg_upsample: bad view");
-  const int threads = W >= 1024 ? 256 : (W >= 512 ? 128 : 64);
-  const int segs = ceil_div(W, 4 * threads);
   const size_t smem = (size_t)n_cls * ((in.W + 2) | 1) * 4;
   MYOLO_REQUIRE(smem <= 48 * 1024, "seg_upsample: source row too wide for the shared-memory kernel (%d cols x %d classes)", in.W, n_cls);
-  const long blocks = (long)in.B * H * segs;
-  if (seg_dtype == MYOLO_F16) seg_upsample_kernel<__half><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, (__half*)seg, argmax);
-  else seg_upsample_kernel<float><<<(unsigned)blocks, threads, smem, s>>>(in, n_cls, H, W, (float*)seg, argmax);
+  if (seg_dtype == MYOLO_F16) launch_seg_upsample_t<__half>(in, n_cls, H, W, (__half*)seg, argmax, smem, s);
+  else launch_seg_upsample_t<float>(in, n_cls, H, W, (float*)seg, argmax, smem, s);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -561,6 +597,57 @@ __global__ void argmax_nchw_f32x4_kernel(const float* __restrict__ src, int B, i
 }
 
 // fp16 logits (the reference's CUDA path runs model.half(), detect.py:96-103): 8 pixels per thread, one 16-byte load per class plane
+// 16 pixels per thread: two independent 16-byte loads per class plane keep twice the bytes in flight (the 8-pixel version reached half the
+// HBM rate of the fp32 kernel, which moves twice the bytes per thread)
+template <typename TOut>
+__global__ void argmax_nchw_f16x16_kernel(const __half* __restrict__ src, int B, int C, long HW, TOut* out) {
+  const long n16 = (long)B * HW / 16;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) {
+    const long pix = i * 16;
+    const long b = pix / HW, off = pix - b * HW;
+    const __half* p = src + b * C * HW + off;
+    __half2 best[8];
+    unsigned char bi[16];
+    {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p)), v1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&v0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { best[k] = h0[k]; best[4 + k] = h1[k]; }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) bi[k] = 0;
+    }
+#pragma unroll 3
+    for (int c = 1; c < C; ++c) {
+      const uint4 v0 = __ldg(reinterpret_cast<const uint4*>(p + (size_t)c * HW)), v1 = __ldg(reinterpret_cast<const uint4*>(p + (size_t)c * HW) + 1);
+      const __half2* h0 = reinterpret_cast<const __half2*>(&v0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const __half2 h = k < 4 ? h0[k] : h1[k - 4];
+        // strict '>' per lane on the fp16 values themselves (exact: no conversion needed); first maximum wins like torch.max
+        const __half2 gt = __hgt2(h, best[k]);
+        if (__low2float(gt) != 0.f) { best[k] = __halves2half2(__low2half(h), __high2half(best[k])); bi[2 * k] = (unsigned char)c; }
+        if (__high2float(gt) != 0.f) { best[k] = __halves2half2(__low2half(best[k]), __high2half(h)); bi[2 * k + 1] = (unsigned char)c; }
+      }
+    }
+    if (sizeof(TOut) == 1) {
+      uint4 o;
+      unsigned char* ob = reinterpret_cast<unsigned char*>(&o);
+#pragma unroll
+      for (int k = 0; k < 16; ++k) ob[k] = bi[k];
+      *reinterpret_cast<uint4*>(out + pix) = o;
+    } else if (sizeof(TOut) == 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        reinterpret_cast<ulonglong2*>(out + pix)[k] = make_ulonglong2((unsigned long long)bi[2 * k], (unsigned long long)bi[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) out[pix + k] = (TOut)bi[k];
+    }
+  }
+}
+
 template <typename TOut>
 __global__ void argmax_nchw_f16x8_kernel(const __half* __restrict__ src, int B, int C, long HW, TOut* out) {
   const long n8 = (long)B * HW / 8;
@@ -634,6 +721,14 @@ extern "C" int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, i
     const int g4 = grid_for((long)B * H * W / 4, 256, 148 * 32);
     if (out_dtype == MYOLO_I64) argmax_nchw_f32x4_kernel<int64_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (int64_t*)out);
     else argmax_nchw_f32x4_kernel<uint8_t><<<g4, 256, 0, s>>>((const float*)logits, B, C, (long)H * W, (uint8_t*)out);
+    MYOLO_LAUNCH_CHECK();
+    return 0;
+  }
+  if (dtype == MYOLO_F16 && H == h && W == w && ((long)H * W) % 16 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0 && C <= 255) {
+    const int g16 = grid_for((long)B * H * W / 16, 256, 148 * 32);
+    if (out_dtype == MYOLO_I64) argmax_nchw_f16x16_kernel<int64_t><<<g16, 256, 0, s>>>((const __half*)logits, B, C, (long)H * W, (int64_t*)out);
+    else argmax_nchw_f16x16_kernel<uint8_t><<<g16, 256, 0, s>>>((const __half*)logits, B, C, (long)H * W, (uint8_t*)out);
     MYOLO_LAUNCH_CHECK();
     return 0;
   }

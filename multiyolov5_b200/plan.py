@@ -122,7 +122,7 @@ class PlanBuilder:
     def __init__(self, B: int, H: int, W: int, train: bool = False):
         self.B, self.H, self.W = B, H, W
         self.train = train                      # train mode: raw conv -> batch-stat BN + act ops, nothing in place, no aliasing
-        self.fuse_c3 = os.environ.get("MYOLO_FUSE_C3") == "1"
+        self.fuse_c3 = os.environ.get("MYOLO_FUSE_C3", "0") == "1"
         self.bn_slots: List[nn.BatchNorm2d] = []
         self.bufs: List[Buf] = []
         self.ops: List[OpRec] = []

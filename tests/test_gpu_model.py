@@ -162,6 +162,26 @@ def test_simt_and_tensor_core_paths_agree(monkeypatch):
     assert relmax(raw[0].cpu().numpy(), raw2[0].cpu().numpy()) < 4e-3
 
 
+@pytest.mark.parametrize("tag", ["s_psp", "m_lab"])
+def test_c3_cv1_cv2_fusion_matches_separate_launches(tag, monkeypatch):
+    """planner option MYOLO_FUSE_C3: the two 1x1 convs of a C3 that read the same input run as ONE conv with concatenated output channels
+    (reference models/common.py:138-139 computes them separately).  Same K loop per output channel -> same values."""
+    hw = (256, 512)
+    monkeypatch.setenv("MYOLO_FUSE_C3", "0")
+    model, cfg, sd = build(tag)
+    x = synth.synth_image(2, hw[0], hw[1], seed=11).cuda()
+    (z, raw), seg = model(x)
+    n0 = len(model.engine().last_plan.pb.ops)
+    monkeypatch.setenv("MYOLO_FUSE_C3", "1")
+    model2, _, _ = build(tag)
+    (z2, raw2), seg2 = model2(x)
+    torch.cuda.synchronize()
+    n1 = len(model2.engine().last_plan.pb.ops)
+    assert n1 < n0, (n0, n1)
+    assert relmax(seg2.cpu().numpy(), seg.cpu().numpy()) < 1e-5 and relmax(z2.cpu().numpy(), z.cpu().numpy()) < 1e-5
+    assert relmax(raw2[2].cpu().numpy(), raw[2].cpu().numpy()) < 1e-5
+
+
 def test_no_cpu_path():
     from multiyolov5_b200 import _lib
     model, _, _ = build("s_psp")

@@ -353,3 +353,42 @@ def test_trainer_bise_head_three_outputs():
     assert np.isfinite([float(h[1]) for h in hist]).all() and last < 0.85 * first, (first, last)
     named = dict(model.named_parameters())
     assert float(named["model.24.aux16.1.weight"].abs().sum()) > 0
+
+
+def test_backward_of_a_stale_forward_is_refused():
+    """one plan = one activation workspace per (B,H,W): forward, forward, backward would silently use the second forward's activations for
+    the first output's gradients.  The engine counts train forwards per plan and refuses the stale backward (reference order is forward,
+    backward, forward, backward - train.py:364-392)."""
+    from multiyolov5_b200 import _lib
+    model, cfg, sd, x = setup(B=2, H=64, W=128)
+    xa, xb = x.cuda(), (x * 0.5).cuda()
+    p1 = model(xa)
+    p2 = model(xb)
+    with pytest.raises(_lib.MyoloError, match="stale"):
+        (p1[1].float().sum() + p2[1].float().sum()).backward()
+    p3 = model(xa)                      # the regular order still works afterwards
+    p3[1].float().sum().backward()
+    torch.cuda.synchronize()
+    g = model.model[0].conv.conv.weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().sum()) > 0
+
+
+def test_eval_after_train_forward_uses_updated_running_statistics():
+    """a train-mode forward moves running_mean / running_var through raw pointers: the inference plans' BN-folded weights must be re-packed"""
+    model, cfg, sd, x = setup(B=2, H=64, W=128)
+    xc = x.cuda()
+    model.eval()
+    (z0, _), _ = model(xc)
+    model.train()
+    model(xc)
+    model.eval()
+    (z1, _), _ = model(xc)
+    torch.cuda.synchronize()
+    sd1 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    fresh, _, _, _ = setup(B=2, H=64, W=128)
+    fresh.load_state_dict(sd1)
+    fresh.cuda().eval()
+    (z2, _), _ = fresh(xc)
+    torch.cuda.synchronize()
+    assert not torch.equal(z0, z1)                                  # statistics moved ...
+    assert torch.equal(z1, z2)                                      # ... and the cached inference plan saw them

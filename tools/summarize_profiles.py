@@ -99,7 +99,27 @@ def full(rep, out):
                 pass
 
 
+def last_step(tag, path, n):
+    """keep only the last n launches of a raw ncu launch list (= one step of tools/one_step.py) and summarise them"""
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = [i for i, r in enumerate(rows) if r[0] == "ID"][0]
+    H, data = rows[hdr], rows[hdr + 1:]
+    ids = sorted({int(r[0]) for r in data})
+    keep = set(ids[-n:])
+    tmp = path + ".laststep.csv"
+    with open(tmp, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(H)
+        for r in data:
+            if int(r[0]) in keep:
+                w.writerow(r)
+    launches(tmp, f"profiles/launches_{tag}.md")
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "last-step":
+        last_step(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+        sys.exit(0)
     if sys.argv[1] == "regen":
         regen(sys.argv[2])
         sys.exit(0)
