@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(256) chan_reduce_v_kernel(TensorView a, Tensor
         bn.running_var[c] = (1.f - bn.momentum) * bn.running_var[c] + bn.momentum * var * (n / fmaxf(n - 1.f, 1.f));
       }
     } else {
-      if (bn.d_beta) bn.d_beta[c] += x0;
-      if (bn.d_gamma) bn.d_gamma[c] += x1;
+      // parameter gradients are accumulated atomically everywhere: the det and the seg backward of one training step may run concurrently
+      if (bn.d_beta) atomicAdd(bn.d_beta + c, x0);
+      if (bn.d_gamma) atomicAdd(bn.d_gamma + c, x1);
     }
   }
 }
@@ -274,8 +275,8 @@ __global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, Te
 __global__ void bn_param_grad_kernel(const float* sums, BnParams bn) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= bn.C) return;
-  if (bn.d_beta) bn.d_beta[c] += sums[c];
-  if (bn.d_gamma) bn.d_gamma[c] += sums[bn.C + c];
+  if (bn.d_beta) atomicAdd(bn.d_beta + c, sums[c]);
+  if (bn.d_gamma) atomicAdd(bn.d_gamma + c, sums[bn.C + c]);
 }
 __global__ void add_acc_kernel(TensorView dst, TensorView src) {   // dst += src (fp16 NHWC)
   const long total = (long)dst.B * dst.H * dst.W * (dst.C / 8);
@@ -1093,7 +1094,7 @@ __global__ void conv_small_wgrad_kernel(TensorView x, TensorView dy, float* dW, 
           acc += ldv(dy, b, oy, ox, o) * ldv(x, b, iy, ix, c);
         }
       }
-    dW[i] += acc;
+    atomicAdd(dW + i, acc);
   }
 }
 int launch_conv_small_bwd(const TensorView& x, const TensorView& dy, const TensorView* dx, const float* w, float* dW, float* dbias, int co,

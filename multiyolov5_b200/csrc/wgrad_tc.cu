@@ -183,7 +183,7 @@ __global__ void wgrad_unpack_kernel(float* __restrict__ packed, float* __restric
     const int o = (int)(i / ((long)ci_pad * taps));
     const float v = packed[i];
     packed[i] = 0.f;
-    if (c < ci) dW[((size_t)o * ci + c) * taps + t] += v;
+    if (c < ci && v != 0.f) atomicAdd(dW + ((size_t)o * ci + c) * taps + t, v);   // both passes of a step may unpack concurrently
   }
 }
 

@@ -122,8 +122,10 @@ class Engine:
         return out
 
     # ---- training -----------------------------------------------------------------------
-    def train_plan_for(self, B, H, W) -> CompiledPlan:
-        key = ("train", B, H, W)
+    def train_plan_for(self, B, H, W, lane=0) -> CompiledPlan:
+        """lane: independent train plans of the same shape (own activation / gradient workspaces) so that the two passes of a training step
+        can be in flight at the same time (train.Trainer overlap_passes)"""
+        key = ("train", B, H, W) if lane == 0 else ("train", B, H, W, lane)
         if key not in self.plans:
             self.plans[key] = CompiledPlan(self.model, B, H, W, train=True)
         return self.plans[key]
@@ -155,14 +157,9 @@ class Engine:
             self._grad_views.append(v)
         return self._flat_grad
 
-    def train_forward(self, x: torch.Tensor, out_raws=None, want_seg=True):
-        """out_raws: optional list of three preallocated (B,na,ny,nx,no) fp32 tensors to write the head outputs into (static buffers of a
-        captured loss graph); want_seg=False skips the full-resolution logits (the det pass never reads them)."""
-        assert x.is_cuda and x.dim() == 4, "expected a CUDA (B,3,H,W) tensor"
-        x = x.contiguous()
-        B, _, H, W = x.shape
-        p = self.train_plan_for(B, H, W)
-        self.ensure_flat_grads()
+    def prepare_train_plan(self, p):
+        """seed, fp16 weight packs and parameter / gradient pointers of a train plan for the current parameter values (idempotent; the
+        Trainer calls it ahead of time on the side stream for the seg pass)"""
         L = _lib.lib()
         sp = _lib.stream_ptr()
         params = self._train_params
@@ -172,13 +169,17 @@ class Engine:
         # re-pack the fp16 weights only when the parameters changed (in-place torch updates bump _version; Trainer's fused optimiser
         # writes through raw pointers and sets weights_dirty)
         ver = sum(q._version for q in params)
-        if self.weights_dirty or getattr(p, "_w_version", None) != ver:
+        if self.weights_dirty:
+            self._dirty_epoch = getattr(self, "_dirty_epoch", 0) + 1      # the fused optimiser wrote through raw pointers
+            self.weights_dirty = False
             for q in self.plans.values():        # every plan (inference ones too) holds packed copies of the old values
                 q.weights_uploaded = False
-            self.weights_dirty = False
+        sig_w = (ver, getattr(self, "_dirty_epoch", 0))
+        if getattr(p, "_w_version", None) != sig_w:
+            p.weights_uploaded = False
         if not p.weights_uploaded:
             p.upload_weights()                   # fp16, K-major, no BN folding
-            p._w_version = ver
+            p._w_version = sig_w
         sig = (self._flat_grad.data_ptr(), params[0].data_ptr(), params[-1].data_ptr(), len(params))
         if getattr(p, "_ptr_sig", None) != sig:  # (re)register parameter / gradient pointers only when they moved
             for i, s in enumerate(p.pb.slots):
@@ -188,6 +189,18 @@ class Engine:
                                                _lib.ptr(bn.running_var), _lib.ptr(bn.weight.grad), _lib.ptr(bn.bias.grad), float(bn.momentum), float(bn.eps)))
             p._ptr_sig = sig
             p._nbt = [bn.num_batches_tracked for bn in p.pb.bn_slots]
+
+    def train_forward(self, x: torch.Tensor, out_raws=None, want_seg=True, lane=0):
+        """out_raws: optional list of three preallocated (B,na,ny,nx,no) fp32 tensors to write the head outputs into (static buffers of a
+        captured loss graph); want_seg=False skips the full-resolution logits (the det pass never reads them)."""
+        assert x.is_cuda and x.dim() == 4, "expected a CUDA (B,3,H,W) tensor"
+        x = x.contiguous()
+        B, _, H, W = x.shape
+        p = self.train_plan_for(B, H, W, lane)
+        self.ensure_flat_grads()
+        self.prepare_train_plan(p)
+        L = _lib.lib()
+        sp = _lib.stream_ptr()
         torch._foreach_add_(p._nbt, 1)
         det, seg_head = self.model.model[-1], self.model.model[-2]
         dec = [o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]

@@ -84,7 +84,7 @@ class Trainer:
     """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
 
     def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
-                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True):
+                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True, overlap_passes=True):
         assert next(model.parameters()).is_cuda, "model.cuda() first"
         self.model, self.hyp, self.batch_size = model, hyp, batch_size
         self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
@@ -109,6 +109,13 @@ class Trainer:
         self.graph_loss = graph_loss        # replay the detection loss (forward + autograd backward, ~700 tiny kernels) as ONE CUDA graph
         self._det_graphs = {}
         self.fused_seg_loss = fused_seg_loss  # CE + x8 upsample forward/backward in one kernel, no full-resolution logits (plain heads only)
+        # overlap_passes: the seg pass runs on its own train plan and stream.  Its forward starts when the det FORWARD has finished (BatchNorm
+        # running statistics are then updated in the reference's order, det batch first: train.py:364,381), so the seg forward/backward
+        # overlaps the det loss + backward; parameter gradients of both passes add up atomically in the one flat buffer.  At 4 images per
+        # pass the kernels are launch/latency bound and each pass alone leaves most of the 148 SMs idle.
+        self.overlap_passes = bool(overlap_passes) and graph_loss
+        self._s_seg = torch.cuda.Stream() if self.overlap_passes else None
+        self._ev_detfwd, self._ev_start, self._ev_seg = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def set_lr(self, lr_bn, lr_weight, lr_bias):
         self.lr = [float(lr_bn), float(lr_weight), float(lr_bias)]
@@ -175,15 +182,16 @@ class Trainer:
         if nt:
             st.t[:nt].copy_(targets)
         _, _, plan = eng.train_forward(imgs, out_raws=st.p, want_seg=False)       # head outputs land in the graph's static inputs
+        self._ev_detfwd.record(torch.cuda.current_stream())
         st.graph.replay()
         eng.train_backward(plan, [q.grad for q in st.p], None)
         return st.items.clone()                                                   # the static tensor is overwritten by the next replay
 
-    def backward_seg(self, segimgs, segtargets):
+    def backward_seg(self, segimgs, segtargets, lane=0):
         # the fused kernels are instantiated for 19 (Cityscapes) and 32 classes; any other n_segcls takes the autograd path below
         if self.fused_seg_loss and self.n_seg_outputs == 1 and self.model.model[-2].c_out in (19, 32):
             eng = self.model.engine()
-            _, _, plan = eng.train_forward(segimgs, want_seg=False)
+            _, _, plan = eng.train_forward(segimgs, want_seg=False, lane=lane)
             loss = eng.train_backward_seg_ce(plan, segtargets, factor=self.batch_size * self.seggain, scale=self.scale)
             return loss * (self.batch_size * self.seggain)
         pred = self.model(segimgs)
@@ -219,8 +227,28 @@ class Trainer:
 
     def step(self, imgs, targets, segimgs, segtargets):
         """one iteration (train.py:363-401).  Returns (det loss items [lbox,lobj,lcls,loss], seg loss) as device tensors."""
-        items = self.backward_det(imgs, targets)
-        segloss = self.backward_seg(segimgs, segtargets)
+        fused_seg = self.fused_seg_loss and self.n_seg_outputs == 1 and self.model.model[-2].c_out in (19, 32)
+        if self.overlap_passes and fused_seg:
+            main = torch.cuda.current_stream()
+            self._ev_start.record(main)
+            # the seg plan's weight packing does not depend on the det pass: it runs ahead on the side stream ...
+            with torch.cuda.stream(self._s_seg):
+                self._s_seg.wait_event(self._ev_start)
+                eng = self.model.engine()
+                B, _, H, W = segimgs.shape
+                eng.ensure_flat_grads()
+                plan = eng.train_plan_for(B, H, W, lane=1)
+                eng.prepare_train_plan(plan)
+            items = self.backward_det(imgs, targets)                 # records _ev_detfwd right after the det forward
+            with torch.cuda.stream(self._s_seg):
+                self._s_seg.wait_event(self._ev_detfwd)              # ... its forward after the det forward (running statistics order)
+                segloss = self.backward_seg(segimgs, segtargets, lane=1)
+                self._ev_seg.record(self._s_seg)
+            main.wait_event(self._ev_seg)
+            segimgs.record_stream(self._s_seg); segtargets.record_stream(self._s_seg)
+        else:
+            items = self.backward_det(imgs, targets)
+            segloss = self.backward_seg(segimgs, segtargets)
         self.ni += 1
         if self.ni % self.accumulate == 0:
             self.optimizer_step()
