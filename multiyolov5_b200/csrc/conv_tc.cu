@@ -94,6 +94,19 @@ __device__ __forceinline__ TileCoord decode_vround(const ConvTcParams& p, int ro
   return t;
 }
 
+// the kc/16 MMAs of one K chunk (16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) descriptor field), fully unrolled
+// for every chunk width so that the issuing lane runs straight-line code.  `acc0`: accumulate flag of the first MMA (the rest accumulate).
+template <int KM>
+__device__ __forceinline__ void mma_chunk_k(uint32_t tmem_d, uint32_t la, uint32_t lb, uint32_t dhi, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int k = 0; k < KM; ++k) umma_f16_ss(tmem_d, desc_join(la + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, k == 0 ? acc0 : 1u);
+}
+__device__ __forceinline__ void mma_chunk(int kmma, uint32_t tmem_d, uint32_t la, uint32_t lb, uint32_t dhi, uint32_t idesc, uint32_t acc0) {
+  if (kmma == 4) mma_chunk_k<4>(tmem_d, la, lb, dhi, idesc, acc0);
+  else if (kmma == 2) mma_chunk_k<2>(tmem_d, la, lb, dhi, idesc, acc0);
+  else mma_chunk_k<1>(tmem_d, la, lb, dhi, idesc, acc0);
+}
+
 __device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -224,9 +237,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int row_bytes = p.kc * 2;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
 
-  if (warp == 0 && lane == 0) {
+  // Producer and MMA roles run WARP-CONVERGED: every lane executes the (warp-uniform) address / descriptor arithmetic so that ptxas keeps it
+  // in uniform registers, and only the issuing instructions are predicated on one elected lane.  (Run inside an `if (lane == 0)` branch the
+  // same code needs ~7 R2UR moves per tcgen05.mma / TMA instruction: ~125 clk per MMA where an N = 64 MMA occupies the tensor pipe for 32.)
+  if (warp == 0) {
     // ===================== TMA producer =====================
-    if (p.ws_mode) {
+    const bool leader = elect_one();
+    if (p.ws_mode && leader) {
       // weights are constants (never written by a predecessor kernel): fetch the resident weight tile before the dependency wait
       mbar_arrive_expect_tx(bres_bar, p.n_chunks * b_sub_bytes);
       for (int q = 0; q < p.n_chunks; ++q) tma_load_2d(smem_b + q * b_sub_bytes, &tmB, bres_bar, q * p.kc, 0);
@@ -242,15 +259,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // G vertically adjacent full-row tiles: rows y0 .. y0+n_valid-1 need input rows y0-1 .. y0+n_valid -> n_valid+2 strips
         const TileCoord t = decode_vround(p, round, 0);
         const int n_valid = min(p.G, p.Ho - t.y0);
-        DBG_STAMP(0);
+        if (leader) DBG_STAMP(0);
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int s = 0; s < n_valid + 2; ++s) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2) * row_bytes);
-            tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - 1, t.y0 - 1 + s, t.b);
+            __syncwarp();
+            if (leader) {
+              mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2) * row_bytes);
+              tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - 1, t.y0 - 1 + s, t.b);
+            }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
-        DBG_STAMP(1);
+        if (leader) DBG_STAMP(1);
         it += n_valid;
         continue;
       }
@@ -258,17 +278,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int tile = round * p.G + g;
         if (tile >= p.total_tiles) break;
         const TileCoord t = decode_tile(p, tile, tiles_per_img);
-        DBG_STAMP(0);
+        if (leader) DBG_STAMP(0);
         if (MODE == 1) {
           for (int ky = 0; ky < 3; ++ky)
             for (int cb = 0; cb < p.cblocks; ++cb) {
               mbar_wait(&empty_bar[stage], phase ^ 1);
-              mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2 * p.dil) * row_bytes + (p.ws_mode ? 0 : 3 * b_sub_bytes));
-              tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - p.dil, t.y0 + (ky - 1) * p.dil, t.b);
-              if (!p.ws_mode)
-                for (int kx = 0; kx < 3; ++kx)
-                  tma_load_2d(smem_b + stage * p.b_stage_bytes + kx * b_sub_bytes, &tmB, &full_bar[stage],
-                              ((ky * 3 + kx) * p.cblocks + cb) * p.kc, t.n0);
+              __syncwarp();
+              if (leader) {
+                mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2 * p.dil) * row_bytes + (p.ws_mode ? 0 : 3 * b_sub_bytes));
+                tma_load_4d(smem_a + stage * p.a_stage_bytes, &tmA0, &full_bar[stage], cb * p.kc, t.x0 - p.dil, t.y0 + (ky - 1) * p.dil, t.b);
+                if (!p.ws_mode)
+                  for (int kx = 0; kx < 3; ++kx)
+                    tma_load_2d(smem_b + stage * p.b_stage_bytes + kx * b_sub_bytes, &tmB, &full_bar[stage],
+                                ((ky * 3 + kx) * p.cblocks + cb) * p.kc, t.n0);
+              }
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
         } else {
@@ -276,26 +299,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
           for (int ks = 0; ks < p.n_kstages; ++ks) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
+            __syncwarp();
             const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-            mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
             uint8_t* sa = smem_a + stage * p.a_stage_bytes;
             uint8_t* sb = smem_b + stage * p.b_stage_bytes;
             for (int j = 0; j < nch; ++j, ++q) {
               const int mi = p.tap_map[tap];
               const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
-              tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.b);
-              if (!p.ws_mode) tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t.n0);
+              if (leader) {
+                tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t.x0 + p.tap_dx[tap], t.y0 + p.tap_dy[tap], t.b);
+                if (!p.ws_mode) tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t.n0);
+              }
               if (++cb == p.cblocks) { cb = 0; ++tap; }
             }
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
         }
-        DBG_STAMP(1);
+        if (leader) DBG_STAMP(1);
         ++it;
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer (single thread) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one elected lane issues; the warp computes the descriptors) =====================
+    const bool leader = elect_one();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = (1u << 4)                       // D format: fp32
                            | (0u << 7) | (0u << 10)        // A, B format: fp16
@@ -309,22 +336,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int kmma = p.kc / 16;
     const uint32_t dhi = desc_hi(p.kc);
     const uint32_t lb_res = desc_lo(smem_u32(smem_b));
+    const uint32_t la_base = desc_lo(smem_u32(smem_a));
+    const uint32_t lb_base = desc_lo(smem_u32(smem_b));
+    const uint32_t a_stage16 = (uint32_t)(p.a_stage_bytes >> 4), b_stage16 = (uint32_t)(p.b_stage_bytes >> 4);
     const int bsub16 = b_sub_bytes >> 4, asub16 = a_sub_bytes >> 4, row16 = row_bytes >> 4;
-    if (p.ws_mode) mbar_wait(bres_bar, 0);
+    if (p.ws_mode) { mbar_wait(bres_bar, 0); __syncwarp(); }
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
-      DBG_STAMP(2);
+      if (leader) DBG_STAMP(2);
       mbar_wait(&tempty_bar[as], aphase ^ 1);
+      __syncwarp();
       tcgen05_fence_after();
-      DBG_STAMP(3);
+      if (leader) DBG_STAMP(3);
       if (MODE == 2) {
         const int r = round % p.rounds_per_img;
         const int n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int s = 0; s < n_valid + 2; ++s) {
             mbar_wait(&full_bar[stage], phase);
+            __syncwarp();
             tcgen05_fence_after();
-            const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
+            const uint32_t la = la_base + (uint32_t)stage * a_stage16;
             // strip s (input row y0-1+s) is filter row ky = s-g of output row g
             for (int g = max(0, s - 2); g <= min(n_valid - 1, s); ++g) {
               const int ky = s - g;
@@ -333,12 +365,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
               for (int kx = 0; kx < 3; ++kx) {
                 const uint32_t lak = la + kx * row16;
-                for (int k = 0; k < kmma; ++k)
-                  umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((cb | ky | kx | k) != 0));
+                if (leader) mma_chunk(kmma, tmem_d, lak, lb, dhi, idesc, (uint32_t)((cb | ky | kx) != 0));
                 lb += (uint32_t)(p.cblocks * bsub16);
               }
             }
-            umma_commit(&empty_bar[stage]);
+            if (leader) umma_commit(&empty_bar[stage]);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
       } else {
@@ -350,48 +381,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             for (int ky = 0; ky < 3; ++ky)
               for (int cb = 0; cb < p.cblocks; ++cb) {
                 mbar_wait(&full_bar[stage], phase);
+                __syncwarp();
                 tcgen05_fence_after();
-                const uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
-                uint32_t lb = p.ws_mode ? lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16)
-                                        : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
+                const uint32_t la = la_base + (uint32_t)stage * a_stage16;
+                uint32_t lb = p.ws_mode ? lb_res + (uint32_t)((ky * 3 * p.cblocks + cb) * bsub16) : lb_base + (uint32_t)stage * b_stage16;
                 const uint32_t lb_step = p.ws_mode ? (uint32_t)(p.cblocks * bsub16) : (uint32_t)bsub16;
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
                   const uint32_t lak = la + kx * p.dil * row16;          // same strip, shifted by kx*dil pixels
-                  for (int k = 0; k < kmma; ++k) {
-                    umma_f16_ss(tmem_d, desc_join(lak + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, first);
-                    first = 1;
-                  }
+                  if (leader) mma_chunk(kmma, tmem_d, lak, lb, dhi, idesc, first);
+                  first = 1;
                   lb += lb_step;
                 }
-                umma_commit(&empty_bar[stage]);
+                if (leader) umma_commit(&empty_bar[stage]);
                 if (++stage == S) { stage = 0; phase ^= 1; }
               }
           } else {
             int q = 0;
             for (int ks = 0; ks < p.n_kstages; ++ks) {
               mbar_wait(&full_bar[stage], phase);
+              __syncwarp();
               tcgen05_fence_after();
-              if (ks == 0) DBG_STAMP(4);
+              if (ks == 0 && leader) DBG_STAMP(4);
               const int nch = min(p.chunks_per_stage, p.n_chunks - q);
-              uint32_t la = desc_lo(smem_u32(smem_a + stage * p.a_stage_bytes));
-              uint32_t lb = p.ws_mode ? lb_res + (uint32_t)(q * bsub16) : desc_lo(smem_u32(smem_b + stage * p.b_stage_bytes));
+              uint32_t la = la_base + (uint32_t)stage * a_stage16;
+              uint32_t lb = p.ws_mode ? lb_res + (uint32_t)(q * bsub16) : lb_base + (uint32_t)stage * b_stage16;
               for (int j = 0; j < nch; ++j, ++q) {
-                for (int k = 0; k < kmma; ++k) {
-                  // advance 16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr>>4) field
-                  umma_f16_ss(tmem_d, desc_join(la + 2 * k, dhi), desc_join(lb + 2 * k, dhi), idesc, (uint32_t)((ks | j | k) != 0));
-                }
+                if (leader) mma_chunk(kmma, tmem_d, la, lb, dhi, idesc, (uint32_t)((ks | j) != 0));
                 la += asub16;
                 lb += bsub16;
               }
-              umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+              if (leader) umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
               if (++stage == S) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
-      umma_commit(&tfull_bar[as]);       // all accumulators of the round complete -> epilogue
-      DBG_STAMP(5);
+      if (leader) umma_commit(&tfull_bar[as]);       // all accumulators of the round complete -> epilogue
+      if (leader) DBG_STAMP(5);
       if (++as == 2) { as = 0; aphase ^= 1; }
       ++it;
     }
@@ -811,6 +838,12 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   } else {
     op.tmO = op.tmB;
   }
+  static int null_env = -1;
+  if (null_env < 0) {
+    const char* e = getenv("MYOLO_CONV_NULL");       // measurement aid: every conv launch runs prologue + teardown only (launch floor)
+    null_env = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (null_env) { p.total_rounds = 0; p.ws_mode = 0; }
   static bool attr_set = false;
   if (!attr_set) {
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -9,6 +9,7 @@
 //          loop stops as soon as 300 boxes are kept: exactly `i[:max_det]` of the reference) with a 256x256 bit matrix
 //          for the intra-chunk dependencies.  Every IoU operation is an explicit round-to-nearest fp32 op in the order
 //          of the torchvision CPU kernel, so kept indices are bit-exact with the reference.
+#include <nvtx3/nvToolsExt.h>
 #include "common.cuh"
 
 namespace myolo {
@@ -260,6 +261,8 @@ extern "C" int64_t myolo_nms_workspace_bytes(int B, int A, int no, int multi_lab
 extern "C" int myolo_nms(const float* pred, int B, int A, int no, float conf_thres, float iou_thres, const int32_t* classes,
                          int n_classes, int agnostic, int multi_label, int max_det, int max_nms, float max_wh, float* out,
                          int32_t* out_count, void* workspace, int64_t workspace_bytes, void* stream) {
+  nvtxRangePushA("myolo_nms");
+  struct Pop { ~Pop() { nvtxRangePop(); } } nvtx_pop_;
   MYOLO_REQUIRE(pred && out && out_count && workspace, "nms: null pointer");
   MYOLO_REQUIRE(B > 0 && A > 0 && no > 5, "nms: bad shape B=%d A=%d no=%d", B, A, no);
   MYOLO_REQUIRE(max_det > 0 && max_det <= kMaxKept, "nms: max_det must be in [1,%d]", kMaxKept);

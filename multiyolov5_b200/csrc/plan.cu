@@ -1,6 +1,12 @@
 // C ABI + layer-plan executor: what Model.__init__/fuse() and Model.forward_once (reference models/yolo.py:293-316,339-347)
 // become on the device.  The host-side planner (multiyolov5_b200/plan.py) lowers the module tree to a flat op list over
 // liveness-packed NHWC buffers; this file resolves views, owns packed weights / tensor maps and replays the list on a stream.
+#include <nvtx3/nvToolsExt.h>
+// NVTX ranges around every C-ABI entry point that launches work: visible in nsys / ncu --nvtx, free when no tool is attached
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 #include <stdarg.h>
 
 #include <algorithm>
@@ -92,6 +98,7 @@ struct myolo_plan {
   std::vector<cudaStream_t> lanes;
   std::vector<cudaEvent_t> op_ev;
   cudaEvent_t ev_start = nullptr;
+  cudaEvent_t ev_tail[2] = {nullptr, nullptr};   // fork / join of the Detect decodes next to the seg upsample
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int n_graph_ops = 0;
@@ -217,6 +224,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   if (pl->graph) cudaGraphDestroy(pl->graph);
   for (auto e : pl->op_ev) cudaEventDestroy(e);
   if (pl->ev_start) cudaEventDestroy(pl->ev_start);
+  for (auto& e : pl->ev_tail) if (e) cudaEventDestroy(e);
   for (auto st : pl->lanes) cudaStreamDestroy(st);
   for (auto& sl : pl->slots) {
     if (sl.w_dgrad) cudaFree(sl.w_dgrad);
@@ -452,7 +460,17 @@ static int build_graph(myolo_plan* pl) {
     const char* e = getenv("MYOLO_LANES");
     nl_env = e ? std::max(4, std::min(16, atoi(e))) : 4;      // >= 4: the captured backward uses lanes 0-3
   }
-  const int NL = nl_env;
+  // forward graphs: ONE lane by default.  Measured on B200 (CUPTI, tools/kernel_trace.py): every conv launch fills the machine, so branch
+  // concurrency buys nothing, while a multi-lane capture makes the graph runtime spread the nodes over ~70 internal streams - every edge
+  // becomes a cross-stream dependency (~5.5 us node to node instead of ~3.5 us), the programmatic-dependent-launch edges between
+  // consecutive convs are lost and the graph launch itself takes ~100 us instead of ~10.  MYOLO_FWD_LANES > 1 restores the branch lanes.
+  static int fwd_lanes = -1;
+  if (fwd_lanes < 0) {
+    const char* e = getenv("MYOLO_FWD_LANES");
+    fwd_lanes = e ? std::max(1, std::min(nl_env, atoi(e))) : 1;
+  }
+  const int NL = nl_env;          // streams / events are sized for the backward's lanes
+  const int NLF = fwd_lanes;      // lanes this (forward) capture actually uses
   if (pl->deps.empty()) compute_deps(pl);
   if (pl->lanes.empty()) {
     pl->lanes.resize(NL);
@@ -479,7 +497,7 @@ static int build_graph(myolo_plan* pl) {
     if (latest >= 0 && lane_last[lane_of[latest]] == latest) L = lane_of[latest];
     if (L < 0) {
       L = 0;
-      for (int k = 1; k < NL; ++k)
+      for (int k = 1; k < NLF; ++k)
         if (lane_last[k] < lane_last[L]) L = k;
     }
     cudaStream_t st = pl->lanes[L];
@@ -521,6 +539,7 @@ static int build_graph(myolo_plan* pl) {
 
 extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
                                   int64_t* seg_argmax, void* stream) {
+  NvtxRange nvtx_("myolo_plan_forward");
   MYOLO_REQUIRE(pl && x, "plan_forward: null plan / input");
   cudaStream_t s = (cudaStream_t)stream;
   const int64_t l0 = g_launch_count;
@@ -551,18 +570,33 @@ extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, fl
       ++n_ext;
     }
   MYOLO_CHECK_CUDA(cudaGraphLaunch(pl->graph_exec, s));
-  for (size_t i = 0; i < pl->ops.size(); ++i)     // ops writing caller-owned outputs: after the graph
+  // ops writing caller-owned outputs run after the graph: the three Detect decodes (small grids, ~50 us in a row) go to a side stream and
+  // overlap the x8 seg upsample (HBM-bound, ~80 us) on the caller's stream; the caller's stream joins before the call returns its outputs
+  const bool fork = (seg || seg_argmax) && (z || raw) && pl->lanes.size() > 1;
+  if (fork) {
+    if (!pl->ev_tail[0])
+      for (auto& e : pl->ev_tail) MYOLO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_tail[0], s));
+    MYOLO_CHECK_CUDA(cudaStreamWaitEvent(pl->lanes[1], pl->ev_tail[0], 0));
+  }
+  for (size_t i = 0; i < pl->ops.size(); ++i)
     if (pl->ops[i].kind == MYOLO_OP_DETECT_DECODE || pl->ops[i].kind == MYOLO_OP_SEG_UPSAMPLE) {
-      int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, s);
+      cudaStream_t st = (fork && pl->ops[i].kind == MYOLO_OP_DETECT_DECODE) ? pl->lanes[1] : s;
+      int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, st);
       if (rc) return rc;
       ++n_ext;
     }
+  if (fork) {
+    MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_tail[1], pl->lanes[1]));
+    MYOLO_CHECK_CUDA(cudaStreamWaitEvent(s, pl->ev_tail[1], 0));
+  }
   pl->last_launches = pl->n_graph_ops + n_ext;
   return 0;
 }
 
 extern "C" int myolo_plan_profile(myolo_plan* pl, const void* x, int x_dtype, float* z, float* const* raw, void* seg, int seg_dtype,
                                   int64_t* seg_argmax, float* host_ms_per_op, void* stream) {
+  NvtxRange nvtx_("myolo_plan_profile");
   MYOLO_REQUIRE(pl && x && host_ms_per_op, "plan_profile: null argument");
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = pl->ops.size();
@@ -655,6 +689,7 @@ extern "C" int myolo_plan_set_conv_grad(myolo_plan* pl, int slot, float* d_weigh
 
 extern "C" int myolo_plan_train_forward(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* seg, void* stream);
 extern "C" int myolo_plan_train_forward_multi(myolo_plan* pl, const void* x, int x_dtype, float* const* raw, float* const* seg, void* stream) {
+  NvtxRange nvtx_("myolo_plan_train_forward");
   MYOLO_REQUIRE(pl, "train_forward: null plan");
   pl->seg_outs[1] = seg ? seg[1] : nullptr;
   pl->seg_outs[2] = seg ? seg[2] : nullptr;
@@ -892,6 +927,7 @@ static int backward_run(myolo_plan* pl, int mask, std::vector<char>& live, cudaS
 
 extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw, const float* grad_seg, void* stream);
 extern "C" int myolo_plan_backward_multi(myolo_plan* pl, const float* const* grad_raw, const float* const* grad_seg, void* stream) {
+  NvtxRange nvtx_("myolo_plan_backward");
   MYOLO_REQUIRE(pl, "backward: null plan");
   pl->grad_segs[1] = grad_seg ? grad_seg[1] : nullptr;
   pl->grad_segs[2] = grad_seg ? grad_seg[2] : nullptr;
@@ -920,6 +956,7 @@ extern "C" int myolo_plan_backward(myolo_plan* pl, const float* const* grad_raw,
 // differentiated straight from the low-resolution logits; the backward then runs as the seg pass (seed mask 8)
 extern "C" int myolo_plan_backward_seg_ce(myolo_plan* pl, const int64_t* labels, int ignore_index, float factor, const float* scale_dev,
                                           float* loss_out, void* stream) {
+  NvtxRange nvtx_("myolo_plan_backward_seg_ce");
   MYOLO_REQUIRE(pl && pl->train_fwd_done && labels, "backward_seg_ce: call myolo_plan_train_forward first / null labels");
   cudaStream_t s = (cudaStream_t)stream;
   if (!pl->gws) MYOLO_CHECK_CUDA(cudaMalloc(&pl->gws, pl->ws_bytes));
@@ -1184,6 +1221,7 @@ extern "C" int myolo_grads_check_finite(const float* grad, int64_t n, int32_t* f
 extern "C" int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t* group, int64_t n, const float* lr,
                               const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale,
                               const int32_t* found_inf, int zero_grad, void* stream) {
+  NvtxRange nvtx_("myolo_sgd_step");
   int rc = check_device(nullptr);
   if (rc) return rc;
   return launch_sgd_step(param, grad, momentum_buf, group, (long)n, lr, weight_decay, n_groups, momentum, nesterov, inv_scale, found_inf,
@@ -1196,6 +1234,7 @@ extern "C" int myolo_sgd_step(float* param, float* grad, float* momentum_buf, co
 #include <dlfcn.h>
 typedef int (*PFN_ncclAllReduce)(const void*, void*, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void* /*ncclComm_t*/, cudaStream_t);
 extern "C" int myolo_allreduce_grads(float* flat_grad, int64_t n, void* nccl_comm, void* stream) {
+  NvtxRange nvtx_("myolo_allreduce_grads");
   MYOLO_REQUIRE(flat_grad && n > 0 && nccl_comm, "allreduce_grads: bad arguments");
   static PFN_ncclAllReduce fn = nullptr;
   if (!fn) {

@@ -121,3 +121,17 @@ def test_seg_consumers_match_reference_fixtures():
     up = restate.bilinear_align_corners_np(seg, (512, 1024))
     c0, l0, i0, u0 = restate.seg_metrics_np(up, tg, 19)
     assert l == l0 and abs(c - c0) <= 1e-4 * l0 and np.abs(inter - i0).max() <= 1e-3 * max(1, i0.max())   # argmax near-ties only
+
+
+@pytest.mark.parametrize("out_dtype", [torch.int64, torch.uint8])
+def test_fp16_argmax_fast_path_first_maximum_wins(out_dtype):
+    """16-pixels-per-thread fp16 kernel (half mode of detect.py:96-103,191-193): exact argmax of the fp16 values, ties -> lowest class id"""
+    from multiyolov5_b200.utils.general import seg_argmax
+    g = torch.Generator(device="cuda").manual_seed(3)
+    seg = (torch.randn((3, 19, 64, 96), device="cuda", generator=g) * 2).half()
+    seg[:, 5] = seg[:, 2]                       # exact ties between two planes everywhere
+    seg[0, :, 10, 10] = 1.5                     # all classes equal at one pixel -> class 0
+    out = seg_argmax(seg, (64, 96), out_dtype=out_dtype)
+    ref = seg.float().argmax(1)                 # torch.max over dim returns the first maximal index
+    assert out.dtype == out_dtype and torch.equal(out.long(), ref)
+    assert int(out[0, 10, 10]) == 0 and not bool((out == 5).any())
