@@ -426,6 +426,7 @@ def main():
         pb = eng.last_plan.pb
         from multiyolov5_b200 import _lib
         import ctypes as C
+        from multiyolov5_b200.plan import conv_algorithmic_flops
         conv_ms = simt_ms = 0.0
         n_conv = n_simt = 0
         flops = simt_flops = 0.0
@@ -434,7 +435,7 @@ def main():
         for i, o in enumerate(pb.ops):
             if o.kind == _lib.OP_CONV:
                 s = pb.slots[o.slot].conv
-                f = 2.0 * B * o.out.h * o.out.w * s.out_channels * s.in_channels * s.kernel_size[0] * s.kernel_size[1]
+                f = conv_algorithmic_flops(s, B, o.out)      # the reference layer's 2 x MACs (restated layer-0 conv included)
                 _lib.check(_lib.lib().myolo_plan_conv_info(eng.last_plan.handle, i, info))
                 if info[0]:      # tcgen05 kernel
                     conv_ms += per_op[i]; n_conv += 1; flops += f

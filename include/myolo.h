@@ -67,6 +67,10 @@ extern "C" {
 
 /* conv op flags */
 #define MYOLO_CONV_FORCE_SIMT 1 /* run on the generic CUDA-core kernel (tiny M / odd shapes / debugging) */
+/* op flags (any kind): a run of 2..4 CONSECUTIVE ops of one kind (REGION_COMBINE of one atom grid, small CONVs, BILINEARs with equal output
+ * extents) may be executed as ONE launch: the first op carries GROUP_HEAD and the member count in aux[7], the others GROUP_MEMBER */
+#define MYOLO_OP_GROUP_HEAD 2
+#define MYOLO_OP_GROUP_MEMBER 4
 
 typedef struct {
   int32_t h, w, c; /* per-image NHWC extents; batch is the plan's B */

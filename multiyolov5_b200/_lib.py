@@ -14,6 +14,7 @@ ACT_NONE, ACT_SILU, ACT_SIGMOID = 0, 1, 2
 (OP_INPUT_FOCUS, OP_CONV, OP_UPSAMPLE_NEAREST, OP_SPP_POOL, OP_BILINEAR, OP_REGION_SUM, OP_REGION_COMBINE, OP_CHANNEL_SCALE,
  OP_ADD, OP_DETECT_DECODE, OP_SEG_UPSAMPLE, OP_BROADCAST, OP_FOCUS_CONV, OP_BN_ACT, OP_ACT, OP_CHANNEL_SCALE_OOP, OP_DROPOUT) = range(1, 18)
 CONV_FORCE_SIMT = 1
+OP_GROUP_HEAD, OP_GROUP_MEMBER = 2, 4      # include/myolo.h: consecutive ops of one kind executed as one launch
 
 EXPORTS = [
     "myolo_abi_version", "myolo_last_error", "myolo_device_info", "myolo_plan_create", "myolo_plan_destroy",

@@ -65,6 +65,7 @@ bool conv_tc_eligible(const ConvOp& op);
 int conv_tc_prepare(ConvOp& op, int num_sms);
 int conv_tc_launch(const ConvOp& op, cudaStream_t stream);
 int conv_simt_launch(const ConvOp& op, cudaStream_t stream);
+int conv_simt_launch_group(const ConvOp* const* ops, int n, cudaStream_t stream);   // <= 4 small convs of one input type in one launch
 
 // weight packing: fp32 [Co][Ci][k][k] (+BN) -> fp16 [Co_pad][k*k][Ci_pad], bias fp32 [Co_pad]
 int pack_conv_weights(const float* w, int co, int ci, int k, const float* gamma, const float* beta, const float* mean,

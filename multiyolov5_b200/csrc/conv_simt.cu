@@ -3,6 +3,8 @@
 // with MYOLO_FORCE_SIMT=1, as an independent on-device cross-check of the tensor-core path.
 // One warp computes one output pixel x 32 consecutive output channels; lanes split K (coalesced 16-byte loads of both
 // the activation pixel and the weight row) and reduce with shuffles.
+#include <algorithm>
+
 #include "conv.h"
 
 namespace myolo {
@@ -37,7 +39,7 @@ struct SimtParams {
 };
 
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
+__device__ __forceinline__ void conv_simt_body(const SimtParams& p) {
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int co_groups = (p.Co + 7) / 8;
@@ -93,6 +95,41 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
       }
     }
   }
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) { conv_simt_body<TIn>(p); }
+// up to 4 small convolutions of the same input type in ONE launch (the 1x1 convs on the pooled bins of PyramidPooling): blockIdx.y = member
+struct SimtGroup { SimtParams p[4]; };
+template <typename TIn>
+__global__ void __launch_bounds__(256) conv_simt_group_kernel(SimtGroup g) { conv_simt_body<TIn>(g.p[blockIdx.y]); }
+
+static int fill_simt_params(const ConvOp& op, SimtParams& p) {
+  p.in = op.in.base; p.in_ctot = op.in.ctot; p.H = op.in.H; p.W = op.in.W; p.Ci = op.Ci_pad;
+  p.out = op.out.base; p.out_ctot = op.out.ctot; p.out_f32 = op.out.dtype == MYOLO_F32; p.Ho = op.out.H; p.Wo = op.out.W;
+  p.Co = op.Co;
+  p.res = op.has_res ? reinterpret_cast<const __half*>(op.res.base) : nullptr; p.res_ctot = op.has_res ? op.res.ctot : 0;
+  p.w = op.w; p.bias = op.bias; p.k = op.k; p.stride = op.stride; p.dil = op.dil; p.act = op.act; p.B = op.in.B;
+  MYOLO_REQUIRE(op.Ci_pad % 8 == 0 && op.in.ctot % (op.in.dtype == MYOLO_F16 ? 8 : 4) == 0, "conv_simt: Ci_pad %d / ctot %d alignment",
+                op.Ci_pad, op.in.ctot);
+  MYOLO_REQUIRE(op.in.C >= op.Ci_pad, "conv_simt: input view has %d channels, packed weights expect %d", op.in.C, op.Ci_pad);
+  return 0;
+}
+int conv_simt_launch_group(const ConvOp* const* ops, int n, cudaStream_t stream) {
+  MYOLO_REQUIRE(n >= 1 && n <= 4, "conv_simt_group: %d members", n);
+  SimtGroup g;
+  long most = 1;
+  for (int i = 0; i < n; ++i) {
+    MYOLO_REQUIRE(ops[i]->in.dtype == ops[0]->in.dtype, "conv_simt_group: mixed input types");
+    int rc = fill_simt_params(*ops[i], g.p[i]);
+    if (rc) return rc;
+    most = std::max(most, ((long)g.p[i].B * g.p[i].Ho * g.p[i].Wo * ((g.p[i].Co + 7) / 8) + 7) / 8);
+  }
+  if (most > 148 * 16) most = 148 * 16;
+  if (ops[0]->in.dtype == MYOLO_F16) conv_simt_group_kernel<__half><<<dim3((int)most, n), 256, 0, stream>>>(g);
+  else conv_simt_group_kernel<float><<<dim3((int)most, n), 256, 0, stream>>>(g);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
 }
 
 int conv_simt_launch(const ConvOp& op, cudaStream_t stream) {

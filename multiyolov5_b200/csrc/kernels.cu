@@ -215,8 +215,7 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, cons
   return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
 }
 
-__global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
-  const RowIdx r = row_index(out.W, out.C / 8);
+__device__ __forceinline__ void bilinear_nhwc_body(const TensorView& in, const TensorView& out, const RowIdx& r) {
   if (!r.ok) return;
   const int v = r.v, b = r.b;
   const Lerp ly = lerp_axis(r.y, in.H, out.H), lx = lerp_axis(r.x, in.W, out.W);
@@ -234,6 +233,33 @@ __global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
   for (int k = 0; k < 8; ++k)
     ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
   reinterpret_cast<uint4*>(vptr(out, b, r.y, r.x))[v] = o;
+}
+__global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) { bilinear_nhwc_body(in, out, row_index(out.W, out.C / 8)); }
+// up to 4 independent resamplings with identical output extents in ONE launch (the four levels of PyramidPooling): blockIdx.y = level*H + y
+struct BilinearGroup { TensorView in[4], out[4]; int n; };
+__global__ void bilinear_nhwc_group_kernel(BilinearGroup g) {
+  const int H = g.out[0].H;
+  const int level = blockIdx.y / H;
+  RowIdx r = row_index(g.out[0].W, g.out[0].C / 8);
+  r.y = blockIdx.y - level * H;
+  bilinear_nhwc_body(g.in[level], g.out[level], r);
+}
+int launch_bilinear_nhwc_group(const TensorView* in, const TensorView* out, int n, cudaStream_t s) {
+  MYOLO_REQUIRE(n >= 1 && n <= 4, "bilinear_nhwc_group: %d members", n);
+  BilinearGroup g;
+  g.n = n;
+  for (int i = 0; i < n; ++i) {
+    MYOLO_REQUIRE(in[i].C == out[i].C && in[i].C % 8 == 0 && in[i].ctot % 8 == 0 && out[i].ctot % 8 == 0 && in[i].dtype == MYOLO_F16 &&
+                      out[i].dtype == MYOLO_F16 && out[i].H == out[0].H && out[i].W == out[0].W && out[i].C == out[0].C && out[i].B == out[0].B,
+                  "bilinear_nhwc_group: member %d does not match", i);
+    g.in[i] = in[i];
+    g.out[i] = out[i];
+  }
+  dim3 grid = row_grid(out[0], out[0].C / 8);
+  grid.y *= n;
+  bilinear_nhwc_group_kernel<<<grid, 256, 0, s>>>(g);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
 }
 int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0 && in.dtype == MYOLO_F16 &&
@@ -296,9 +322,10 @@ int launch_region_sum(const TensorView& in, const int* d_yb, int ny, const int* 
   return 0;
 }
 
-__global__ void region_combine_kernel(TensorView atoms, const int* __restrict__ bins, int nbins, TensorView out) {
+__device__ __forceinline__ void region_combine_body(const TensorView& atoms, const int* __restrict__ bins, int nbins, const TensorView& out,
+                                                    long first, long stride) {
   const long total = (long)out.B * nbins * out.C;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  for (long i = first; i < total; i += stride) {
     const int c = (int)(i % out.C);
     const int bin = (int)((i / out.C) % nbins);
     const int b = (int)(i / ((long)out.C * nbins));
@@ -311,6 +338,29 @@ __global__ void region_combine_kernel(TensorView atoms, const int* __restrict__ 
     if (out.dtype == MYOLO_F32) vptr_f(out, b, oy, ox)[c] = val;
     else vptr(out, b, oy, ox)[c] = __float2half_rn(val);
   }
+}
+__global__ void region_combine_kernel(TensorView atoms, const int* __restrict__ bins, int nbins, TensorView out) {
+  region_combine_body(atoms, bins, nbins, out, blockIdx.x * (long)blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
+}
+// the pooling levels of one pyramid in ONE launch: blockIdx.y = level
+struct CombineGroup { const int* bins[4]; int nbins[4]; TensorView out[4]; };
+__global__ void region_combine_group_kernel(TensorView atoms, CombineGroup g) {
+  const int l = blockIdx.y;
+  region_combine_body(atoms, g.bins[l], g.nbins[l], g.out[l], blockIdx.x * (long)blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
+}
+int launch_region_combine_group(const TensorView& atoms, int atoms_nx, const int* const* d_bins, const int* nbins, const TensorView* out, int n,
+                                cudaStream_t s) {
+  MYOLO_REQUIRE(n >= 1 && n <= 4 && atoms.dtype == MYOLO_F32 && atoms.W == atoms_nx, "region_combine_group: bad arguments");
+  CombineGroup g;
+  long most = 0;
+  for (int i = 0; i < n; ++i) {
+    MYOLO_REQUIRE(out[i].H * out[i].W == nbins[i] && atoms.C == out[i].C, "region_combine_group: member %d does not match", i);
+    g.bins[i] = d_bins[i]; g.nbins[i] = nbins[i]; g.out[i] = out[i];
+    most = std::max(most, (long)out[i].B * nbins[i] * out[i].C);
+  }
+  region_combine_group_kernel<<<dim3(grid_for(most, 256), n), 256, 0, s>>>(atoms, g);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
 }
 int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bins, int nbins, const TensorView& out,
                           cudaStream_t s) {

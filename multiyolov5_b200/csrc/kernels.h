@@ -13,6 +13,9 @@ int launch_upsample_nearest2x(const TensorView& in, const TensorView& out, cudaS
 // SPP: out slices 1..3 = maxpool 5/9/13 of slice 0 (views share one buffer); reference models/common.py:170-174
 int launch_spp_pool(const TensorView& in, const TensorView& out5, int n_cascade, cudaStream_t s);
 int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream_t s);
+int launch_bilinear_nhwc_group(const TensorView* in, const TensorView* out, int n, cudaStream_t s);
+int launch_region_combine_group(const TensorView& atoms, int atoms_nx, const int* const* d_bins, const int* nbins, const TensorView* out, int n,
+                                cudaStream_t s);
 int launch_region_sum(const TensorView& in, const int* d_ybounds, int ny, const int* d_xbounds, int nx, const TensorView& out,
                       cudaStream_t s);
 int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bins, int nbins, const TensorView& out,

@@ -322,6 +322,45 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
   const myolo_op& op = pl->ops[i];
   TensorView in, in2, out;
   int rc;
+  // grouped launches: a run of consecutive ops of one kind executed by the head's launch (include/myolo.h MYOLO_OP_GROUP_*)
+  if (op.flags & MYOLO_OP_GROUP_MEMBER) return 0;
+  if (op.flags & MYOLO_OP_GROUP_HEAD) {
+    const int n = op.aux[7];
+    MYOLO_REQUIRE(n >= 2 && n <= 4 && i + n <= (int)pl->ops.size(), "op %d: bad group size %d", i, n);
+    for (int j = 1; j < n; ++j)
+      MYOLO_REQUIRE(pl->ops[i + j].kind == op.kind && (pl->ops[i + j].flags & MYOLO_OP_GROUP_MEMBER), "op %d: group member %d malformed", i, j);
+    if (op.kind == MYOLO_OP_REGION_COMBINE) {
+      TensorView outs[4];
+      const int* bins[4];
+      int nb[4];
+      if ((rc = resolve_view(pl, op.in, &in))) return rc;
+      for (int j = 0; j < n; ++j) {
+        const myolo_op& o = pl->ops[i + j];
+        MYOLO_REQUIRE(o.in.buf == op.in.buf && o.aux[2] == op.aux[2], "op %d: grouped region_combine ops must share the atom grid", i + j);
+        if ((rc = resolve_view(pl, o.out, &outs[j]))) return rc;
+        bins[j] = pl->d_extra + o.aux[0];
+        nb[j] = o.aux[1];
+      }
+      return launch_region_combine_group(in, op.aux[2], bins, nb, outs, n, s);
+    }
+    if (op.kind == MYOLO_OP_BILINEAR) {
+      TensorView ins[4], outs[4];
+      for (int j = 0; j < n; ++j)
+        if ((rc = resolve_view(pl, pl->ops[i + j].in, &ins[j])) || (rc = resolve_view(pl, pl->ops[i + j].out, &outs[j]))) return rc;
+      return launch_bilinear_nhwc_group(ins, outs, n, s);
+    }
+    if (op.kind == MYOLO_OP_CONV) {
+      const ConvOp* cs[4];
+      for (int j = 0; j < n; ++j) {
+        if (!pl->conv_ready[i + j] && (rc = prepare_conv(pl, i + j))) return rc;
+        MYOLO_REQUIRE(!pl->convs[i + j].use_tc, "op %d: only CUDA-core convs can be grouped", i + j);
+        cs[j] = &pl->convs[i + j];
+      }
+      return conv_simt_launch_group(cs, n, s);
+    }
+    set_error("op %d: kind %d cannot head a group", i, op.kind);
+    return MYOLO_E_INVALID;
+  }
   switch (op.kind) {
     case MYOLO_OP_INPUT_FOCUS:
       if ((rc = resolve_view(pl, op.out, &out))) return rc;

@@ -87,8 +87,10 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0 && lane == 0) {
+  // producer / MMA roles run warp-converged with one elected issuing lane (descriptor arithmetic stays in uniform registers; see conv_tc.cu)
+  if (warp == 0) {
     // ===================== TMA producer =====================
+    const bool leader = elect_one();
     const int half = p.k / 2;
     int stage = 0;
     uint32_t phase = 0;
@@ -100,10 +102,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
       for (int st = 0; st < p.steps_per_row; ++st) {
         const int ox0 = st * p.Kc;
         mbar_wait(&empty[stage], phase ^ 1);
+        __syncwarp();
         uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
-        mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_boxes * p.Kc * 128 + p.k * p.b_bytes));
-        tma_load_4d(sa, &tmDy, &full[stage], co0, ox0, oy, b);
-        if (p.a_boxes == 2) tma_load_4d(sa + p.Kc * 128, &tmDy, &full[stage], co0 + 64, ox0, oy, b);
+        if (leader) {
+          mbar_arrive_expect_tx(&full[stage], (uint32_t)(p.a_boxes * p.Kc * 128 + p.k * p.b_bytes));
+          tma_load_4d(sa, &tmDy, &full[stage], co0, ox0, oy, b);
+          if (p.a_boxes == 2) tma_load_4d(sa + p.Kc * 128, &tmDy, &full[stage], co0 + 64, ox0, oy, b);
+        }
         for (int kx = 0; kx < p.k; ++kx) {
           uint8_t* sb = sa + p.a_bytes + kx * p.b_bytes;
           int ix0, px = 0;
@@ -111,13 +116,15 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
           else { px = (kx == 1) ? 0 : 1; ix0 = ox0 + (kx == 0 ? -1 : 0); }
           const int m = py * 2 + px;
           const CUtensorMap* tm = m == 0 ? &tmX0 : (m == 1 ? &tmX1 : (m == 2 ? &tmX2 : &tmX3));
-          for (int nb = 0; nb < p.n_boxes; ++nb) tma_load_4d(sb + nb * p.Kc * p.bc * 2, tm, &full[stage], ci0 + nb * p.bc, ix0, iy, b);
+          if (leader)
+            for (int nb = 0; nb < p.n_boxes; ++nb) tma_load_4d(sb + nb * p.Kc * p.bc * 2, tm, &full[stage], ci0 + nb * p.bc, ix0, iy, b);
         }
         if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ===================== MMA issuer =====================
+    const bool leader = elect_one();
     const uint32_t idesc = (1u << 4)                            // D: fp32
                            | (0u << 7) | (0u << 10)             // A, B: fp16
                            | (1u << 15) | (1u << 16)            // A, B MN-major (channels contiguous, pixels strided)
@@ -131,18 +138,20 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
     const int jn = p.Kc / 16;
     for (int s = 0; s < n_steps; ++s) {
       mbar_wait(&full[stage], phase);
+      __syncwarp();
       tcgen05_fence_after();
       const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
       const uint64_t da = mn_major_desc(sa, lbo, 128);
       for (int kx = 0; kx < p.k; ++kx) {
         const uint64_t db = mn_major_desc(sa + p.a_bytes + kx * p.b_bytes, lbo_b, rb);
+#pragma unroll 4
         for (int j = 0; j < jn; ++j)   // 16 pixels per instruction = two 8-pixel groups = 2048 bytes
-          umma_f16_ss(tmem_base + kx * p.N, da + (uint64_t)(j * 128), db + (uint64_t)(j * jb), idesc, (uint32_t)((s | j) != 0));
+          if (leader) umma_f16_ss(tmem_base + kx * p.N, da + (uint64_t)(j * 128), db + (uint64_t)(j * jb), idesc, (uint32_t)((s | j) != 0));
       }
-      umma_commit(&empty[stage]);
+      if (leader) umma_commit(&empty[stage]);
       if (++stage == p.num_stages) { stage = 0; phase ^= 1; }
     }
-    umma_commit(acc_full);
+    if (leader) umma_commit(acc_full);
   } else if (warp >= 2) {
     // ===================== epilogue: TMEM -> fp32 reductions =====================
     if (n_steps > 0) {

@@ -35,6 +35,7 @@ class Buf:
     first: int = -1
     last: int = -1
     offset: int = 0
+    alias_of: Optional["Buf"] = None    # same memory seen with another (w, c) factorisation of the pixel row (pixel-pair views)
 
     def nbytes(self, B):
         return B * self.h * self.w * self.c * (2 if self.dtype == F16 else 4)
@@ -99,6 +100,44 @@ class _CatConv:
         return torch.cat([self.a.weight.detach(), self.b.weight.detach()], 0)
 
 
+class _PairedConv:
+    """A 3x3 stride-1 conv on C_in (<= 16, zero padded to 16) channels restated on PIXEL PAIRS: the NHWC input (H, W, 16) is the same memory as
+    (H, W/2, 32) and the output (H, W, Co) the same as (H, W/2, 2 Co).  Output pair j = pixels (2j, 2j+1) needs input pixels 2j-1 .. 2j+2 =
+    pairs j-1, j, j+1, so the restated conv is again 3x3 / stride 1 / pad 1 with
+        W'[p_out*Co + co, p_in*16 + ci, ky, pt] = W[co, ci, ky, kx],  kx = 2*(pt-1) + p_in - p_out + 1  (zero where kx is outside 0..2).
+    Same arithmetic (the extra products are exact zeros), but the implicit-GEMM kernel sees 64-byte instead of 32-byte pixel rows, half as
+    many of them, and N = 2 Co: the first layer is bound by the TMA's per-row cost (~4.4 clk per 32-byte row measured on B200)."""
+
+    def __init__(self, conv: nn.Conv2d):
+        assert conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.dilation == (1, 1) and conv.padding == (1, 1)
+        assert conv.groups == 1 and conv.bias is None and conv.in_channels <= 16
+        self.base = conv
+        self.kernel_size, self.stride, self.dilation, self.padding, self.groups = (3, 3), (1, 1), (1, 1), (1, 1), 1
+        self.in_channels, self.out_channels, self.bias = 32, 2 * conv.out_channels, None
+
+    @property
+    def weight(self):
+        w = self.base.weight.detach()
+        co, ci = w.shape[0], w.shape[1]
+        out = torch.zeros((2 * co, 32, 3, 3), dtype=w.dtype, device=w.device)
+        for p_out in range(2):
+            for p_in in range(2):
+                for pt in range(3):
+                    kx = 2 * (pt - 1) + p_in - p_out + 1
+                    if 0 <= kx <= 2:
+                        out[p_out * co:(p_out + 1) * co, p_in * 16:p_in * 16 + ci, :, pt] = w[:, :, :, kx]
+        return out
+
+
+def conv_algorithmic_flops(conv, B: int, out_view) -> float:
+    """2 x MACs of the REFERENCE convolution behind a plan conv op (SURVEY.md section 8d accounting): restated convs (_PairedConv) count what
+    the reference layer computes, not the zero-padded products"""
+    if isinstance(conv, _PairedConv):
+        b = conv.base
+        return 2.0 * B * out_view.h * (out_view.w * 2) * b.out_channels * b.in_channels * 9
+    return 2.0 * B * out_view.h * out_view.w * conv.out_channels * conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1]
+
+
 class _CatBN:
     def __init__(self, a: nn.BatchNorm2d, b: nn.BatchNorm2d):
         assert a.eps == b.eps
@@ -122,7 +161,8 @@ class PlanBuilder:
     def __init__(self, B: int, H: int, W: int, train: bool = False):
         self.B, self.H, self.W = B, H, W
         self.train = train                      # train mode: raw conv -> batch-stat BN + act ops, nothing in place, no aliasing
-        self.fuse_c3 = os.environ.get("MYOLO_FUSE_C3", "0") == "1"
+        # cv1 and cv2 of a C3 read the same input: ONE launch with concatenated output channels (measured on B200: -70 us per forward)
+        self.fuse_c3 = os.environ.get("MYOLO_FUSE_C3", "1") == "1"
         self.bn_slots: List[nn.BatchNorm2d] = []
         self.bufs: List[Buf] = []
         self.ops: List[OpRec] = []
@@ -139,9 +179,19 @@ class PlanBuilder:
     def _touch(self, v: Optional[V], idx: int):
         if v is None:
             return
-        if v.buf.first < 0:
-            v.buf.first = idx
-        v.buf.last = idx
+        for b in (v.buf, v.buf.alias_of):
+            if b is None:
+                continue
+            if b.first < 0:
+                b.first = idx
+            b.last = idx
+
+    def alias_buf(self, base: Buf, h, w, c) -> V:
+        """another (w, c) factorisation of the same NHWC memory"""
+        assert base.alias_of is None and h * w * c == base.h * base.w * base.c and base.dtype == F16
+        b = Buf(len(self.bufs), h, w, c, base.dtype, alias_of=base)
+        self.bufs.append(b)
+        return V(b, 0, c)
 
     def emit(self, rec: OpRec):
         idx = len(self.ops)
@@ -249,10 +299,9 @@ class PlanBuilder:
         c_ = m.cv1.conv.out_channels
         n = len(m.m)
         if self.fuse_c3 and not self.train and n >= 1:
-            # EXPERIMENTAL (MYOLO_FUSE_C3=1, off by default, not yet validated on the GPU): cv1 and cv2 read the same input, so they
-            # run as ONE 1x1 conv with concatenated output channels writing [cv1_out | cv2_out]; the last bottleneck then overwrites
-            # the (by then dead) cv1 half with the m-chain output, which is exactly the concat cv3 reads.  One launch and one read
-            # of x less per C3; no kernel change.
+            # cv1 and cv2 read the same input, so they run as ONE 1x1 conv with concatenated output channels writing [cv1_out | cv2_out];
+            # the last bottleneck then overwrites the (by then dead) cv1 half with the m-chain output, which is exactly the concat cv3
+            # reads.  One launch and one read of x less per C3; no kernel change (tests/test_gpu_model.py::test_c3_cv1_cv2_fusion...).
             both = self.new_buf(x.h, x.w, 2 * c_)
             self.conv(x, _CatConv(m.cv1.conv, m.cv2.conv), _CatBN(m.cv1.bn, m.cv2.bn), ACT_SILU, both, name="c3.cv1+cv2")
             y = both.sub(0, c_)
@@ -300,6 +349,15 @@ class PlanBuilder:
             return dst
         s2d = self.new_buf(self.H // 2, self.W // 2, 16)
         self.emit(OpRec(OP_INPUT_FOCUS, None, None, s2d))
+        if (not self.train and dst is None and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and isinstance(m.conv.act, nn.SiLU)
+                and (self.W // 2) % 2 == 0 and os.environ.get("MYOLO_L0_PAIR", "1") == "1"):
+            # layer 0 on pixel pairs (_PairedConv): same memory, 64-byte rows, N = 2 Co
+            out = self.new_buf(self.H // 2, self.W // 2, conv.out_channels)
+            x2 = self.alias_buf(s2d.buf, self.H // 2, self.W // 4, 32)
+            y2 = self.alias_buf(out.buf, self.H // 2, self.W // 4, 2 * conv.out_channels)
+            self.conv(x2, _PairedConv(conv), _CatBN(m.conv.bn, m.conv.bn), ACT_SILU, y2, name="focus.conv(pixel pairs)")
+            self._touch(out, len(self.ops) - 1)
+            return out
         return self.Conv(m.conv, s2d, dst)
 
     def RFB2(self, m: cm.RFB2, x: V, dst=None) -> V:
@@ -325,13 +383,32 @@ class PlanBuilder:
             self.dilated(br, x, cat.sub((i + 1) * hid, hid))
         return self.Conv(m.ConvLinear, cat, dst)
 
+    def group(self, first: int, n: int):
+        """ops[first : first+n] (same kind, emitted back to back) run as ONE launch (include/myolo.h MYOLO_OP_GROUP_*)"""
+        if n < 2 or n > 4 or self.train or os.environ.get("MYOLO_GROUP_OPS", "1") != "1":
+            return
+        kinds = {o.kind for o in self.ops[first:first + n]}
+        assert len(kinds) == 1 and first + n <= len(self.ops)
+        self.ops[first].flags |= _lib.OP_GROUP_HEAD
+        self.ops[first].aux[7] = n
+        for o in self.ops[first + 1:first + n]:
+            o.flags |= _lib.OP_GROUP_MEMBER
+
     def PyramidPooling(self, m: cm.PyramidPooling, x_in_cat: V, cat: V) -> V:
-        """x_in_cat is slice 0 of `cat` (2C channels); fills slices 1..4 and returns cat."""
+        """x_in_cat is slice 0 of `cat` (2C channels); fills slices 1..4 and returns cat.  The four levels run level-parallel: one launch
+        each for the bin averages, the four 1x1 convs on the pooled bins and the four upsamplings (12 tiny kernels -> 3)."""
         C = x_in_cat.c
-        pooled = self.pool_pyramid(x_in_cat, m.k)
-        for i, (p, conv) in enumerate(zip(pooled, (m.conv1, m.conv2, m.conv3, m.conv4))):
-            f = self.Conv(conv, p)
+        n0 = len(self.ops)
+        pooled = self.pool_pyramid(x_in_cat, m.k)             # REGION_SUM + one REGION_COMBINE per level
+        self.group(n0 + 1, len(pooled))
+        n1 = len(self.ops)
+        feats = [self.Conv(conv, p) for p, conv in zip(pooled, (m.conv1, m.conv2, m.conv3, m.conv4))]
+        if not self.train and all(p.h * p.w < 128 for p in pooled):          # all four are CUDA-core convs (maps below one 128-pixel tile)
+            self.group(n1, len(feats))
+        n2 = len(self.ops)
+        for i, f in enumerate(feats):
             self.bilinear(f, x_in_cat.h, x_in_cat.w, cat.sub(C + i * (C // 4), C // 4))
+        self.group(n2, len(feats))
         return cat
 
     def FFM(self, m: cm.FFM, x: V, dst=None) -> V:
@@ -554,7 +631,7 @@ def build_plan(model, B: int, H: int, W: int, noalias: bool = False, train: bool
 def assign_offsets(pb: PlanBuilder, align: int = 256, noalias: bool = False):
     """first-fit packing of [first,last] live intervals (ops run sequentially on one stream, so disjoint lifetimes may alias)."""
     placed = []  # (offset, size, first, last)
-    order = sorted((b for b in pb.bufs if b.first >= 0), key=lambda b: (-b.nbytes(pb.B), b.first))
+    order = sorted((b for b in pb.bufs if b.first >= 0 and b.alias_of is None), key=lambda b: (-b.nbytes(pb.B), b.first))
     total = 0
     for b in order:
         size = (b.nbytes(pb.B) + align - 1) // align * align
@@ -568,7 +645,9 @@ def assign_offsets(pb: PlanBuilder, align: int = 256, noalias: bool = False):
         placed.append((off, size, b.first, b.last))
         total = max(total, off + size)
     for b in pb.bufs:
-        if b.first < 0:
+        if b.alias_of is not None:
+            b.offset = b.alias_of.offset
+        elif b.first < 0:
             b.offset = 0
     pb.workspace_bytes = max(total, align)
     return pb.workspace_bytes
