@@ -50,7 +50,10 @@ def test_planner_invariants(tag, B, H, W):
     from multiyolov5_b200.plan import build_plan
     pb = build_plan(Model(NETS[tag]), B, H, W)
     n = len(pb.ops)
-    used = [b for b in pb.bufs if b.first >= 0]
+    aliases = [b for b in pb.bufs if b.alias_of is not None]
+    for b in aliases:       # pixel-pair views (layer 0): same bytes, same total size, another (w, c) factorisation
+        assert b.offset == b.alias_of.offset and b.nbytes(B) == b.alias_of.nbytes(B) and b.h == b.alias_of.h
+    used = [b for b in pb.bufs if b.first >= 0 and b.alias_of is None]
     # liveness packing never overlaps two simultaneously-live buffers, and beats the unpacked footprint
     for i, a in enumerate(used):
         assert a.offset % 256 == 0 and a.offset + a.nbytes(B) <= pb.workspace_bytes
