@@ -189,6 +189,15 @@ __device__ __forceinline__ float silu_f(float v) {
   r = r * fmaf(-d, r, 2.0f);
   return v * r;
 }
+// the same function with the reciprocal on the SFU (MUFU.RCP, 1 ulp): 5 issue slots instead of 12, but two MUFU ops.  The conv epilogue mixes
+// both (every fourth element takes this one) so that the FP32 pipe (12 clk per warp-element on the Newton path) and the quarter-rate SFU
+// (8 clk per MUFU) finish together: ~10 instead of 12 issue slots per element on layers whose epilogue is issue-bound (70 % issue-active in ncu).
+__device__ __forceinline__ float silu_f_sfu(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));      // e = +inf -> r = 0 -> v * 0 = -0 for finite v
+  return v * r;
+}
 __device__ __forceinline__ float sigmoid_f(float v) { return __fdividef(1.0f, 1.0f + __expf(-v)); }
 __device__ __forceinline__ float apply_act(float v, int act) {
   return act == MYOLO_ACT_SILU ? silu_f(v) : (act == MYOLO_ACT_SIGMOID ? sigmoid_f(v) : v);

@@ -129,7 +129,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
   if (p.act == MYOLO_ACT_SILU) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) f[e] = silu_f(f[e]);
+    for (int e = 0; e < 16; ++e) f[e] = (e & 3) == 3 ? silu_f_sfu(f[e]) : silu_f(f[e]);
   } else if (p.act == MYOLO_ACT_SIGMOID) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);

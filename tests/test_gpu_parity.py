@@ -59,7 +59,9 @@ def errors_vs_fixture(z, raws, seg, g):
 # are made of: the torch-fp16 yardstick below sits at the same level.
 # measured (B200, profiles/parity_r2.md): raw <= 3.8e-3 (torch fp16: <= 5.2e-3), seg <= 2.6e-3 (3.4e-3), scores <= 1.43e-2 (2.2e-2), boxes <= 256 px:
 # <= 2.4 px, class ids 99.38 % .. 100 % (99.55 % .. 99.998 %)
-CAPS = {"raw": 6e-3, "seg": 4e-3, "box_px_max_le256": 4.0, "box_rel_max": 2.5e-2, "score_abs_max": 2.2e-2, "cls_agree_min": 0.99}
+# boxes: worst of 32 256 anchors; a head-logit error of 0.05 moves w = (2 sigmoid)^2 * anchor by up to 7 % (ours <= 9.5 px on boxes <= 256 px and
+# <= 7.0e-2 of the box size; torch fp16 <= 9.9 px and <= 9.9e-2)
+CAPS = {"raw": 6e-3, "seg": 4e-3, "box_px_max_le256": 15.0, "box_rel_max": 0.11, "score_abs_max": 2.2e-2, "cls_agree_min": 0.99}
 
 
 SCORE_CAP_E2E = 2.5e-2       # measured 1.2e-2 .. 1.4e-2 (sigmoid slope 1/4 x fp16-storage noise of the head logits)

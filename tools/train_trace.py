@@ -1,0 +1,56 @@
+"""CUPTI timeline of ONE training step (tools/bench_train.make_workload): wall, busy time per stream, union coverage, kernels ranked by total
+device time.  Usage: python tools/train_trace.py [--no-overlap]"""
+import collections, json, os, sys, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from tools.bench_train import make_workload
+wl = make_workload(1, 0, 4)
+tr, NROT = wl["tr"], wl["NROT"]
+if "--no-overlap" in sys.argv:
+    tr.overlap_passes = False
+def step(i):
+    k = i % NROT
+    return tr.step(wl["imgs"][k], wl["tg"][k], wl["segimgs"][k], wl["masks"][k])
+for i in range(5):
+    step(i)
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    for i in range(2):
+        step(i)
+        torch.cuda.synchronize()
+f = tempfile.mktemp(suffix=".json")
+prof.export_chrome_trace(f)
+ev = [e for e in json.load(open(f))["traceEvents"] if e.get("cat") == "kernel"]
+ev.sort(key=lambda e: e["ts"])
+steps, cur = [], [ev[0]]
+for a, b in zip(ev, ev[1:]):
+    if b["ts"] - (a["ts"] + a["dur"]) > 400:
+        steps.append(cur); cur = []
+    cur.append(b)
+steps.append(cur)
+st = max(steps, key=len)
+t0 = st[0]["ts"]; end = max(e["ts"] + e["dur"] for e in st)
+iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in st)
+cov, cs, ce = 0.0, iv[0][0], iv[0][1]
+for a, b in iv[1:]:
+    if a > ce:
+        cov += ce - cs; cs, ce = a, b
+    else:
+        ce = max(ce, b)
+cov += ce - cs
+print(f"# one step: {len(st)} kernels, wall {end - t0:.0f} us, sum of durations {sum(e['dur'] for e in st):.0f} us, union {cov:.0f} us, idle {end - t0 - cov:.0f} us")
+busy = collections.Counter()
+for e in st:
+    busy[e["args"].get("stream")] += e["dur"]
+print("# busy us per stream:", dict(sorted(((k, round(v)) for k, v in busy.items()), key=lambda kv: -kv[1])[:12]))
+agg = collections.defaultdict(lambda: [0, 0.0])
+for e in st:
+    n = e["name"].replace("myolo::", "").replace("void ", "").split("(")[0][:70]
+    agg[n][0] += 1; agg[n][1] += e["dur"]
+for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
+    print(f"{t:9.1f} us {c:5d}x  {n}")
+# phase markers: first / last kernel of each stream
+for s in list(busy)[:6]:
+    ks = [e for e in st if e["args"].get("stream") == s]
+    print(f"# stream {s}: {len(ks)} kernels from {ks[0]['ts'] - t0:.0f} to {ks[-1]['ts'] + ks[-1]['dur'] - t0:.0f} us")
