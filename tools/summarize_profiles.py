@@ -116,9 +116,52 @@ def last_step(tag, path, n):
     launches(tmp, f"profiles/launches_{tag}.md")
 
 
+def conv_sections(tag, path, perop=None):
+    """`ncu --section SpeedOfLight ... --page raw --csv` of EVERY conv_tc launch of one step (tools/capture_profiles.sh) -> a compact tracked
+    table profiles/conv_launches_<tag>.csv/.md: duration, tensor-pipe %, issue %, DRAM %, L2 %, grid, smem per launch (+ the layer shape when
+    the `#conv` lines of `bench.py --profile-ops` are given)"""
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H, data = rows[hdr], rows[hdr + 2:]
+    col = {k: H.index(k) for k in ("Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                                   "sm__issue_active.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+                                   "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
+                                   "launch__registers_per_thread")}
+    unit = rows[hdr + 1][col["gpu__time_duration.sum"]]
+    scale = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}.get(unit, 1.0)
+    shapes = []
+    if perop:
+        shapes = [" ".join(l.split()[2:6]) for l in open(perop) if l.startswith("#conv") and "[1," in l]
+    out_csv, out_md = f"profiles/conv_launches_{tag}.csv", f"profiles/conv_launches_{tag}.md"
+    with open(out_csv, "w") as f, open(out_md, "w") as g:
+        f.write("launch,kernel,layer,duration_us,tensor_pipe_pct,issue_active_pct,dram_pct,l2_pct,grid,smem_bytes,regs\n")
+        g.write("# every conv_tc launch of one forward (ncu SpeedOfLight sections, --clock-control none, cold-cache / serialised)\n\n"
+                "| # | layer | us | tensor pipe % | issue % | DRAM % | L2 % | grid | smem KB |\n|---:|---|---:|---:|---:|---:|---:|---:|---:|\n")
+        tot = 0.0
+        for n, r in enumerate(data):
+            if len(r) <= max(col.values()):
+                continue
+            v = lambda k: r[col[k]].replace(",", "")  # noqa: E731
+            us = float(v("gpu__time_duration.sum")) * scale
+            tot += us
+            layer = shapes[n] if n < len(shapes) else ""
+            kern = v("Kernel Name").split("(")[0].replace("void ", "").replace(", ", ";")
+            f.write(f"{n},{kern},{layer},{us:.2f},{float(v('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')):.1f},"
+                    f"{float(v('sm__issue_active.avg.pct_of_peak_sustained_elapsed')):.1f},{float(v('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f},"
+                    f"{float(v('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.1f},{v('launch__grid_size')},{v('launch__shared_mem_per_block_dynamic')},{v('launch__registers_per_thread')}\n")
+            g.write(f"| {n} | {layer} | {us:.1f} | {float(v('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')):.1f} | "
+                    f"{float(v('sm__issue_active.avg.pct_of_peak_sustained_elapsed')):.1f} | {float(v('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | "
+                    f"{float(v('lts__throughput.avg.pct_of_peak_sustained_elapsed')):.1f} | {v('launch__grid_size')} | {float(v('launch__shared_mem_per_block_dynamic')) / 1024:.0f} |\n")
+        g.write(f"\nsum of durations {tot:.1f} us\n")
+    print("wrote", out_md)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "last-step":
         last_step(sys.argv[2], sys.argv[3], int(sys.argv[4]))
+        sys.exit(0)
+    if sys.argv[1] == "conv-sections":
+        conv_sections(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
         sys.exit(0)
     if sys.argv[1] == "regen":
         regen(sys.argv[2])
