@@ -54,3 +54,20 @@ for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
 for s in list(busy)[:6]:
     ks = [e for e in st if e["args"].get("stream") == s]
     print(f"# stream {s}: {len(ks)} kernels from {ks[0]['ts'] - t0:.0f} to {ks[-1]['ts'] + ks[-1]['dur'] - t0:.0f} us")
+
+# concurrency profile: per 0.5 ms bucket, kernel-time / wall-time (> 1 means kernels of different streams overlap) and the dominant kernels
+B = 500.0
+nb = int((end - t0) / B) + 1
+load = [0.0] * nb
+names = [collections.Counter() for _ in range(nb)]
+for e in st:
+    a, b = e["ts"] - t0, e["ts"] - t0 + e["dur"]
+    k = int(a / B)
+    while a < b and k < nb:
+        hi = min(b, (k + 1) * B)
+        load[k] += hi - a
+        names[k][e["name"].replace("myolo::", "").replace("void ", "").split("(")[0].split("<")[0][:22]] += hi - a
+        a = hi; k += 1
+print("# bucket(ms)  kernel-time/wall  top kernels")
+for k in range(nb):
+    print(f"{k * B / 1000:6.1f}  {load[k] / B:5.2f}  " + ", ".join(f"{n}:{t:.0f}" for n, t in names[k].most_common(3)))
