@@ -171,6 +171,17 @@ int myolo_sgd_step(float* param, float* grad, float* momentum_buf, const uint8_t
                    const float* weight_decay, int n_groups, float momentum, int nesterov, const float* inv_scale /* device */,
                    const int32_t* found_inf /* device, nullable */, int zero_grad, void* stream);
 
+/* Detection loss forward + backward in four launches (reference utils/loss.py:115-217 `ComputeLoss.__call__` / `build_targets` + autograd):
+ * p[l] / dp[l]: the nl raw head outputs (B, na, ny[l], nx[l], no) fp32 and their gradients (overwritten); targets (nt, 6) [image, class,
+ * x, y, w, h] normalised, all-zero rows never match; anchors_grid: nl*na*2 floats in grid units (host); balance: nl floats (host).
+ * d loss / d p = mult * (*scale_dev) * d[bs-free ComputeLoss value]/dp with mult = batch * world * detgain chosen by the caller; items_out (device
+ * float[4]) = lbox, lobj, lcls, their sum (detached, as the reference's loss_items).  fl_gamma = 0, cls_pw = obj_pw = 1 only. */
+int64_t myolo_det_loss_workspace_bytes(int B, int na, int nl, const int32_t* ny, const int32_t* nx);
+int myolo_det_loss(const float* const* p, float* const* dp, const float* targets, int nt, int B, int na, int no, int nl, const int32_t* ny,
+                   const int32_t* nx, const float* anchors_grid, const float* balance, float hyp_box, float hyp_obj, float hyp_cls,
+                   float anchor_t, float gr, float cp, float cn, float mult, const float* scale_dev, float* items_out, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
 /* The path's ONE exchange step (reference train.py:243-245 wraps the model in DistributedDataParallel): in-place
  * SUM all-reduce of the flat fp32 gradient buffer over the ranks of `nccl_comm` (an ncclComm_t; averaging is folded into myolo_sgd_step's
  * inv_scale), enqueued on `stream`.  The library does not link NCCL: it binds ncclAllReduce from the libnccl the host process has already

@@ -21,7 +21,7 @@ EXPORTS = [
     "myolo_plan_set_conv_weights", "myolo_plan_forward", "myolo_plan_read_view", "myolo_plan_last_launch_count",
     "myolo_plan_profile", "myolo_nms_workspace_bytes", "myolo_nms", "myolo_seg_upsample_argmax", "myolo_bilinear_nchw",
     "myolo_conv_bn_silu", "myolo_plan_set_bn", "myolo_plan_set_conv_grad", "myolo_plan_train_forward", "myolo_plan_backward",
-    "myolo_grads_check_finite", "myolo_sgd_step", "myolo_conv_wgrad", "myolo_letterbox", "myolo_seg_lut_blend", "myolo_seg_metrics", "myolo_plan_backward_seg_ce", "myolo_plan_read_grad_view", "myolo_plan_set_seed", "myolo_plan_train_forward_multi", "myolo_plan_backward_multi", "myolo_plan_conv_info", "myolo_allreduce_grads",
+    "myolo_grads_check_finite", "myolo_sgd_step", "myolo_conv_wgrad", "myolo_letterbox", "myolo_seg_lut_blend", "myolo_seg_metrics", "myolo_plan_backward_seg_ce", "myolo_plan_read_grad_view", "myolo_plan_set_seed", "myolo_plan_train_forward_multi", "myolo_plan_backward_multi", "myolo_plan_conv_info", "myolo_allreduce_grads", "myolo_det_loss", "myolo_det_loss_workspace_bytes",
 ]
 
 
@@ -85,6 +85,10 @@ def lib():
     L.myolo_grads_check_finite.argtypes = [vp, i64, vp, vp]
     L.myolo_sgd_step.argtypes = [vp, vp, vp, vp, i64, C.POINTER(f32), C.POINTER(f32), i32, f32, i32, vp, vp, i32, vp]
     L.myolo_allreduce_grads.argtypes = [vp, i64, vp, vp]
+    L.myolo_det_loss_workspace_bytes.argtypes = [i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.myolo_det_loss_workspace_bytes.restype = i64
+    L.myolo_det_loss.argtypes = [C.POINTER(vp), C.POINTER(vp), vp, i32, i32, i32, i32, i32, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                 C.POINTER(f32), C.POINTER(f32), f32, f32, f32, f32, f32, f32, f32, f32, vp, vp, vp, i64, vp]
     L.myolo_plan_conv_info.argtypes = [vp, i32, C.POINTER(C.c_int32)]
     L.myolo_nms_workspace_bytes.argtypes = [i32, i32, i32, i32]
     L.myolo_nms_workspace_bytes.restype = i64

@@ -33,7 +33,8 @@ static constexpr int kMaxWsBytes = 40 * 1024;
 static constexpr int kMaxWsBytesBig = 40 * 1024;    // = kMaxWsBytes: resident tiles that force one CTA per SM (MYOLO_WS_BIG_KB=100: 3x3 64->64,
                                                      // 1x1 256->128 ...) measured 29 us SLOWER per forward on B200 (no co-resident CTA to overlap with)
 static constexpr int kSmemPerCta = 112 * 1024;   // two CTAs per SM: their epilogues / TMA latencies overlap
-static constexpr int kBiasBytes = 4096;         // bias vector of the layer in shared memory (<= 1024 output channels)
+static constexpr int kBiasBytes = 8192;         // bias vector of the layer in shared memory (<= 1920 output channels: the data gradient
+                                                // of SPP.cv2 has 1024)
 
 #ifdef MYOLO_TIMELINE
 #define DBG_STAMP(slot) do { if (p.dbg && blockIdx.x == 0 && it < 64) p.dbg[it * 16 + (slot)] = clock64(); } while (0)

@@ -1059,7 +1059,8 @@ static int backward_walk(myolo_plan* pl, std::vector<char>& live, cudaStream_t s
   static int ml_env = -1;
   if (ml_env < 0) {
     const char* e = getenv("MYOLO_BWD_LANES");
-    ml_env = e ? atoi(e) : 1;
+    ml_env = e ? atoi(e) : 0;     // measured on B200: the three-lane chain costs 2.7 ms per step (14.6 -> 11.9 ms): like the forward graph, a
+                                  // multi-lane capture is spread over dozens of internal streams and every edge becomes a cross-stream wait
   }
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cap);

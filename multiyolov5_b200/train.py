@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 from .parallel import allreduce_flat_grads
-from .utils.loss import ComputeLoss, SegmentationLosses
+from .utils.loss import ComputeLoss, FusedComputeLoss, SegmentationLosses
 
 
 def scale_hyp(hyp: dict, nl: int, nc: int, imgsz: int, total_batch_size: int, nbs: int = 64, label_smoothing: float = 0.0) -> dict:
@@ -84,7 +84,7 @@ class Trainer:
     """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
 
     def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
-                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True, overlap_passes=True):
+                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True, overlap_passes=True, fused_det_loss=True):
         assert next(model.parameters()).is_cuda, "model.cuda() first"
         self.model, self.hyp, self.batch_size = model, hyp, batch_size
         self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
@@ -92,6 +92,10 @@ class Trainer:
         model.hyp, model.gr = hyp, getattr(model, "gr", 1.0)
         model.train()
         self.compute_loss = ComputeLoss(model)
+        # detection loss forward + backward as four launches of the library (csrc/detloss.cu) instead of ~760 torch kernels; the torch
+        # formulation stays for focal loss / positive weights / autobalance and as the test oracle
+        self._fused_det = FusedComputeLoss(model) if fused_det_loss else None
+        self.fused_det_loss = bool(fused_det_loss) and self._fused_det.supported
         self.n_seg_outputs = 3 if type(model.model[-2]).__name__ == "SegMaskBiSe" else 1
         # BiSe returns [out, aux16, aux32]: loss1 + 1.5*aux_weight*loss2 + 0.5*aux_weight*loss3 (reference train.py:387-388, utils/loss.py:239-244)
         self.compute_seg_loss = SegmentationLosses(ignore_index=-1, aux=self.n_seg_outputs == 3, aux_num=2)
@@ -113,7 +117,7 @@ class Trainer:
         # running statistics are then updated in the reference's order, det batch first: train.py:364,381), so the seg forward/backward
         # overlaps the det loss + backward; parameter gradients of both passes add up atomically in the one flat buffer.  At 4 images per
         # pass the kernels are launch/latency bound and each pass alone leaves most of the 148 SMs idle.
-        self.overlap_passes = bool(overlap_passes) and graph_loss
+        self.overlap_passes = bool(overlap_passes) and (graph_loss or fused_det_loss)
         self._s_seg = torch.cuda.Stream() if self.overlap_passes else None
         self._ev_detfwd, self._ev_start, self._ev_seg = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
@@ -166,6 +170,14 @@ class Trainer:
         return st
 
     def backward_det(self, imgs, targets):
+        if self.fused_det_loss:
+            eng = self.model.engine()
+            raws, _, plan = eng.train_forward(imgs, want_seg=False)
+            self._ev_detfwd.record(torch.cuda.current_stream())
+            mult = (self.world_size if self.rank != -1 else 1) * self.detgain              # train.py:367-368 and :290
+            grads, items = self._fused_det(raws, targets, mult=mult, scale=self.scale)
+            eng.train_backward(plan, grads, None)
+            return items
         if not self.graph_loss:
             pred = self.model(imgs)                                               # train mode: [[x0,x1,x2], seg]
             loss, items = self._det_loss_scaled(pred[0], targets)

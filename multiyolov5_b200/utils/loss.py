@@ -168,6 +168,44 @@ class ComputeLoss:
         return loss * bs, torch.cat((lbox, lobj, lcls, loss)).detach()
 
 
+class FusedComputeLoss:
+    """`ComputeLoss` forward + backward in four launches of libmyolo_sm100a (`myolo_det_loss`, csrc/detloss.cu): same arithmetic as the class
+    above (which stays the oracle of tests/test_gpu_train.py::test_fused_det_loss_matches_torch_formulation and the fallback for focal loss /
+    positive weights / autobalance).  `__call__(p, targets, mult, scale)` returns (grads [d loss / d p_i], loss_items); the gradient is that of
+    `ComputeLoss(...)(p, targets)[0] * mult / batch * scale` with the batch factor already inside, i.e. of `loss * mult_after_bs * scale`."""
+
+    def __init__(self, model):
+        self.ref = ComputeLoss(model)
+        r = self.ref
+        self.supported = (r.gamma == 0.0 and r.cls_pw == 1.0 and r.obj_pw == 1.0 and not r.autobalance and r.nl <= 3 and r.na <= 3)
+        self._ws = None
+
+    def __call__(self, p, targets, mult=1.0, scale=None):
+        import ctypes as C
+        from .. import _lib
+        r = self.ref
+        assert self.supported and all(t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in p)
+        B, na, _, _, no = p[0].shape
+        nl = len(p)
+        ny = (C.c_int32 * nl)(*[int(t.shape[2]) for t in p])
+        nx = (C.c_int32 * nl)(*[int(t.shape[3]) for t in p])
+        L = _lib.lib()
+        need = int(L.myolo_det_loss_workspace_bytes(B, na, nl, ny, nx))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=p[0].device)
+        targets = targets.float().contiguous()
+        dp = [torch.empty_like(t) for t in p]
+        items = torch.empty(4, dtype=torch.float32, device=p[0].device)
+        vp = C.c_void_p
+        anchors = (C.c_float * (nl * na * 2))(*[float(v) for v in r.anchors.reshape(-1).tolist()])
+        balance = (C.c_float * nl)(*[float(b) for b in r.balance])
+        _lib.check(L.myolo_det_loss((vp * nl)(*[_lib.ptr(t) for t in p]), (vp * nl)(*[_lib.ptr(t) for t in dp]), _lib.ptr(targets),
+                                    int(targets.shape[0]), B, na, no, nl, ny, nx, anchors, balance, float(r.hyp["box"]), float(r.hyp["obj"]),
+                                    float(r.hyp["cls"]), float(r.hyp["anchor_t"]), float(r.gr), float(r.cp), float(r.cn), float(mult) * B,
+                                    _lib.ptr(scale), _lib.ptr(items), _lib.ptr(self._ws), need, _lib.stream_ptr()))
+        return dp, items
+
+
 class SegmentationLosses(nn.CrossEntropyLoss):
     """2-D cross entropy over (B,C,H,W) logits with ignore_index=-1; with aux=True the BiSe head's auxiliary outputs are weighted
     1 : 1.5*aux_weight : 0.5*aux_weight (aux_num=2) or 1 : aux_weight (aux_num=1), as reference utils/loss.py:235-249."""

@@ -398,3 +398,55 @@ def test_eval_after_train_forward_uses_updated_running_statistics():
     torch.cuda.synchronize()
     assert not torch.equal(z0, z1)                                  # statistics moved ...
     assert torch.equal(z1, z2)                                      # ... and the cached inference plan saw them
+
+
+@pytest.mark.parametrize("name", ["a", "empty", "edge"])
+def test_fused_det_loss_matches_reference_fixture(name):
+    """`myolo_det_loss` (csrc/detloss.cu: target assignment, CIoU / BCE losses and THEIR GRADIENTS in four launches) against the fixtures written
+    by the unmodified reference's ComputeLoss + autograd (tests/golden/loss_cases.npz: loss items and d loss / d p_i)"""
+    import json, os
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.utils.loss import FusedComputeLoss
+    g = np.load(os.path.join(synth.GOLDEN_DIR, "loss_cases.npz"))
+    hyp = json.loads(bytes(g["hyp_json"]).decode())
+    model = Model("yolov5s_city_seg.yaml")
+    model.hyp, model.gr = hyp, 1.0
+    crit = FusedComputeLoss(model)
+    assert crit.supported
+    p = [torch.from_numpy(g[f"{name}_p{i}"]).cuda().contiguous() for i in range(3)]
+    grads, items = crit(p, torch.from_numpy(g[f"{name}_targets"]).cuda())
+    torch.cuda.synchronize()
+    assert np.allclose(items.cpu().numpy(), g[f"{name}_items"], rtol=2e-5, atol=1e-6), (items.cpu().numpy(), g[f"{name}_items"])
+    for i in range(3):
+        ref = g[f"{name}_g{i}"]
+        err = np.abs(grads[i].cpu().numpy() - ref).max() / np.abs(ref).max()
+        assert err <= 2e-5, (i, err)
+
+
+def test_fused_det_loss_matches_torch_formulation_at_bench_shapes():
+    """the shapes of the train step (4 x 3 x 64x128 / 32x64 / 16x32, 80 boxes with duplicate cells) incl. loss scale and multiplier"""
+    from multiyolov5_b200.models.yolo import Model
+    from multiyolov5_b200.train import scale_hyp
+    from multiyolov5_b200.utils.loss import ComputeLoss, FusedComputeLoss
+    model = Model("yolov5s_city_seg.yaml").cuda()
+    hyp = dict(lr0=0.0015, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
+    model.hyp, model.gr = scale_hyp(hyp, nl=3, nc=10, imgsz=1024, total_batch_size=32), 1.0
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    B = 4
+    p = [torch.randn((B, 3, 512 // s, 1024 // s, 15), device="cuda", generator=gen).requires_grad_(True) for s in (8, 16, 32)]
+    rs = np.random.RandomState(3)
+    t = np.zeros((80 + 16, 6), np.float32)                       # 16 all-zero padding rows: never match
+    t[:80, 0] = np.repeat(np.arange(B), 20); t[:80, 1] = rs.randint(0, 10, 80)
+    t[:80, 2:4] = rs.uniform(0.1, 0.9, (80, 2)); t[:80, 4:6] = rs.uniform(0.02, 0.22, (80, 2))
+    t[10:14, 2:6] = t[10, 2:6]                                   # identical boxes in one image: several candidates share cells
+    t[10:14, 0] = t[10, 0]
+    tg = torch.from_numpy(t).cuda()
+    scale = torch.full((), 1024.0, device="cuda")
+    loss, items = ComputeLoss(model)(p, tg)
+    (loss * 8 * 0.6 * scale).backward()
+    grads, fitems = FusedComputeLoss(model)([q.detach() for q in p], tg, mult=8 * 0.6, scale=scale)
+    torch.cuda.synchronize()
+    assert torch.allclose(fitems, items, rtol=2e-5, atol=1e-6), (fitems, items)
+    for q, gq in zip(p, grads):
+        err = float((gq - q.grad).abs().max() / q.grad.abs().max())
+        assert err <= 5e-5, err

@@ -71,3 +71,8 @@ for e in st:
 print("# bucket(ms)  kernel-time/wall  top kernels")
 for k in range(nb):
     print(f"{k * B / 1000:6.1f}  {load[k] / B:5.2f}  " + ", ".join(f"{n}:{t:.0f}" for n, t in names[k].most_common(3)))
+
+print("# individual launches of selected kernels (start us, duration us, grid):")
+for e in st:
+    if any(k in e["name"] for k in ("conv_simt", "spp_bwd", "seg_ce", "zero_stuff")):
+        print(f"{e['ts'] - t0:9.0f} {e['dur']:7.1f} grid{e['args'].get('grid')} {e['name'].replace('myolo::', '')[:60]}")
