@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/myolo.h"
@@ -41,6 +42,32 @@ extern thread_local int64_t g_launch_count;
   } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch for the small kernels of the training chains (~1350 launches per step, most of them 5-15 us): the kernel may be
+// scheduled while its stream predecessor is still running, which takes the ~2 us launch latency off the critical path.  A kernel launched
+// through launch_pdl() MUST call pdl_enter() before it touches memory (its predecessor's output is only visible after the wait).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MYOLO_NO_PDL");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 static inline int64_t align_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 
 // A resolved NHWC tensor slice on the device.
@@ -57,6 +84,10 @@ struct TensorView {
 // device-side PTX wrappers
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
 __device__ __forceinline__ bool elect_one() {

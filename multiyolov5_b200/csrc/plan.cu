@@ -408,7 +408,10 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
       MYOLO_REQUIRE(op.aux[0] >= 0 && op.aux[0] < (int)pl->bns.size() && pl->bns[op.aux[0]].set, "op %d: BN slot %d not set", i, op.aux[0]);
       const BnParams& bn = pl->bns[op.aux[0]];
       if ((int)pl->bn_stats.size() <= i) pl->bn_stats.resize(pl->ops.size(), nullptr);
-      if (!pl->bn_stats[i]) MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], (4 * (size_t)bn.C + 4) * sizeof(float)));
+      if (!pl->bn_stats[i]) {     // [mean, invstd | sums (kept zero between launches) | final sums of the backward | ticket]
+        MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], (6 * (size_t)bn.C + 4) * sizeof(float)));
+        MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->bn_stats[i], 0, (6 * (size_t)bn.C + 4) * sizeof(float), s));
+      }
       if ((rc = launch_bn_stats(in, bn, pl->bn_stats[i], pl->bn_stats[i] + 2 * bn.C, s))) return rc;
       return launch_bn_act_fwd(in, has_res ? &in2 : nullptr, out, bn, pl->bn_stats[i], op.act, s);
     }

@@ -93,9 +93,10 @@ template <int MODE>
 __global__ void __launch_bounds__(256) chan_reduce_v_kernel(TensorView a, TensorView bview, const float* __restrict__ stats,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta, int act,
                                                             float* out, long npix, int C, BnParams bn, float* stats_out,
-                                                            unsigned* ticket) {
+                                                            unsigned* ticket, float* final_out) {
   __shared__ float sh[2][2048];
   __shared__ int is_last;
+  pdl_enter();
   const int nv = C >> 3, lanes = 256 / nv;
   const int t = threadIdx.x;
   const bool active = t < lanes * nv;
@@ -144,8 +145,14 @@ __global__ void __launch_bounds__(256) chan_reduce_v_kernel(TensorView a, Tensor
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  // the last block consumes the sums and leaves accumulators + ticket ZERO for the next launch on this scratch (allocated zeroed): no
+  // memset node between the producing conv and this kernel, so the programmatic-launch edge survives
+  if (t == 0) *ticket = 0u;
   for (int c = t; c < C; c += 256) {
     const float x0 = __ldcg(out + c), x1 = __ldcg(out + C + c);
+    out[c] = 0.f;
+    out[C + c] = 0.f;
+    if (final_out) { final_out[c] = x0; final_out[C + c] = x1; }
     if (MODE == 0) {
       const float n = (float)npix;
       const float mean = x0 / n;
@@ -185,24 +192,27 @@ __global__ void bn_finalize_kernel(float* sums, float* stats, BnParams bn, long 
 int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s) {
   MYOLO_REQUIRE(u.dtype == MYOLO_F16 && bn.set && bn.C == u.C, "bn_stats: bad view / BN parameters not set");
   const long npix = (long)u.B * u.H * u.W;
-  // scratch: 2*C sums followed by the completion ticket
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C + 1) * sizeof(float), s));
+  // scratch (zero on entry, left zero by the kernel): 2*C sums, 2*C final sums (backward), the completion ticket
   if (u.C % 8 == 0 && u.C <= 2048 && u.ctot % 8 == 0) {
-    chan_reduce_v_kernel<0><<<reduce_v_grid(npix, u.C), 256, 0, s>>>(u, u, nullptr, nullptr, nullptr, 0, scratch, npix, u.C, bn, stats,
-                                                                    reinterpret_cast<unsigned*>(scratch + 2 * u.C));
-    MYOLO_LAUNCH_CHECK();
+    MYOLO_CHECK_CUDA(launch_pdl(chan_reduce_v_kernel<0>, dim3(reduce_v_grid(npix, u.C)), dim3(256), 0, s, u, u, (const float*)nullptr,
+                                (const float*)nullptr, (const float*)nullptr, 0, scratch, npix, u.C, bn, stats,
+                                reinterpret_cast<unsigned*>(scratch + 4 * u.C), (float*)nullptr));
+    g_launch_count++;
     return 0;
   }
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C) * sizeof(float), s));
   dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
   chan_reduce_kernel<0><<<g, 256, 0, s>>>(u, u, nullptr, nullptr, nullptr, 0, scratch, npix, u.C);
   MYOLO_LAUNCH_CHECK();
   bn_finalize_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, stats, bn, npix);
   MYOLO_LAUNCH_CHECK();
+  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C) * sizeof(float), s));    // contract of the scratch: zero between launches
   return 0;
 }
 
 __global__ void bn_act_fwd_kernel(TensorView u, TensorView res, bool has_res, TensorView y, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const float* __restrict__ stats, int act) {
+  pdl_enter();
   const long total = (long)u.B * u.H * u.W * (u.C / 8);
   const int nv = u.C / 8, C = u.C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -230,15 +240,16 @@ int launch_bn_act_fwd(const TensorView& u, const TensorView* res, const TensorVi
                       cudaStream_t s) {
   MYOLO_REQUIRE(u.C % 8 == 0 && u.C == y.C && u.ctot % 8 == 0 && y.ctot % 8 == 0 && (!res || (res->C == u.C && res->ctot % 8 == 0)),
                 "bn_act_fwd: bad views");
-  bn_act_fwd_kernel<<<grid_for_t((long)u.B * u.H * u.W * (u.C / 8), 256), 256, 0, s>>>(u, res ? *res : u, res != nullptr, y, bn.gamma, bn.beta,
-                                                                                     stats, act);
-  MYOLO_LAUNCH_CHECK();
+  MYOLO_CHECK_CUDA(launch_pdl(bn_act_fwd_kernel, dim3(grid_for_t((long)u.B * u.H * u.W * (u.C / 8), 256)), dim3(256), 0, s, u, res ? *res : u,
+                              res != nullptr, y, (const float*)bn.gamma, (const float*)bn.beta, stats, act));
+  g_launch_count++;
   return 0;
 }
 
 __global__ void bn_act_bwd_kernel(TensorView u, TensorView dy, TensorView du, TensorView dres, bool has_res, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const float* __restrict__ stats, const float* __restrict__ sums, int act,
                                   float inv_n) {
+  pdl_enter();
   const long total = (long)u.B * u.H * u.W * (u.C / 8);
   const int nv = u.C / 8, C = u.C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -302,21 +313,25 @@ int launch_bn_act_bwd(const TensorView& u, const TensorView& dy, const TensorVie
   MYOLO_REQUIRE(u.C % 8 == 0 && dy.C == u.C && du.C == u.C && dy.ctot % 8 == 0 && du.ctot % 8 == 0 && u.ctot % 8 == 0, "bn_act_bwd: bad views");
   MYOLO_REQUIRE(!d_res || (d_res->C == u.C && d_res->ctot % 8 == 0), "bn_act_bwd: bad residual gradient view");
   const long npix = (long)u.B * u.H * u.W;
-  MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C + 1) * sizeof(float), s));
+  const float* sums = scratch;
   if (u.C <= 2048) {
-    chan_reduce_v_kernel<1><<<reduce_v_grid(npix, u.C), 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C, bn, nullptr,
-                                                                    reinterpret_cast<unsigned*>(scratch + 2 * u.C));
-    MYOLO_LAUNCH_CHECK();
+    MYOLO_CHECK_CUDA(launch_pdl(chan_reduce_v_kernel<1>, dim3(reduce_v_grid(npix, u.C)), dim3(256), 0, s, u, dy, stats, (const float*)bn.gamma,
+                                (const float*)bn.beta, act, scratch, npix, u.C, bn, (float*)nullptr,
+                                reinterpret_cast<unsigned*>(scratch + 4 * u.C), scratch + 2 * u.C));
+    g_launch_count++;
+    sums = scratch + 2 * u.C;            // the reduce kernel leaves its accumulators zero and hands the totals over here
   } else {
+    MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C) * sizeof(float), s));
     dim3 g(ceil_div(u.C, 32), (unsigned)std::min<long>(256, std::max<long>(1, npix / 256)));
     chan_reduce_kernel<1><<<g, 256, 0, s>>>(u, dy, stats, bn.gamma, bn.beta, act, scratch, npix, u.C);
     MYOLO_LAUNCH_CHECK();
     bn_param_grad_kernel<<<ceil_div(u.C, 128), 128, 0, s>>>(scratch, bn);
     MYOLO_LAUNCH_CHECK();
   }
-  bn_act_bwd_kernel<<<grid_for_t(npix * (u.C / 8), 256), 256, 0, s>>>(u, dy, du, d_res ? *d_res : du, d_res != nullptr, bn.gamma, bn.beta, stats,
-                                                                     scratch, act, 1.0f / (float)npix);
-  MYOLO_LAUNCH_CHECK();
+  MYOLO_CHECK_CUDA(launch_pdl(bn_act_bwd_kernel, dim3(grid_for_t(npix * (u.C / 8), 256)), dim3(256), 0, s, u, dy, du, d_res ? *d_res : du,
+                              d_res != nullptr, (const float*)bn.gamma, (const float*)bn.beta, stats, sums, act, 1.0f / (float)npix));
+  g_launch_count++;
+  if (sums == scratch) MYOLO_CHECK_CUDA(cudaMemsetAsync(scratch, 0, (2 * (size_t)u.C) * sizeof(float), s));   // (> 2048 channels: generic path)
   return 0;
 }
 
@@ -916,6 +931,7 @@ int launch_zero_stuff2(const TensorView& src, const TensorView& dst, cudaStream_
 
 // dgrad weights: W'[ci][tap'][co] = W[co][ci][k*k-1-tap']   (fp16, [Ci_pad_out][k*k][Co_pad_in]); zero bias of length Ci_pad_out
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, int co, int ci, int k, __half* wp, float* zb, int ci_pad_out, int co_pad_in) {
+  pdl_enter();
   const int taps = k * k;
   const long total = (long)ci_pad_out * taps * co_pad_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -929,8 +945,9 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, int co, int ci, i
   for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ci_pad_out; c += gridDim.x * blockDim.x) zb[c] = 0.f;
 }
 int pack_dgrad_weights(const float* w, int co, int ci, int k, __half* wp, float* zero_bias, int ci_pad_out, int co_pad_in, cudaStream_t s) {
-  pack_dgrad_kernel<<<grid_for_t((long)ci_pad_out * k * k * co_pad_in, 256, 4096), 256, 0, s>>>(w, co, ci, k, wp, zero_bias, ci_pad_out, co_pad_in);
-  MYOLO_LAUNCH_CHECK();
+  MYOLO_CHECK_CUDA(launch_pdl(pack_dgrad_kernel, dim3(grid_for_t((long)ci_pad_out * k * k * co_pad_in, 256, 4096)), dim3(256), 0, s, w, co, ci, k,
+                              wp, zero_bias, ci_pad_out, co_pad_in));
+  g_launch_count++;
   return 0;
 }
 

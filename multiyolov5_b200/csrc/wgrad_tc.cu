@@ -74,6 +74,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   const int row1 = min(p.rows_total, row0 + p.rows_per_cta);
   const int n_steps = (row1 - row0) * p.steps_per_row;
 
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");      // programmatic dependent launch: see common.cuh launch_pdl
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.num_stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(acc_full, 1);
@@ -86,6 +87,9 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // dY, X and the packed accumulation buffer come from predecessor kernels: every thread waits (the epilogue's red.global.add must not
+  // race a predecessor's unpack of the same buffer)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // producer / MMA roles run warp-converged with one elected issuing lane (descriptor arithmetic stays in uniform registers; see conv_tc.cu)
   if (warp == 0) {
@@ -185,6 +189,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_cons
 
 // dW[co][ci][t] += packed[co][t][ci]; packed = 0
 __global__ void wgrad_unpack_kernel(float* __restrict__ packed, float* __restrict__ dW, int co, int ci, int ci_pad, int taps) {
+  pdl_enter();
   const long total = (long)co * ci_pad * taps;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % ci_pad);
@@ -294,10 +299,11 @@ int launch_conv_wgrad_tc(const TensorView& x, const TensorView& dy, int k, int s
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_wgrad_tc_kernel<<<dim3(items, slabs), kWgThreads, smem, s>>>(tmDy, tmX[0], tmX[1], tmX[2], tmX[3], p);
+  MYOLO_CHECK_CUDA(launch_pdl(conv_wgrad_tc_kernel, dim3(items, slabs), dim3(kWgThreads), (size_t)smem, s, tmDy, tmX[0], tmX[1], tmX[2], tmX[3], p));
   MYOLO_LAUNCH_CHECK();
   if (!direct) {
-    wgrad_unpack_kernel<<<std::min(148 * 8, ceil_div(co * cp * k * k, 256)), 256, 0, s>>>(dw_packed, dW, co, ci, cp, k * k);
+    MYOLO_CHECK_CUDA(launch_pdl(wgrad_unpack_kernel, dim3(std::min(148 * 8, ceil_div(co * cp * k * k, 256))), dim3(256), 0, s, dw_packed, dW, co, ci,
+                                cp, k * k));
     MYOLO_LAUNCH_CHECK();
   }
   return 0;

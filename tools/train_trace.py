@@ -16,21 +16,20 @@ for i in range(5):
 torch.cuda.synchronize()
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(2):
+    for i in range(4):          # back to back (no synchronisation): the CPU runs ahead as it does in training; step 2 of 4 is analysed
         step(i)
-        torch.cuda.synchronize()
+    torch.cuda.synchronize()
 f = tempfile.mktemp(suffix=".json")
 prof.export_chrome_trace(f)
 ev = [e for e in json.load(open(f))["traceEvents"] if e.get("cat") == "kernel"]
 ev.sort(key=lambda e: e["ts"])
-steps, cur = [], [ev[0]]
-for a, b in zip(ev, ev[1:]):
-    if b["ts"] - (a["ts"] + a["dur"]) > 400:
-        steps.append(cur); cur = []
-    cur.append(b)
-steps.append(cur)
-st = max(steps, key=len)
-t0 = st[0]["ts"]; end = max(e["ts"] + e["dur"] for e in st)
+# a step ends with its sgd_step_kernel: cut there
+ends = [i for i, e in enumerate(ev) if "sgd_step_kernel" in e["name"]]
+assert len(ends) >= 3, len(ends)
+t_lo = ev[ends[1]]["ts"] + ev[ends[1]]["dur"]
+t_hi = ev[ends[2]]["ts"] + ev[ends[2]]["dur"]
+st = [e for e in ev if t_lo <= e["ts"] < t_hi]
+t0 = t_lo; end = t_hi
 iv = sorted((e["ts"], e["ts"] + e["dur"]) for e in st)
 cov, cs, ce = 0.0, iv[0][0], iv[0][1]
 for a, b in iv[1:]:
