@@ -931,7 +931,9 @@ int launch_zero_stuff2(const TensorView& src, const TensorView& dst, cudaStream_
 
 // dgrad weights: W'[ci][tap'][co] = W[co][ci][k*k-1-tap']   (fp16, [Ci_pad_out][k*k][Co_pad_in]); zero bias of length Ci_pad_out
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, int co, int ci, int k, __half* wp, float* zb, int ci_pad_out, int co_pad_in) {
-  pdl_enter();
+  // waits for its predecessor but does NOT release its dependents early: the data-gradient conv that may follow fetches these weights
+  // BEFORE its own dependency wait (weights are constants for every other predecessor)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int taps = k * k;
   const long total = (long)ci_pad_out * taps * co_pad_in;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
