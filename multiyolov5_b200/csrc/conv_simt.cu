@@ -98,11 +98,17 @@ __device__ __forceinline__ void conv_simt_body(const SimtParams& p) {
 }
 
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) { conv_simt_body<TIn>(p); }
+__global__ void __launch_bounds__(256) conv_simt_kernel(SimtParams p) {
+  pdl_enter();
+  conv_simt_body<TIn>(p);
+}
 // up to 4 small convolutions of the same input type in ONE launch (the 1x1 convs on the pooled bins of PyramidPooling): blockIdx.y = member
 struct SimtGroup { SimtParams p[4]; };
 template <typename TIn>
-__global__ void __launch_bounds__(256) conv_simt_group_kernel(SimtGroup g) { conv_simt_body<TIn>(g.p[blockIdx.y]); }
+__global__ void __launch_bounds__(256) conv_simt_group_kernel(SimtGroup g) {
+  pdl_enter();
+  conv_simt_body<TIn>(g.p[blockIdx.y]);
+}
 
 static int fill_simt_params(const ConvOp& op, SimtParams& p) {
   p.in = op.in.base; p.in_ctot = op.in.ctot; p.H = op.in.H; p.W = op.in.W; p.Ci = op.Ci_pad;
@@ -126,8 +132,8 @@ int conv_simt_launch_group(const ConvOp* const* ops, int n, cudaStream_t stream)
     most = std::max(most, ((long)g.p[i].B * g.p[i].Ho * g.p[i].Wo * ((g.p[i].Co + 7) / 8) + 7) / 8);
   }
   if (most > 148 * 16) most = 148 * 16;
-  if (ops[0]->in.dtype == MYOLO_F16) conv_simt_group_kernel<__half><<<dim3((int)most, n), 256, 0, stream>>>(g);
-  else conv_simt_group_kernel<float><<<dim3((int)most, n), 256, 0, stream>>>(g);
+  if (ops[0]->in.dtype == MYOLO_F16) MYOLO_CHECK_CUDA(launch_pdl(conv_simt_group_kernel<__half>, dim3((int)most, n), dim3(256), 0, stream, g));
+  else MYOLO_CHECK_CUDA(launch_pdl(conv_simt_group_kernel<float>, dim3((int)most, n), dim3(256), 0, stream, g));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -146,8 +152,8 @@ int conv_simt_launch(const ConvOp& op, cudaStream_t stream) {
   long blocks = (warps + 7) / 8;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  if (op.in.dtype == MYOLO_F16) conv_simt_kernel<__half><<<(int)blocks, 256, 0, stream>>>(p);
-  else conv_simt_kernel<float><<<(int)blocks, 256, 0, stream>>>(p);
+  if (op.in.dtype == MYOLO_F16) MYOLO_CHECK_CUDA(launch_pdl(conv_simt_kernel<__half>, dim3((int)blocks), dim3(256), 0, stream, p));
+  else MYOLO_CHECK_CUDA(launch_pdl(conv_simt_kernel<float>, dim3((int)blocks), dim3(256), 0, stream, p));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }

@@ -86,6 +86,7 @@ int launch_input_focus(const void* x, int x_dtype, int B, int H, int W, const Te
 // nearest x2 (yaml layers 11, 15)
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample_nearest2x_kernel(TensorView in, TensorView out) {
+  pdl_enter();
   const RowIdx r = row_index(out.W, out.C / 8);
   if (!r.ok) return;
   const uint4 val = __ldg(reinterpret_cast<const uint4*>(vptr(in, r.b, r.y >> 1, r.x >> 1)) + r.v);
@@ -94,7 +95,7 @@ __global__ void upsample_nearest2x_kernel(TensorView in, TensorView out) {
 int launch_upsample_nearest2x(const TensorView& in, const TensorView& out, cudaStream_t s) {
   MYOLO_REQUIRE(out.H == 2 * in.H && out.W == 2 * in.W && in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0,
                 "upsample_nearest2x: bad views");
-  upsample_nearest2x_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(in, out);
+  MYOLO_CHECK_CUDA(launch_pdl(upsample_nearest2x_kernel, row_grid(out, out.C / 8), dim3(256), 0, s, in, out));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -114,6 +115,7 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 }
 
 __global__ void spp_pool_kernel(TensorView in, TensorView out, int n_cascade) {
+  pdl_enter();
   extern __shared__ uint4 spp_smem[];
   const int HW = in.H * in.W;
   uint4* cur = spp_smem;
@@ -189,7 +191,7 @@ int launch_spp_pool(const TensorView& in, const TensorView& out5, int n_cascade,
     MYOLO_CHECK_CUDA(cudaFuncSetAttribute(spp_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
-  spp_pool_kernel<<<in.B * (in.C / 8), 256, smem, s>>>(in, out5, n_cascade);
+  MYOLO_CHECK_CUDA(launch_pdl(spp_pool_kernel, dim3(in.B * (in.C / 8)), dim3(256), (size_t)smem, s, in, out5, n_cascade));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -234,10 +236,12 @@ __device__ __forceinline__ void bilinear_nhwc_body(const TensorView& in, const T
     ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
   reinterpret_cast<uint4*>(vptr(out, b, r.y, r.x))[v] = o;
 }
-__global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) { bilinear_nhwc_body(in, out, row_index(out.W, out.C / 8)); }
+__global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
+  pdl_enter(); bilinear_nhwc_body(in, out, row_index(out.W, out.C / 8)); }
 // up to 4 independent resamplings with identical output extents in ONE launch (the four levels of PyramidPooling): blockIdx.y = level*H + y
 struct BilinearGroup { TensorView in[4], out[4]; int n; };
 __global__ void bilinear_nhwc_group_kernel(BilinearGroup g) {
+  pdl_enter();
   const int H = g.out[0].H;
   const int level = blockIdx.y / H;
   RowIdx r = row_index(g.out[0].W, g.out[0].C / 8);
@@ -257,7 +261,7 @@ int launch_bilinear_nhwc_group(const TensorView* in, const TensorView* out, int 
   }
   dim3 grid = row_grid(out[0], out[0].C / 8);
   grid.y *= n;
-  bilinear_nhwc_group_kernel<<<grid, 256, 0, s>>>(g);
+  MYOLO_CHECK_CUDA(launch_pdl(bilinear_nhwc_group_kernel, grid, dim3(256), 0, s, g));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -265,7 +269,7 @@ int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream
   MYOLO_REQUIRE(in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0 && in.dtype == MYOLO_F16 &&
                     out.dtype == MYOLO_F16,
                 "bilinear_nhwc: bad views");
-  bilinear_nhwc_kernel<<<row_grid(out, out.C / 8), 256, 0, s>>>(in, out);
+  MYOLO_CHECK_CUDA(launch_pdl(bilinear_nhwc_kernel, row_grid(out, out.C / 8), dim3(256), 0, s, in, out));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -277,6 +281,7 @@ int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream
 // ------------------------------------------------------------------------------------------------
 __global__ void region_sum_kernel(TensorView in, const int* __restrict__ yb, int ny, const int* __restrict__ xb, int nx,
                                   TensorView out) {
+  pdl_enter();
   __shared__ float red[256 * 8];
   const int atom = blockIdx.x % (ny * nx);
   const int b = blockIdx.x / (ny * nx);
@@ -317,7 +322,7 @@ int launch_region_sum(const TensorView& in, const int* d_yb, int ny, const int* 
   MYOLO_REQUIRE(in.dtype == MYOLO_F16 && out.dtype == MYOLO_F32 && in.C % 8 == 0 && in.C / 8 <= 256 && out.C == in.C &&
                     out.H == ny && out.W == nx && in.ctot % 8 == 0,
                 "region_sum: bad views");
-  region_sum_kernel<<<in.B * ny * nx, 256, 0, s>>>(in, d_yb, ny, d_xb, nx, out);
+  MYOLO_CHECK_CUDA(launch_pdl(region_sum_kernel, dim3(in.B * ny * nx), dim3(256), 0, s, in, d_yb, ny, d_xb, nx, out));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -340,11 +345,13 @@ __device__ __forceinline__ void region_combine_body(const TensorView& atoms, con
   }
 }
 __global__ void region_combine_kernel(TensorView atoms, const int* __restrict__ bins, int nbins, TensorView out) {
+  pdl_enter();
   region_combine_body(atoms, bins, nbins, out, blockIdx.x * (long)blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
 }
 // the pooling levels of one pyramid in ONE launch: blockIdx.y = level
 struct CombineGroup { const int* bins[4]; int nbins[4]; TensorView out[4]; };
 __global__ void region_combine_group_kernel(TensorView atoms, CombineGroup g) {
+  pdl_enter();
   const int l = blockIdx.y;
   region_combine_body(atoms, g.bins[l], g.nbins[l], g.out[l], blockIdx.x * (long)blockDim.x + threadIdx.x, (long)gridDim.x * blockDim.x);
 }
@@ -358,7 +365,7 @@ int launch_region_combine_group(const TensorView& atoms, int atoms_nx, const int
     g.bins[i] = d_bins[i]; g.nbins[i] = nbins[i]; g.out[i] = out[i];
     most = std::max(most, (long)out[i].B * nbins[i] * out[i].C);
   }
-  region_combine_group_kernel<<<dim3(grid_for(most, 256), n), 256, 0, s>>>(atoms, g);
+  MYOLO_CHECK_CUDA(launch_pdl(region_combine_group_kernel, dim3(grid_for(most, 256), n), dim3(256), 0, s, atoms, g));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -366,7 +373,7 @@ int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bi
                           cudaStream_t s) {
   MYOLO_REQUIRE(atoms.dtype == MYOLO_F32 && out.H * out.W == nbins && atoms.C == out.C && atoms.W == atoms_nx,
                 "region_combine: bad views");
-  region_combine_kernel<<<grid_for((long)out.B * nbins * out.C, 256), 256, 0, s>>>(atoms, d_bins, nbins, out);
+  MYOLO_CHECK_CUDA(launch_pdl(region_combine_kernel, dim3(grid_for((long)out.B * nbins * out.C, 256)), dim3(256), 0, s, atoms, d_bins, nbins, out));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }
@@ -375,6 +382,7 @@ int launch_region_combine(const TensorView& atoms, int atoms_nx, const int* d_bi
 // FFM: feat = feat*att + feat (in place); att is a (B,1,1,C) map (reference models/common.py:228-229)
 // ------------------------------------------------------------------------------------------------
 __global__ void channel_scale_kernel(TensorView feat, TensorView att) {
+  pdl_enter();
   const RowIdx r = row_index(feat.W, feat.C / 8);
   if (!r.ok) return;
   uint4* ptr = reinterpret_cast<uint4*>(vptr(feat, r.b, r.y, r.x)) + r.v;
@@ -391,7 +399,7 @@ __global__ void channel_scale_kernel(TensorView feat, TensorView att) {
 int launch_channel_scale(const TensorView& feat, const TensorView& att, cudaStream_t s) {
   MYOLO_REQUIRE(feat.dtype == MYOLO_F16 && feat.C % 8 == 0 && feat.ctot % 8 == 0 && att.C == feat.C && att.H == 1 && att.W == 1,
                 "channel_scale: bad views");
-  channel_scale_kernel<<<row_grid(feat, feat.C / 8), 256, 0, s>>>(feat, att);
+  MYOLO_CHECK_CUDA(launch_pdl(channel_scale_kernel, row_grid(feat, feat.C / 8), dim3(256), 0, s, feat, att));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }

@@ -23,6 +23,9 @@ def aggregate_throughput(images_local: int, ms_local: float, device=None) -> flo
     return float(n.item() / (t.item() * 1e-3))
 
 
+LAST_ALLREDUCE_PATH = "none"      # which route the last allreduce_flat_grads took (reported by bench.py's train record)
+
+
 def nccl_comm_ptr(group=None, device=None):
     """the raw ncclComm_t of the process group's NCCL backend (what the C ABI's myolo_allreduce_grads takes), or None (gloo / no comm yet)"""
     try:
@@ -45,10 +48,13 @@ def allreduce_flat_grads(flat_grad: torch.Tensor, group=None, stream=None) -> in
     world = dist.get_world_size(group)
     if world > 1:
         comm = nccl_comm_ptr(group, flat_grad.device) if flat_grad.is_cuda and dist.get_backend(group) == "nccl" else None
+        global LAST_ALLREDUCE_PATH
         if comm is not None:
             from . import _lib
             sp = stream.cuda_stream if stream is not None else _lib.stream_ptr()
             _lib.check(_lib.lib().myolo_allreduce_grads(_lib.ptr(flat_grad), flat_grad.numel(), comm, sp))
+            LAST_ALLREDUCE_PATH = "myolo_allreduce_grads (ncclAllReduce on torch's communicator, issued by libmyolo_sm100a)"
         else:
             dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+            LAST_ALLREDUCE_PATH = f"torch.distributed.all_reduce ({dist.get_backend(group)})"
     return world

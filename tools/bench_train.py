@@ -74,6 +74,11 @@ def timed_steps(step, steps, world):
     return float(t.item())
 
 
+def _ar_path():
+    from multiyolov5_b200 import parallel
+    return parallel.LAST_ALLREDUCE_PATH
+
+
 def train_record(world, rank, steps=10, warmup=3, B=4, min_seconds=1.0, with_reference_gpu=False):
     """the `train` sub-record of bench.py's JSON line (BASELINE.json configs[3]): step time, whole-job images/s, the all-reduce's own time,
     and a >= min_seconds sustained run next to the short one"""
@@ -104,7 +109,7 @@ def train_record(world, rank, steps=10, warmup=3, B=4, min_seconds=1.0, with_ref
            "sustained": {"steps": n_long, "seconds": ms_long * 1e-3, "ms_per_step": ms_long / n_long,
                          "images_per_s": 2 * B * world * n_long / (ms_long * 1e-3)},
            "allreduce_ms": ar_ms, "allreduce_mbytes": tr.flat.n * 4 / 1e6, "allreduce_share_of_step": ar_ms / (ms / steps) if world > 1 else 0.0,
-           "collective": "NCCL all-reduce (sum) of the flat fp32 gradient buffer, averaging folded into the optimiser" if world > 1 else "none (1 GPU)",
+           "collective": ("all-reduce (sum) of the flat fp32 gradient buffer, averaging folded into the optimiser; route: " + _ar_path()) if world > 1 else "none (1 GPU)",
            "conv_tflops_algorithmic": flops / (ms / steps * 1e-3) / 1e12, "dtype": "f16 storage / f32 accumulate, fp32 master weights",
            "loss_scale": float(tr.scale)}
     if with_reference_gpu and rank == 0:
