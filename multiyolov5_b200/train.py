@@ -93,7 +93,7 @@ class Trainer:
         model.train()
         self.compute_loss = ComputeLoss(model)
         # detection loss forward + backward as four launches of the library (csrc/detloss.cu) instead of ~760 torch kernels; the torch
-        # formulation stays for focal loss / positive weights / autobalance and as the test oracle
+        # formulation stays for focal loss / positive weights / autobalance and is what the tests compare it with
         self._fused_det = FusedComputeLoss(model) if fused_det_loss else None
         self.fused_det_loss = bool(fused_det_loss) and self._fused_det.supported
         self.n_seg_outputs = 3 if type(model.model[-2]).__name__ == "SegMaskBiSe" else 1
