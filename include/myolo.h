@@ -115,6 +115,10 @@ void myolo_plan_destroy(myolo_plan* plan);
 int myolo_plan_set_conv_weights(myolo_plan* plan, int weight_slot, const float* w, int co, int ci, int k,
                                 const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                                 const float* bias, void* stream);
+/* Re-packs EVERY slot from the pointers the last myolo_plan_set_conv_weights calls registered, in one launch (training: the fp32
+ * parameters changed in place - optimizer.step() reference train.py:396-398 - and every fp16 copy, forward and data-gradient, follows).
+ * The pointers must still be valid; call myolo_plan_set_conv_weights again for a slot whose tensors moved. */
+int myolo_plan_repack_weights(myolo_plan* plan, void* stream);
 /* One forward pass.  x: (B,3,H,W) NCHW of x_dtype (F32/F16 in [0,1], or U8 scaled by 1/255 like detect.py:137).
  * z: (B, sum_i 3*ny_i*nx_i, 5+nc) fp32;  raw[i]: (B,3,ny_i,nx_i,5+nc) fp32 (nullable);
  * seg: (B,n_segcls,H,W) of seg_dtype (nullable); seg_argmax: (B,H,W) int64 class ids (nullable, fused path). */

@@ -68,6 +68,20 @@ int conv_simt_launch(const ConvOp& op, cudaStream_t stream);
 int conv_simt_launch_group(const ConvOp* const* ops, int n, cudaStream_t stream);   // <= 4 small convs of one input type in one launch
 
 // weight packing: fp32 [Co][Ci][k][k] (+BN) -> fp16 [Co_pad][k*k][Ci_pad], bias fp32 [Co_pad]
+// one job of the grouped weight pack (conv_simt.cu pack_group_kernel)
+static constexpr int kPackChunk = 2048;
+struct PackJob {
+  const float* w;
+  const float *gamma, *beta, *mean, *var, *bias;
+  __half* wp;
+  float* bp;
+  int co, ci, k;
+  int n_pad, c_pad;      // kind 0: (co_pad, ci_pad);  kind 1: (ci_pad_out, co_pad_in)
+  float eps;
+  int kind;
+  int chunk0;            // first chunk (= block) of this job
+};
+int pack_group_launch(const PackJob* d_jobs, int n_jobs, int total_chunks, cudaStream_t stream);
 int pack_conv_weights(const float* w, int co, int ci, int k, const float* gamma, const float* beta, const float* mean,
                       const float* var, float eps, const float* bias, __half* wp, float* bp, int co_pad, int ci_pad,
                       cudaStream_t stream);

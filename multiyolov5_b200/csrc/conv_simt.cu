@@ -187,6 +187,57 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int co, int ci,
   }
 }
 
+// every weight pack of a plan in ONE launch (training repacks all fp16 copies after each optimiser step: ~280 tiny launches otherwise).
+// A job is a forward pack (kind 0: [co_pad][taps][ci_pad], BN fold optional, bias vector) or a data-gradient pack (kind 1:
+// W'[ci][tap'][co] = W[co][ci][taps-1-tap'], zero bias); block b handles chunk b of kPackChunk elements, jobs found by binary search
+// over the chunk prefix.
+__global__ void __launch_bounds__(256) pack_group_kernel(const PackJob* __restrict__ jobs, int n_jobs) {
+  int lo = 0, hi = n_jobs - 1;
+  const int b = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].chunk0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const PackJob j = jobs[lo];
+  const int taps = j.k * j.k;
+  const long total = (long)j.n_pad * taps * j.c_pad;
+  const long base = (long)(b - j.chunk0) * kPackChunk;
+  for (int e = threadIdx.x; e < kPackChunk; e += 256) {
+    const long i = base + e;
+    if (i >= total) break;
+    const int c = (int)(i % j.c_pad);
+    const int t = (int)((i / j.c_pad) % taps);
+    const int n = (int)(i / ((long)j.c_pad * taps));
+    float v = 0.f;
+    if (j.kind == 0) {            // n = output channel, c = input channel
+      if (n < j.co && c < j.ci) {
+        v = j.w[((size_t)n * j.ci + c) * taps + t];
+        if (j.gamma) v *= j.gamma[n] / sqrtf(j.var[n] + j.eps);
+      }
+    } else {                      // n = input channel (the data gradient's output), c = output channel
+      if (n < j.ci && c < j.co) v = j.w[((size_t)c * j.ci + n) * taps + (taps - 1 - t)];
+    }
+    j.wp[i] = __float2half_rn(v);
+  }
+  if (b == j.chunk0) {
+    for (int o = threadIdx.x; o < j.n_pad; o += 256) {
+      float bv = 0.f;
+      if (j.kind == 0 && o < j.co) {
+        if (j.gamma) bv = j.beta[o] - j.gamma[o] * j.mean[o] / sqrtf(j.var[o] + j.eps);
+        if (j.bias) bv += j.gamma ? j.bias[o] * j.gamma[o] / sqrtf(j.var[o] + j.eps) : j.bias[o];
+      }
+      j.bp[o] = bv;
+    }
+  }
+}
+
+int pack_group_launch(const PackJob* d_jobs, int n_jobs, int total_chunks, cudaStream_t stream) {
+  if (n_jobs <= 0 || total_chunks <= 0) return 0;
+  pack_group_kernel<<<total_chunks, 256, 0, stream>>>(d_jobs, n_jobs);
+  MYOLO_LAUNCH_CHECK();
+  return 0;
+}
+
 int pack_conv_weights(const float* w, int co, int ci, int k, const float* gamma, const float* beta, const float* mean,
                       const float* var, float eps, const float* bias, __half* wp, float* bp, int co_pad, int ci_pad,
                       cudaStream_t stream) {

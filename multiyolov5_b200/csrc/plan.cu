@@ -65,6 +65,8 @@ struct WeightSlot {
   bool set = false;
   // training
   const float* w_master = nullptr;   // caller's fp32 parameter (device)
+  const float *gamma = nullptr, *beta = nullptr, *mean = nullptr, *var = nullptr, *bias_master = nullptr;   // as passed to set_conv_weights
+  float eps = 0.f;
   float* d_w = nullptr;              // caller's .grad (accumulated)
   float* d_bias = nullptr;
   __half* w_dgrad = nullptr;         // flipped / transposed fp16 pack for the data gradient
@@ -120,6 +122,10 @@ struct myolo_plan {
   float* seg_outs[3] = {nullptr, nullptr, nullptr};          // train forward: extra seg outputs (index 1, 2)
   const float* grad_segs[3] = {nullptr, nullptr, nullptr};   // backward: their gradients
   bool bwd_dirty = false;
+  // grouped weight repack (myolo_plan_repack_weights): device job table over all slots, rebuilt when a pointer or pack buffer changed
+  PackJob* d_pack_jobs = nullptr;
+  int n_pack_jobs = 0, n_pack_chunks = 0, pack_jobs_cap = 0;
+  bool pack_table_dirty = true;
   unsigned long long seed = 0;       // dropout
   unsigned long long* d_step = nullptr;
   std::vector<cudaEvent_t> bwd_ev;   // per-op completion events of the multi-lane captured backward (+4 join events)
@@ -219,6 +225,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   }
   if (pl->ws) cudaFree(pl->ws);
   if (pl->d_extra) cudaFree(pl->d_extra);
+  if (pl->d_pack_jobs) cudaFree(pl->d_pack_jobs);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   for (auto& e : pl->bwd_exec) if (e) cudaGraphExecDestroy(e);
   if (pl->graph) cudaGraphDestroy(pl->graph);
@@ -265,6 +272,7 @@ extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float
     s.bias = nullptr;
     MYOLO_CHECK_CUDA(cudaMalloc(&s.w, (size_t)co_pad * k * k * ci_pad * 2));
     MYOLO_CHECK_CUDA(cudaMalloc(&s.bias, (size_t)co_pad * 4));
+    pl->pack_table_dirty = true;
     for (size_t i = 0; i < pl->ops.size(); ++i)
       if (pl->ops[i].kind == MYOLO_OP_CONV && pl->ops[i].weight_slot == slot) pl->conv_ready[i] = 0;
     pl->graph_dirty = true;
@@ -275,9 +283,59 @@ extern "C" int myolo_plan_set_conv_weights(myolo_plan* pl, int slot, const float
   s.co_pad = co_pad;
   s.ci_pad = ci_pad;
   s.set = true;
+  if (s.w_master != w || s.gamma != gamma || s.beta != beta || s.mean != mean || s.var != var || s.bias_master != bias || s.eps != eps)
+    pl->pack_table_dirty = true;
   s.w_master = w;
+  s.gamma = gamma;
+  s.beta = beta;
+  s.mean = mean;
+  s.var = var;
+  s.bias_master = bias;
+  s.eps = eps;
   s.dgrad_valid = false;
   return pack_conv_weights(w, co, ci, k, gamma, beta, mean, var, eps, bias, s.w, s.bias, co_pad, ci_pad, (cudaStream_t)stream);
+}
+
+// reference train.py:396-398 changes every parameter once per step; the fp16 copies (forward packs and, once a backward has run, the
+// flipped / transposed data-gradient packs) follow in ONE launch from the pointers myolo_plan_set_conv_weights registered
+extern "C" int myolo_plan_repack_weights(myolo_plan* pl, void* stream) {
+  NvtxRange nvtx("myolo_plan_repack_weights");
+  MYOLO_REQUIRE(pl, "repack_weights: null plan");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (pl->pack_table_dirty) {
+    std::vector<PackJob> jobs;
+    int chunk = 0;
+    for (size_t i = 0; i < pl->slots.size(); ++i) {
+      const WeightSlot& sl = pl->slots[i];
+      MYOLO_REQUIRE(sl.set && sl.w_master, "repack_weights: slot %d was never set (call myolo_plan_set_conv_weights first)", (int)i);
+      PackJob j{sl.w_master, sl.gamma, sl.beta, sl.mean, sl.var, sl.bias_master, sl.w, sl.bias, sl.co, sl.ci, sl.k, sl.co_pad, sl.ci_pad, sl.eps, 0, chunk};
+      chunk += (int)(((long)sl.co_pad * sl.k * sl.k * sl.ci_pad + kPackChunk - 1) / kPackChunk);
+      jobs.push_back(j);
+      if (sl.w_dgrad && sl.dgrad_n_pad > 0) {
+        PackJob d{sl.w_master, nullptr, nullptr, nullptr, nullptr, nullptr, sl.w_dgrad, sl.zero_bias, sl.co, sl.ci, sl.k, sl.dgrad_n_pad, sl.dgrad_cpad, 0.f, 1, chunk};
+        chunk += (int)(((long)sl.dgrad_n_pad * sl.k * sl.k * sl.dgrad_cpad + kPackChunk - 1) / kPackChunk);
+        jobs.push_back(d);
+      }
+    }
+    if ((int)jobs.size() > pl->pack_jobs_cap) {
+      if (pl->d_pack_jobs) cudaFree(pl->d_pack_jobs);
+      pl->d_pack_jobs = nullptr;
+      pl->pack_jobs_cap = (int)jobs.size() + 64;
+      MYOLO_CHECK_CUDA(cudaMalloc(&pl->d_pack_jobs, (size_t)pl->pack_jobs_cap * sizeof(PackJob)));
+    }
+    // rare (first step / first backward / moved parameters): ordered behind the stream's earlier launches of the old table, host-synchronous
+    MYOLO_CHECK_CUDA(cudaStreamSynchronize(s));
+    MYOLO_CHECK_CUDA(cudaMemcpy(pl->d_pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice));
+    pl->n_pack_jobs = (int)jobs.size();
+    pl->n_pack_chunks = chunk;
+    pl->pack_table_dirty = false;
+  }
+  int rc = pack_group_launch(pl->d_pack_jobs, pl->n_pack_jobs, pl->n_pack_chunks, s);
+  if (rc) return rc;
+  g_launch_count++;
+  for (auto& sl : pl->slots)
+    if (sl.w_dgrad && sl.dgrad_n_pad > 0) sl.dgrad_valid = true;
+  return 0;
 }
 
 static int prepare_conv(myolo_plan* pl, int i) {
@@ -859,6 +917,7 @@ static int conv_backward(myolo_plan* pl, int i, bool need_dgrad, cudaStream_t s,
   if (!sl.w_dgrad) {
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.w_dgrad, (size_t)n_pad * op.k * op.k * cpad * 2));
     MYOLO_CHECK_CUDA(cudaMalloc(&sl.zero_bias, (size_t)n_pad * 4));
+    pl->pack_table_dirty = true;
   }
   if (!sl.dgrad_valid) {   // (first use; later refreshes happen in refresh_dgrad_packs, outside any captured graph)
     if ((rc = pack_dgrad_weights(sl.w_master, sl.co, sl.ci, op.k, sl.w_dgrad, sl.zero_bias, n_pad, cpad, s))) return rc;

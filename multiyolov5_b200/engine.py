@@ -1,5 +1,6 @@
 """Runtime glue between the nn.Module shells and libmyolo_sm100a.so: compiles one plan per input shape, uploads
 (BN-folded, fp16-packed) weights, allocates caller-owned output tensors and launches the plan on the current stream."""
+import os
 import ctypes as C
 from typing import Dict, Tuple
 
@@ -21,6 +22,7 @@ class CompiledPlan:
         self.handle = h
         self.B, self.H, self.W = B, H, W
         self.weights_uploaded = False
+        self.weights_registered = None       # pointer signature of the tensors the library holds (myolo_plan_repack_weights)
 
     def __del__(self):
         try:
@@ -30,9 +32,22 @@ class CompiledPlan:
         except Exception:
             pass
 
+    def _pointer_signature(self):
+        sig = []
+        for s in self.pb.slots:
+            for t in (s.conv.weight, s.conv.bias) + ((s.bn.weight, s.bn.bias, s.bn.running_mean, s.bn.running_var) if s.bn is not None else ()):
+                sig.append(0 if t is None else (t.data_ptr() if t.dtype == torch.float32 and t.is_contiguous() else -1))
+        return tuple(sig)
+
     def upload_weights(self):
         L = _lib.lib()
         sp = _lib.stream_ptr()
+        # same fp32 tensors as at the last full upload (in-place optimiser updates): every pack of the plan in one launch
+        sig = self._pointer_signature()
+        if self.weights_registered == sig and -1 not in sig and os.environ.get("MYOLO_REPACK", "1") != "0":
+            _lib.check(L.myolo_plan_repack_weights(self.handle, sp))
+            self.weights_uploaded = True
+            return
         keep = []
 
         def f32(t):
@@ -58,6 +73,7 @@ class CompiledPlan:
             _lib.check(L.myolo_plan_set_conv_weights(self.handle, i, _lib.ptr(w), co, ci, k, _lib.ptr(g), _lib.ptr(b), _lib.ptr(m),
                                                      _lib.ptr(v), eps, _lib.ptr(bias), sp))
         self.weights_uploaded = True
+        self.weights_registered = sig
 
 
 class Engine:

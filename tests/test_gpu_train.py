@@ -450,3 +450,35 @@ def test_fused_det_loss_matches_torch_formulation_at_bench_shapes():
     for q, gq in zip(p, grads):
         err = float((gq - q.grad).abs().max() / q.grad.abs().max())
         assert err <= 5e-5, err
+
+
+def test_grouped_weight_repack_equals_per_slot_packs(monkeypatch):
+    """after an in-place parameter update every fp16 copy (forward packs and the flipped / transposed data-gradient packs) is rewritten by
+    ONE launch (myolo_plan_repack_weights); the result must equal the per-slot pack kernels' (MYOLO_REPACK=0)"""
+    from multiyolov5_b200 import _lib
+
+    def two_steps(repack):
+        monkeypatch.setenv("MYOLO_REPACK", "1" if repack else "0")
+        model, cfg, sd, x = setup(B=2, H=64, W=128)
+        xc = x.cuda()
+        out = model(xc)
+        (out[1].float().square().mean() + sum(r.float().square().mean() for r in out[0])).backward()
+        with torch.no_grad():
+            for i, p in enumerate(model.parameters()):
+                p.mul_(1.0 + 0.01 * ((i % 5) - 2))           # in place: same tensors, new values
+                p.grad.zero_()
+        out = model(xc)
+        (out[1].float().square().mean() + sum(r.float().square().mean() for r in out[0])).backward()
+        torch.cuda.synchronize()
+        return ([r.detach().float().cpu() for r in out[0]] + [out[1].detach().float().cpu()],
+                {k: p.grad.detach().cpu().clone() for k, p in model.named_parameters()})
+
+    o1, g1 = two_steps(True)
+    o0, g0 = two_steps(False)
+    for a, b in zip(o1, o0):                                   # forward packs (batch statistics are reduced with atomics: not bit-stable)
+        assert rel_f(a, b) < 1e-3
+    worst = 0.0
+    for k in g0:                                               # gradients are accumulated atomically: equal up to fp32 summation order
+        d = float((g1[k] - g0[k]).abs().max()) / (float(g0[k].abs().max()) + 1e-12)
+        worst = max(worst, d)
+    assert worst < 2e-3, worst
