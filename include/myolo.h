@@ -144,6 +144,12 @@ int myolo_plan_set_bn(myolo_plan* plan, int bn_slot, int channels, float* gamma,
 int myolo_plan_set_conv_grad(myolo_plan* plan, int weight_slot, float* d_weight, float* d_bias);
 /* seed of the train-mode dropout masks (default 0); masks change with every train forward */
 int myolo_plan_set_seed(myolo_plan* plan, uint64_t seed);
+/* Concurrent train-mode forwards of one model on two plans (the det and the seg pass of reference train.py:364-392): a plan with
+ * defer != 0 leaves running_mean / running_var untouched in its forward and keeps the batch sums; myolo_plan_apply_running then performs
+ * the momentum update of every BN layer in one launch - call it after the other plan's forward so the statistics move in the
+ * reference's order (det batch first, then seg batch). */
+int myolo_plan_set_defer_running(myolo_plan* plan, int defer);
+int myolo_plan_apply_running(myolo_plan* plan, void* stream);
 /* train-mode forward: raw[i] (B,na,ny,nx,no) fp32 and seg (B,n_segcls,H,W) fp32, like Model.forward in training (models/yolo.py:225,316) */
 int myolo_plan_train_forward(myolo_plan* plan, const void* x, int x_dtype, float* const* raw, float* seg, void* stream);
 /* backward of the last train forward: grad_raw[i] / grad_seg are dL/d(raw[i]) / dL/d(seg) (fp32, nullable); parameter gradients are

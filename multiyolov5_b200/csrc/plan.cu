@@ -126,6 +126,10 @@ struct myolo_plan {
   PackJob* d_pack_jobs = nullptr;
   int n_pack_jobs = 0, n_pack_chunks = 0, pack_jobs_cap = 0;
   bool pack_table_dirty = true;
+  // deferred running statistics (myolo_plan_set_defer_running / myolo_plan_apply_running)
+  bool defer_running = false;
+  RunningJob* d_run_jobs = nullptr;
+  int n_run_jobs = 0;
   unsigned long long seed = 0;       // dropout
   unsigned long long* d_step = nullptr;
   std::vector<cudaEvent_t> bwd_ev;   // per-op completion events of the multi-lane captured backward (+4 join events)
@@ -226,6 +230,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   if (pl->ws) cudaFree(pl->ws);
   if (pl->d_extra) cudaFree(pl->d_extra);
   if (pl->d_pack_jobs) cudaFree(pl->d_pack_jobs);
+  if (pl->d_run_jobs) cudaFree(pl->d_run_jobs);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
   for (auto& e : pl->bwd_exec) if (e) cudaGraphExecDestroy(e);
   if (pl->graph) cudaGraphDestroy(pl->graph);
@@ -470,7 +475,7 @@ static int run_op(myolo_plan* pl, int i, const void* x, int x_dtype, float* z, f
         MYOLO_CHECK_CUDA(cudaMalloc(&pl->bn_stats[i], (6 * (size_t)bn.C + 4) * sizeof(float)));
         MYOLO_CHECK_CUDA(cudaMemsetAsync(pl->bn_stats[i], 0, (6 * (size_t)bn.C + 4) * sizeof(float), s));
       }
-      if ((rc = launch_bn_stats(in, bn, pl->bn_stats[i], pl->bn_stats[i] + 2 * bn.C, s))) return rc;
+      if ((rc = launch_bn_stats(in, bn, pl->bn_stats[i], pl->bn_stats[i] + 2 * bn.C, s, pl->defer_running))) return rc;
       return launch_bn_act_fwd(in, has_res ? &in2 : nullptr, out, bn, pl->bn_stats[i], op.act, s);
     }
     case MYOLO_OP_ACT:
@@ -778,10 +783,45 @@ extern "C" int myolo_plan_set_bn(myolo_plan* pl, int bn_slot, int channels, floa
       b.d_beta != d_beta || b.momentum != momentum || b.eps != eps) {
     pl->graph_dirty = true;      // kernel arguments are baked into the captured graphs
     pl->bwd_dirty = true;
+    if (pl->d_run_jobs) { cudaFree(pl->d_run_jobs); pl->d_run_jobs = nullptr; pl->n_run_jobs = 0; }
   }
   b.gamma = gamma; b.beta = beta; b.running_mean = running_mean; b.running_var = running_var;
   b.d_gamma = d_gamma; b.d_beta = d_beta; b.momentum = momentum; b.eps = eps; b.C = channels; b.set = true;
   return 0;
+}
+
+// Two train-mode forwards of ONE model may run concurrently on two plans (the det and the seg pass of reference train.py:364-392) if the
+// running statistics still move in the reference's order: the second plan defers its updates (its BN kernels leave the batch sums in the
+// plan's scratch) and applies them with one launch once the first plan's forward has finished.
+extern "C" int myolo_plan_set_defer_running(myolo_plan* pl, int defer) {
+  MYOLO_REQUIRE(pl, "set_defer_running: null plan");
+  if (pl->defer_running != (defer != 0)) pl->graph_dirty = true;     // baked into the captured BN launches
+  pl->defer_running = defer != 0;
+  return 0;
+}
+
+extern "C" int myolo_plan_apply_running(myolo_plan* pl, void* stream) {
+  NvtxRange nvtx("myolo_plan_apply_running");
+  MYOLO_REQUIRE(pl && pl->defer_running, "apply_running: the plan does not defer its running statistics");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!pl->d_run_jobs) {
+    std::vector<RunningJob> jobs;
+    for (size_t i = 0; i < pl->ops.size(); ++i) {
+      const myolo_op& op = pl->ops[i];
+      if (op.kind != MYOLO_OP_BN_ACT) continue;
+      MYOLO_REQUIRE(i < pl->bn_stats.size() && pl->bn_stats[i], "apply_running: no train forward has run on this plan yet");
+      const BnParams& bn = pl->bns[op.aux[0]];
+      if (!bn.running_mean) continue;
+      TensorView in;
+      int rc = resolve_view(pl, op.in, &in);
+      if (rc) return rc;
+      jobs.push_back(RunningJob{bn.running_mean, bn.running_var, pl->bn_stats[i] + 4 * (size_t)bn.C, bn.C, (long)in.B * in.H * in.W, bn.momentum});
+    }
+    MYOLO_CHECK_CUDA(cudaMalloc(&pl->d_run_jobs, std::max<size_t>(1, jobs.size()) * sizeof(RunningJob)));
+    MYOLO_CHECK_CUDA(cudaMemcpy(pl->d_run_jobs, jobs.data(), jobs.size() * sizeof(RunningJob), cudaMemcpyHostToDevice));
+    pl->n_run_jobs = (int)jobs.size();
+  }
+  return launch_bn_apply_running(pl->d_run_jobs, pl->n_run_jobs, s);
 }
 
 extern "C" int myolo_plan_set_seed(myolo_plan* pl, uint64_t seed) {

@@ -189,14 +189,36 @@ __global__ void bn_finalize_kernel(float* sums, float* stats, BnParams bn, long 
   }
 }
 
-int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s) {
+// deferred running statistics: one launch applies r <- (1-m) r + m * stat for every BN layer of a plan from the sums its last forward left
+__global__ void __launch_bounds__(256) bn_apply_running_kernel(const RunningJob* __restrict__ jobs) {
+  const RunningJob j = jobs[blockIdx.x];
+  const float n = (float)j.npix;
+  for (int c = threadIdx.x; c < j.C; c += 256) {
+    const float mean = j.sums[c] / n;
+    const float var = fmaxf(j.sums[j.C + c] / n - mean * mean, 0.f);
+    j.running_mean[c] = (1.f - j.momentum) * j.running_mean[c] + j.momentum * mean;
+    j.running_var[c] = (1.f - j.momentum) * j.running_var[c] + j.momentum * var * (n / fmaxf(n - 1.f, 1.f));
+  }
+}
+int launch_bn_apply_running(const RunningJob* d_jobs, int n_jobs, cudaStream_t s) {
+  if (n_jobs <= 0) return 0;
+  bn_apply_running_kernel<<<n_jobs, 256, 0, s>>>(d_jobs);
+  MYOLO_LAUNCH_CHECK();
+  g_launch_count++;
+  return 0;
+}
+
+int launch_bn_stats(const TensorView& u, const BnParams& bn_in, float* stats, float* scratch, cudaStream_t s, bool defer_running) {
+  BnParams bn = bn_in;
   MYOLO_REQUIRE(u.dtype == MYOLO_F16 && bn.set && bn.C == u.C, "bn_stats: bad view / BN parameters not set");
+  MYOLO_REQUIRE(!defer_running || (u.C % 8 == 0 && u.C <= 2048 && u.ctot % 8 == 0), "bn_stats: deferred running statistics need C %% 8 == 0");
+  if (defer_running) bn.running_mean = bn.running_var = nullptr;     // the sums stay in scratch + 2C for myolo_plan_apply_running
   const long npix = (long)u.B * u.H * u.W;
   // scratch (zero on entry, left zero by the kernel): 2*C sums, 2*C final sums (backward), the completion ticket
   if (u.C % 8 == 0 && u.C <= 2048 && u.ctot % 8 == 0) {
     MYOLO_CHECK_CUDA(launch_pdl(chan_reduce_v_kernel<0>, dim3(reduce_v_grid(npix, u.C)), dim3(256), 0, s, u, u, (const float*)nullptr,
                                 (const float*)nullptr, (const float*)nullptr, 0, scratch, npix, u.C, bn, stats,
-                                reinterpret_cast<unsigned*>(scratch + 4 * u.C), (float*)nullptr));
+                                reinterpret_cast<unsigned*>(scratch + 4 * u.C), defer_running ? scratch + 2 * u.C : (float*)nullptr));
     g_launch_count++;
     return 0;
   }

@@ -21,7 +21,16 @@ struct BnParams {           // device pointers owned by the caller (nn.BatchNorm
 
 // ---- forward ----
 // per-channel mean / inverse std over (B,H,W) of u (fp16 NHWC view) -> stats[0..C) = mean, stats[C..2C) = invstd; updates running stats
-int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s);
+int launch_bn_stats(const TensorView& u, const BnParams& bn, float* stats, float* scratch, cudaStream_t s, bool defer_running = false);
+struct RunningJob {         // one BN layer of a deferred running-statistics update (sums = [sum | sum of squares] over npix values)
+  float* running_mean;
+  float* running_var;
+  const float* sums;
+  int C;
+  long npix;
+  float momentum;
+};
+int launch_bn_apply_running(const RunningJob* d_jobs, int n_jobs, cudaStream_t s);
 // y = act(gamma*(u-mean)*invstd + beta) (+ residual)
 int launch_bn_act_fwd(const TensorView& u, const TensorView* res, const TensorView& y, const BnParams& bn, const float* stats, int act,
                       cudaStream_t s);

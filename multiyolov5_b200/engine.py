@@ -217,7 +217,8 @@ class Engine:
         self.prepare_train_plan(p)
         L = _lib.lib()
         sp = _lib.stream_ptr()
-        torch._foreach_add_(p._nbt, 1)
+        if not getattr(p, "_defer_running", False):      # a deferring plan counts its batch in apply_running
+            torch._foreach_add_(p._nbt, 1)
         det, seg_head = self.model.model[-1], self.model.model[-2]
         dec = [o.in_ for o in p.pb.ops if o.kind == _lib.OP_DETECT_DECODE]
         shapes = [(B, det.na, v.h, v.w, det.no) for v in dec]
@@ -240,6 +241,17 @@ class Engine:
                 q.weights_uploaded = False
         self.last_plan = p
         return raws, (segs[0] if n_seg == 1 else segs), p
+
+    def set_defer_running(self, plan, on=True):
+        """a deferring train plan leaves running_mean / running_var / num_batches_tracked alone in its forward (apply_running moves them):
+        lets the seg pass's forward run next to the det pass's while the statistics still move in the reference's order"""
+        if getattr(plan, "_defer_running", False) != bool(on):
+            _lib.check(_lib.lib().myolo_plan_set_defer_running(plan.handle, int(bool(on))))
+            plan._defer_running = bool(on)
+
+    def apply_running(self, plan):
+        _lib.check(_lib.lib().myolo_plan_apply_running(plan.handle, _lib.stream_ptr()))
+        torch._foreach_add_(plan._nbt, 1)
 
     def _check_generation(self, plan, generation):
         if generation is not None and generation != getattr(plan, "fwd_generation", 0):

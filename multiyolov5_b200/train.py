@@ -13,6 +13,7 @@ clears the gradients.  `torch.distributed` is plumbing only (process group + all
 Out of scope (the reference's outer loop, not the hot path): data loading, LR schedule / warm-up (call `set_lr` / `set_momentum`),
 EMA, checkpointing, plotting, DDP buffer broadcast.
 """
+import os
 import ctypes as C
 
 import torch
@@ -84,7 +85,8 @@ class Trainer:
     """`Trainer(model, hyp, batch_size).step(imgs, targets, segimgs, segtargets)`; hyp already scaled (see scale_hyp)."""
 
     def __init__(self, model, hyp, batch_size, world_size=1, rank=-1, accumulate=1, detgain=0.6, seggain=0.35, init_scale=2.0 ** 16,
-                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True, overlap_passes=True, fused_det_loss=True):
+                 growth_interval=2000, process_group=None, graph_loss=True, fused_seg_loss=True, overlap_passes=True, fused_det_loss=True,
+                 concurrent_forwards=None):
         assert next(model.parameters()).is_cuda, "model.cuda() first"
         self.model, self.hyp, self.batch_size = model, hyp, batch_size
         self.world_size, self.rank, self.accumulate, self.pg = world_size, rank, accumulate, process_group
@@ -119,6 +121,9 @@ class Trainer:
         # pass the kernels are launch/latency bound and each pass alone leaves most of the 148 SMs idle.
         self.overlap_passes = bool(overlap_passes) and (graph_loss or fused_det_loss)
         self._s_seg = torch.cuda.Stream() if self.overlap_passes else None
+        if concurrent_forwards is None:
+            concurrent_forwards = os.environ.get("MYOLO_CONCURRENT_FWD", "1") != "0"
+        self.concurrent_forwards = bool(concurrent_forwards) and self.overlap_passes
         self._ev_detfwd, self._ev_start, self._ev_seg = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def set_lr(self, lr_bn, lr_weight, lr_bias):
@@ -243,18 +248,28 @@ class Trainer:
         if self.overlap_passes and fused_seg:
             main = torch.cuda.current_stream()
             self._ev_start.record(main)
-            # the seg plan's weight packing does not depend on the det pass: it runs ahead on the side stream ...
+            # the seg pass runs on its own train plan and stream.  Its forward starts with the det forward (both are chains of small
+            # launches at 4 images: two chains fill the machine better than one); its BatchNorm running statistics are deferred and
+            # applied after the det forward, i.e. in the reference's order (train.py:364 det batch, :385 seg batch)
             with torch.cuda.stream(self._s_seg):
                 self._s_seg.wait_event(self._ev_start)
                 eng = self.model.engine()
                 B, _, H, W = segimgs.shape
                 eng.ensure_flat_grads()
                 plan = eng.train_plan_for(B, H, W, lane=1)
+                eng.set_defer_running(plan, self.concurrent_forwards)
                 eng.prepare_train_plan(plan)
+                if self.concurrent_forwards:
+                    eng.train_forward(segimgs, want_seg=False, lane=1)
             items = self.backward_det(imgs, targets)                 # records _ev_detfwd right after the det forward
             with torch.cuda.stream(self._s_seg):
-                self._s_seg.wait_event(self._ev_detfwd)              # ... its forward after the det forward (running statistics order)
-                segloss = self.backward_seg(segimgs, segtargets, lane=1)
+                self._s_seg.wait_event(self._ev_detfwd)
+                if self.concurrent_forwards:
+                    eng.apply_running(plan)
+                    segloss = eng.train_backward_seg_ce(plan, segtargets, factor=self.batch_size * self.seggain, scale=self.scale)
+                    segloss = segloss * (self.batch_size * self.seggain)
+                else:                                                # forward after the det forward, overlapping the det backward
+                    segloss = self.backward_seg(segimgs, segtargets, lane=1)
                 self._ev_seg.record(self._s_seg)
             main.wait_event(self._ev_seg)
             segimgs.record_stream(self._s_seg); segtargets.record_stream(self._s_seg)

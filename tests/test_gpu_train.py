@@ -459,7 +459,7 @@ def test_grouped_weight_repack_equals_per_slot_packs(monkeypatch):
 
     def two_steps(repack):
         monkeypatch.setenv("MYOLO_REPACK", "1" if repack else "0")
-        model, cfg, sd, x = setup(B=2, H=64, W=128)
+        model, cfg, sd, x = setup(B=2, H=128, W=256)
         xc = x.cuda()
         out = model(xc)
         (out[1].float().square().mean() + sum(r.float().square().mean() for r in out[0])).backward()
@@ -475,10 +475,56 @@ def test_grouped_weight_repack_equals_per_slot_packs(monkeypatch):
 
     o1, g1 = two_steps(True)
     o0, g0 = two_steps(False)
-    for a, b in zip(o1, o0):                                   # forward packs (batch statistics are reduced with atomics: not bit-stable)
-        assert rel_f(a, b) < 1e-3
-    worst = 0.0
-    for k in g0:                                               # gradients are accumulated atomically: equal up to fp32 summation order
-        d = float((g1[k] - g0[k]).abs().max()) / (float(g0[k].abs().max()) + 1e-12)
-        worst = max(worst, d)
-    assert worst < 2e-3, worst
+    o0b, g0b = two_steps(False)
+    # batch statistics and parameter gradients are reduced with fp32 atomics and tiny maps (2x4 pixels at P5 here) amplify the summation
+    # order: the yardstick is the run-to-run spread of the per-slot path itself; a wrong pack is an O(1) error
+    noise_o = max(rel_f(a, b) for a, b in zip(o0b, o0))
+    diff_o = max(rel_f(a, b) for a, b in zip(o1, o0))
+
+    def gdiff(ga, gb):
+        return max(float((ga[k] - gb[k]).abs().max()) / (float(gb[k].abs().max()) + 1e-12) for k in gb)
+    noise_g, diff_g = gdiff(g0b, g0), gdiff(g1, g0)
+    print(f"\nrepack vs per-slot: outputs {diff_o:.2e} (run-to-run {noise_o:.2e}), gradients {diff_g:.2e} (run-to-run {noise_g:.2e})")
+    assert diff_o <= max(3 * noise_o, 1e-3), (diff_o, noise_o)
+    assert diff_g <= max(3 * noise_g, 2e-3), (diff_g, noise_g)
+
+
+def test_concurrent_forwards_keep_the_reference_order_of_running_statistics():
+    """Trainer(concurrent_forwards=True) runs the seg forward next to the det forward; the seg plan defers its BatchNorm running-statistics
+    update and applies it after the det forward.  running_mean / running_var / num_batches_tracked and the stepped parameters must equal
+    the strictly sequential schedule's (reference train.py:364-398: det forward+backward, seg forward+backward, optimizer.step)."""
+    from multiyolov5_b200.train import Trainer, scale_hyp
+    B = 2
+    rs = np.random.RandomState(0)
+    imgs = synth.synth_image(B, 128, 256, seed=1).cuda()
+    segimgs = synth.synth_image(B, 128, 256, seed=2).cuda()
+    t = np.zeros((12, 6), np.float32)
+    t[:, 0] = rs.randint(0, B, 12); t[:, 1] = rs.randint(0, 15, 12)
+    t[:, 2:4] = rs.uniform(0.1, 0.9, (12, 2)); t[:, 4:6] = rs.uniform(0.05, 0.4, (12, 2))
+    targets = torch.from_numpy(t).cuda()
+    mask = torch.from_numpy(rs.randint(-1, 19, (B, 128, 256)).astype(np.int64)).cuda()
+
+    def run(**kw):
+        model, cfg, sd, _ = setup(B=B, H=128, W=256)
+        hyp = dict(lr0=0.01, momentum=0.937, weight_decay=5e-4, box=0.05, cls=0.5, cls_pw=1.0, obj=1.0, obj_pw=1.0, anchor_t=4.0, fl_gamma=0.0)
+        hyp = scale_hyp(hyp, nl=3, nc=cfg["nc"], imgsz=256, total_batch_size=4)
+        tr = Trainer(model, hyp, batch_size=B, init_scale=2.0 ** 10, **kw)
+        for _ in range(3):
+            items, segloss = tr.step(imgs, targets, segimgs, mask)
+        torch.cuda.synchronize()
+        return {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}, float(items[3]), float(segloss)
+
+    sa, da, ga = run(concurrent_forwards=True)
+    sb, db, gb = run(overlap_passes=False)
+    assert abs(da - db) < 2e-3 * abs(db) and abs(ga - gb) < 2e-3 * abs(gb), (da, db, ga, gb)
+    worst = {}
+    for k in sb:
+        if k.endswith("num_batches_tracked"):
+            assert int(sa[k]) == int(sb[k]) == 6, (k, int(sa[k]), int(sb[k]))        # 3 steps x (det batch + seg batch)
+            continue
+        kind = "running" if "running_" in k else "param"
+        d = float((sa[k] - sb[k]).abs().max()) / (float(sb[k].abs().max()) + 1e-12)
+        worst[kind] = max(worst.get(kind, 0.0), d)
+    print("\nconcurrent vs sequential schedule after 3 steps: worst relative difference", worst)
+    # both schedules do the same arithmetic; fp32 atomics (batch sums, parameter gradients) make neither bit-stable run to run
+    assert worst["running"] < 2e-3 and worst["param"] < 2e-2, worst
