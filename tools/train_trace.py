@@ -75,3 +75,10 @@ print("# individual launches of selected kernels (start us, duration us, grid):"
 for e in st:
     if any(k in e["name"] for k in ("conv_simt", "spp_bwd", "seg_ce", "zero_stuff")):
         print(f"{e['ts'] - t0:9.0f} {e['dur']:7.1f} grid{e['args'].get('grid')} {e['name'].replace('myolo::', '')[:60]}")
+
+# the whole step, one line per kernel (start us, duration us, stream, name): gpurun_out/train_trace_full.txt
+os.makedirs("gpurun_out", exist_ok=True)
+with open("gpurun_out/train_trace_full.txt", "w") as fh:
+    for e in st:
+        fh.write(f"{e['ts'] - t0:9.1f} {e['dur']:7.1f} s{e['args'].get('stream')} grid{e['args'].get('grid')} "
+                 f"{e['name'].replace('myolo::', '').replace('void ', '')[:90]}\n")
