@@ -432,6 +432,7 @@ def main():
         flops = simt_flops = 0.0
         info = (C.c_int32 * 12)()
         conv_table = []
+        layer_rows = []
         for i, o in enumerate(pb.ops):
             if o.kind == _lib.OP_CONV:
                 s = pb.slots[o.slot].conv
@@ -439,6 +440,11 @@ def main():
                 _lib.check(_lib.lib().myolo_plan_conv_info(eng.last_plan.handle, i, info))
                 if info[0]:      # tcgen05 kernel
                     conv_ms += per_op[i]; n_conv += 1; flops += f
+                    # algorithmic bytes of the launch: input + output (+ residual) activations once, weights once, fp16 (fp32 head outputs: 4 B)
+                    nbytes = (B * o.in_.h * o.in_.w * o.in_.c * 2 + B * o.out.h * o.out.w * s.out_channels * (2 if o.out.buf.dtype == _lib.F16 else 4)
+                              + (B * o.out.h * o.out.w * s.out_channels * 2 if o.in2 is not None else 0)
+                              + s.out_channels * s.in_channels * s.kernel_size[0] * s.kernel_size[1] * 2)
+                    layer_rows.append((f, nbytes, per_op[i]))
                 else:            # CUDA-core kernel (maps < one 128-pixel tile: PPM bins, FFM attention FCs)
                     simt_ms += per_op[i]; n_simt += 1; simt_flops += f
                 conv_table.append((i, o.tag, f"{s.in_channels}->{s.out_channels} k{s.kernel_size[0]}s{s.stride[0]}d{s.dilation[0]} @{o.out.h}x{o.out.w}",
@@ -463,6 +469,14 @@ def main():
                 "simt_conv_flops_per_step": simt_flops,
                 "algorithmic_flops_per_step": flops, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
                 "conv_share_of_forward": conv_ms / float(per_op.sum())}
+        # the same launches against their OWN roofline min(tensor, AI x HBM): most layers of this network are activation-bandwidth bound
+        # (1x1 convs, 16-64 channel layers), so the aggregate tensor fraction above cannot approach 1 whatever the kernel does
+        hbm_peak = peaks.get("hbm_gbs", 6500.0) * 1e9
+        t_bound = [max(f / (peak * 1e12), nb / hbm_peak) * 1e3 for f, nb, _ in layer_rows]
+        roof["per_layer"] = {"bound_ms": float(sum(t_bound)), "measured_ms": float(conv_ms), "frac": float(sum(t_bound) / conv_ms),
+                             "hbm_bound_launches": int(sum(1 for (f, nb, _) in layer_rows if nb / hbm_peak > f / (peak * 1e12))),
+                             "tensor_bound_launches": int(sum(1 for (f, nb, _) in layer_rows if nb / hbm_peak <= f / (peak * 1e12))),
+                             "note": "sum over the tcgen05 conv launches of max(FLOP / tensor peak, algorithmic bytes / HBM peak) / measured device time"}
         if args.profile_ops:
             for i, o in enumerate(pb.ops):
                 print(f"{i:3d} kind={o.kind:2d} {o.tag:24s} {per_op[i] * 1e3:9.1f} us", file=sys.stderr)

@@ -623,8 +623,10 @@ __global__ void seg_argmax_nchw_kernel(const TIn* __restrict__ src, int B, int C
     int bi = 0;
     for (int c = 0; c < C; ++c) {
       const TIn* pl = src + ((size_t)b * C + c) * h * w;
-      const float val = bilerp((float)pl[ly.i0 * w + lx.i0], (float)pl[ly.i0 * w + lx.i1], (float)pl[ly.i1 * w + lx.i0],
-                               (float)pl[ly.i1 * w + lx.i1], ly, lx);
+      float val = bilerp((float)pl[ly.i0 * w + lx.i0], (float)pl[ly.i0 * w + lx.i1], (float)pl[ly.i1 * w + lx.i0],
+                         (float)pl[ly.i1 * w + lx.i1], ly, lx);
+      // half logits: F.interpolate on a half tensor returns fp16 values, and the reference takes max(0) over THOSE (detect.py:191-193)
+      if (sizeof(TIn) == 2) val = __half2float(__float2half_rn(val));
       if (c == 0 || val > best) { best = val; bi = c; }
     }
     out[i] = (TOut)bi;

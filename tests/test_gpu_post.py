@@ -135,3 +135,21 @@ def test_fp16_argmax_fast_path_first_maximum_wins(out_dtype):
     ref = seg.float().argmax(1)                 # torch.max over dim returns the first maximal index
     assert out.dtype == out_dtype and torch.equal(out.long(), ref)
     assert int(out[0, 10, 10]) == 0 and not bool((out == 5).any())
+
+
+def test_half_logits_resized_argmax_compares_fp16_rounded_values():
+    """detect.py:191-193 in half mode with a real resize: F.interpolate on a half tensor returns fp16 values and max(0)[1] runs over those.
+    Our kernel interpolates in fp32 and rounds to fp16 before comparing; where the fp16 values of two classes tie, the lowest id wins.
+    Yardstick: torch's own half bilinear on the same GPU.  Interpolation weights are computed slightly differently (ATen forms the source
+    index from a precomputed scale), so a pixel may differ where the top two fp16 values are within one ulp: bounded, not zero."""
+    from multiyolov5_b200.utils.general import seg_argmax
+    g = torch.Generator(device="cuda").manual_seed(5)
+    seg = (torch.randn((2, 19, 32, 48), device="cuda", generator=g) * 3).half()
+    out = seg_argmax(seg, (200, 333))
+    up = torch.nn.functional.interpolate(seg, (200, 333), mode="bilinear", align_corners=True)
+    ref = up.float().argmax(1)
+    agree = float((out == ref).float().mean())
+    top2 = up.float().topk(2, dim=1).values
+    close = (top2[:, 0] - top2[:, 1]) <= 2e-2 * top2[:, 0].abs().clamp_min(1.0)      # ~ a few fp16 ulps
+    assert bool(((out == ref) | close).all()), "disagreement away from an fp16 near-tie"
+    assert agree > 0.995, agree
