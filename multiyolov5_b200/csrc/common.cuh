@@ -139,6 +139,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// the same wait for roles that are AHEAD of the pipeline (producer waiting for a free ring slot, MMA issuer waiting for a drained accumulator):
+// a spinning warp competes with the epilogue warps of its scheduler for issue slots, so it backs off between polls
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (ns) __nanosleep(ns);
+    if (++spins > (1u << 24)) {
+      printf("myolo: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -221,7 +234,7 @@ __device__ __forceinline__ float silu_f(float v) {
   return v * r;
 }
 // the same function with the reciprocal on the SFU (MUFU.RCP, 1 ulp): 5 issue slots instead of 12, but two MUFU ops.  The conv epilogue mixes
-// both (every fourth element takes this one) so that the FP32 pipe (12 clk per warp-element on the Newton path) and the quarter-rate SFU
+// both (every second element takes this one) so that the FP32 pipe (12 clk per warp-element on the Newton path) and the quarter-rate SFU
 // (8 clk per MUFU) finish together: ~10 instead of 12 issue slots per element on layers whose epilogue is issue-bound (70 % issue-active in ncu).
 __device__ __forceinline__ float silu_f_sfu(float v) {
   float e, r;

@@ -4,6 +4,20 @@
 
 namespace myolo {
 
+// division by a runtime constant as multiply-high + shift (the tile decode runs once per tile in EVERY epilogue warp: three hardware
+// divisions there cost ~800 clk per tile under the epilogue's issue pressure - measured with the clock64 timeline)
+struct FastDiv {
+  unsigned mul, shr;
+};
+static inline FastDiv make_fastdiv(unsigned d) {     // exact for 0 <= n < 2^31, d >= 1
+  unsigned l = 0;
+  while ((1ull << l) < d) ++l;
+  FastDiv f;
+  f.mul = (unsigned)((((1ull << l) - d) << 32) / d + 1);
+  f.shr = l;
+  return f;
+}
+
 struct ConvTcParams {
   int B, Ho, Wo;
   int tw, th;            // output tile = tw x th pixels, tw*th == 128 (UMMA M)
@@ -43,6 +57,8 @@ struct ConvTcParams {
   float* out_f32;
   int out_f32_ctot;
   long long* dbg;        // optional clock64 timeline buffer (MYOLO_CONV_TIMELINE=1), else null
+  unsigned spin_ns;      // back-off of the roles that wait for the epilogue (0 = plain polling)
+  FastDiv fd_ntn, fd_tpi, fd_tx, fd_rpi;   // n_tiles_n, tiles_x * tiles_y, tiles_x, rounds_per_img
 };
 
 struct ConvOp {

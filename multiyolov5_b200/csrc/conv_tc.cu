@@ -21,6 +21,10 @@
 // utils/torch_utils.py:182-202; Bottleneck shortcut add (models/common.py:105).
 #include "conv.h"
 
+#ifndef MYOLO_SILU_SFU_EVERY
+#define MYOLO_SILU_SFU_EVERY 2   // every n-th element of an epilogue chunk takes the two-MUFU SiLU: measured on B200 (tools/ab_lib.sh) 4 -> 3 -> 2: 9429 -> 9453 -> 9518 img/s
+#endif
+
 namespace myolo {
 
 static constexpr int kTileM = 128;
@@ -72,13 +76,14 @@ template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 
 struct TileCoord { int b, y0, x0, n0; };
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) { return (int)((__umulhi((unsigned)n, f.mul) + (unsigned)n) >> f.shr); }
 __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile, int tiles_per_img) {
   TileCoord t;
-  const int n_tile = tile % p.n_tiles_n;
-  const int m_tile = tile / p.n_tiles_n;
-  t.b = m_tile / tiles_per_img;
+  const int m_tile = fdiv(tile, p.fd_ntn);
+  const int n_tile = tile - m_tile * p.n_tiles_n;
+  t.b = fdiv(m_tile, p.fd_tpi);
   const int r = m_tile - t.b * tiles_per_img;
-  const int ty = r / p.tiles_x;
+  const int ty = fdiv(r, p.fd_tx);
   t.y0 = ty * p.th;
   t.x0 = (r - ty * p.tiles_x) * p.tw;
   t.n0 = n_tile * p.BN;
@@ -87,9 +92,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvTcParams& p, int tile
 // tile g of a vertical round (MODE 2): G consecutive output rows of one full-row column block
 __device__ __forceinline__ TileCoord decode_vround(const ConvTcParams& p, int round, int g) {
   TileCoord t;
-  t.b = round / p.rounds_per_img;
+  t.b = fdiv(round, p.fd_rpi);
   const int r = round - t.b * p.rounds_per_img;
-  const int tyg = r / p.tiles_x;
+  const int tyg = fdiv(r, p.fd_tx);
   t.x0 = (r - tyg * p.tiles_x) * p.tw;
   t.y0 = tyg * p.G + g;
   t.n0 = 0;
@@ -130,7 +135,7 @@ __device__ __forceinline__ void epilogue_chunk(const ConvTcParams& p, const uint
   f[14] = __uint_as_float(v[14]) + b3.z; f[15] = __uint_as_float(v[15]) + b3.w;
   if (p.act == MYOLO_ACT_SILU) {
 #pragma unroll
-    for (int e = 0; e < 16; ++e) f[e] = (e & 3) == 3 ? silu_f_sfu(f[e]) : silu_f(f[e]);
+    for (int e = 0; e < 16; ++e) f[e] = (e % MYOLO_SILU_SFU_EVERY) == MYOLO_SILU_SFU_EVERY - 1 ? silu_f_sfu(f[e]) : silu_f(f[e]);
   } else if (p.act == MYOLO_ACT_SIGMOID) {
 #pragma unroll
     for (int e = 0; e < 16; ++e) f[e] = sigmoid_f(f[e]);
@@ -264,7 +269,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (leader) DBG_STAMP(0);
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int s = 0; s < n_valid + 2; ++s) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin_ns);
             __syncwarp();
             if (leader) {
               mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2) * row_bytes);
@@ -284,7 +289,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (MODE == 1) {
           for (int ky = 0; ky < 3; ++ky)
             for (int cb = 0; cb < p.cblocks; ++cb) {
-              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin_ns);
               __syncwarp();
               if (leader) {
                 mbar_arrive_expect_tx(&full_bar[stage], (p.tw + 2 * p.dil) * row_bytes + (p.ws_mode ? 0 : 3 * b_sub_bytes));
@@ -300,7 +305,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           int tap = 0, cb = 0, q = 0;
           const int stage_tx = a_sub_bytes + (p.ws_mode ? 0 : b_sub_bytes);
           for (int ks = 0; ks < p.n_kstages; ++ks) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin_ns);
             __syncwarp();
             const int nch = min(p.chunks_per_stage, p.n_chunks - q);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], nch * stage_tx);
@@ -346,13 +351,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     int it = 0;
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
       if (leader) DBG_STAMP(2);
-      mbar_wait(&tempty_bar[as], aphase ^ 1);
+      mbar_wait_relaxed(&tempty_bar[as], aphase ^ 1, p.spin_ns);
       __syncwarp();
       tcgen05_fence_after();
       if (leader) DBG_STAMP(3);
       if (MODE == 2) {
-        const int r = round % p.rounds_per_img;
-        const int n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
+        const int r = round - fdiv(round, p.fd_rpi) * p.rounds_per_img;
+        const int n_valid = min(p.G, p.Ho - fdiv(r, p.fd_tx) * p.G);
         for (int cb = 0; cb < p.cblocks; ++cb)
           for (int s = 0; s < n_valid + 2; ++s) {
             mbar_wait(&full_bar[stage], phase);
@@ -450,8 +455,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int round = blockIdx.x; round < p.total_rounds; round += gridDim.x) {
       int n_valid;
       if (MODE == 2) {
-        const int r = round % p.rounds_per_img;
-        n_valid = min(p.G, p.Ho - (r / p.tiles_x) * p.G);
+        const int r = round - fdiv(round, p.fd_rpi) * p.rounds_per_img;
+        n_valid = min(p.G, p.Ho - fdiv(r, p.fd_tx) * p.G);
       } else {
         n_valid = min(p.G, p.total_tiles - round * p.G);
       }
@@ -483,6 +488,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
               else tma_store_wait_read<0>();
             }
             __syncwarp();
+            if (warp == 2 && lane == 0 && g == g_first) DBG_STAMP(8);
           }
           if (!waited) {
             mbar_wait(&tfull_bar[as], aphase);
@@ -744,6 +750,16 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     p.rounds_per_img = p.tiles_x * ceil_div(Ho, p.G);
     p.total_rounds = p.B * p.rounds_per_img;
   }
+  static int spin_ns = -1;
+  if (spin_ns < 0) {
+    const char* e = getenv("MYOLO_SPIN_NS");
+    spin_ns = e ? atoi(e) : 0;
+  }
+  p.spin_ns = spin_ns;
+  p.fd_ntn = make_fastdiv((unsigned)p.n_tiles_n);
+  p.fd_tpi = make_fastdiv((unsigned)(p.tiles_x * p.tiles_y));
+  p.fd_tx = make_fastdiv((unsigned)p.tiles_x);
+  p.fd_rpi = make_fastdiv((unsigned)std::max(1, p.rounds_per_img));
   // epilogue work split between the two warps of a TMEM lane quarter
   const int nchunk16 = p.BN / 16;
   if (p.G >= 2) { p.ep_split_cols = 0; p.ep_cols = p.BN; }

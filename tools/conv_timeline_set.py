@@ -7,6 +7,8 @@ os.environ["MYOLO_CONV_TIMELINE"] = "1"
 import torch
 from multiyolov5_b200 import ops
 SHAPES = [  # B, H, W, Ci, Co, k, s, d   (input map)
+    (16, 64, 128, 64, 64, 1, 1, 1),     # P3 bottleneck cv1 (1024 tiles, 3.5 per CTA)
+    (16, 32, 64, 128, 128, 1, 1, 1),    # P4 bottleneck cv1 (256 tiles, one per CTA)
     (16, 16, 32, 512, 256, 1, 1, 1),    # P5 1x1 (C3 cv1/cv2, SPP cv1)
     (16, 16, 32, 256, 256, 3, 1, 1),    # P5 bottleneck 3x3
     (16, 32, 64, 256, 128, 1, 1, 1),    # P4 1x1
