@@ -234,7 +234,7 @@ int myolo_seg_upsample_argmax(const void* logits, int dtype, int B, int C, int h
 int myolo_bilinear_nchw(const float* src, int B, int C, int h, int w, int H, int W, float* dst, void* stream);
 
 /* ---- standalone kernels for per-op parity tests and ncu captures ---- */
-/* SiLU(conv(x)*bnscale+bnshift) on NHWC fp16: x (B,H,W,Ci) -> y (B,Ho,Wo,Co); w fp32 [Co][Ci][k][k]; path: 0 auto, 1 tcgen05, 2 simt */
+/* SiLU(conv(x)*bnscale+bnshift) on NHWC fp16: x (B,H,W,Ci) -> y (B,Ho,Wo,Co); w fp32 [Co][Ci][k][k]; path: 0 auto, 1 tcgen05, 2 simt, 3 tcgen05 with pair mode (two M tiles per weight fetch) wherever legal */
 int myolo_conv_bn_silu(const void* x_nhwc_f16, int B, int H, int W, int ci, const float* w, int co, int k, int stride,
                        int dil, const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                        const float* bias, int act, const void* residual_nhwc_f16, void* y_nhwc_f16, int path, void* stream);

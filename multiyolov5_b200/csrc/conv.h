@@ -57,6 +57,9 @@ struct ConvTcParams {
   float* out_f32;
   int out_f32_ctot;
   long long* dbg;        // optional clock64 timeline buffer (MYOLO_CONV_TIMELINE=1), else null
+  // pair mode: a round is TWO M tiles (same N tile) that share every weight load - 256 x BN outputs per B fetch (L2->SM-bound layers)
+  int pair, m_tiles, n_pair_rounds, m_done;   // rounds [0, n_pair_rounds) are pairs, later rounds single tiles from M tile m_done on
+  int acc_stride, tmem_cols;                  // TMEM columns per accumulator stage / allocated (256 / 512 when a pair needs 2 x 128)
   unsigned spin_ns;      // back-off of the roles that wait for the epilogue (0 = plain polling)
   FastDiv fd_ntn, fd_tpi, fd_tx, fd_rpi;   // n_tiles_n, tiles_x * tiles_y, tiles_x, rounds_per_img
 };
@@ -79,6 +82,7 @@ struct ConvOp {
 bool conv_tc_eligible(const ConvOp& op);
 // builds tensor maps / params; requires op.in/out/res/w/bias device pointers to be final
 int conv_tc_prepare(ConvOp& op, int num_sms);
+extern int g_conv_tc_force_pair;   // tests: take pair mode wherever it is legal, not only where the cost rule picks it (myolo_conv_bn_silu path 3)
 int conv_tc_launch(const ConvOp& op, cudaStream_t stream);
 int conv_simt_launch(const ConvOp& op, cudaStream_t stream);
 int conv_simt_launch_group(const ConvOp* const* ops, int n, cudaStream_t stream);   // <= 4 small convs of one input type in one launch

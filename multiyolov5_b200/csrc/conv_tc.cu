@@ -101,6 +101,33 @@ __device__ __forceinline__ TileCoord decode_vround(const ConvTcParams& p, int ro
   return t;
 }
 
+// tile g of a round: pair mode maps rounds to (M-tile pair, N tile) and, past n_pair_rounds, to single tiles; otherwise tile = round*G + g
+__device__ __forceinline__ TileCoord decode_rg(const ConvTcParams& p, int round, int g, int tiles_per_img) {
+  if (!p.pair) return decode_tile(p, round * p.G + g, tiles_per_img);
+  int m, nt;
+  if (round < p.n_pair_rounds) {
+    const int pm = fdiv(round, p.fd_ntn);
+    nt = round - pm * p.n_tiles_n;
+    m = 2 * pm + g;
+  } else {
+    const int s = round - p.n_pair_rounds;
+    const int ms = fdiv(s, p.fd_ntn);
+    nt = s - ms * p.n_tiles_n;
+    m = p.m_done + ms;
+  }
+  TileCoord t;
+  t.b = fdiv(m, p.fd_tpi);
+  const int r = m - t.b * tiles_per_img;
+  const int ty = fdiv(r, p.fd_tx);
+  t.y0 = ty * p.th;
+  t.x0 = (r - ty * p.tiles_x) * p.tw;
+  t.n0 = nt * p.BN;
+  return t;
+}
+__device__ __forceinline__ int round_tiles(const ConvTcParams& p, int round) {
+  return p.pair ? (round < p.n_pair_rounds ? 2 : 1) : min(p.G, p.total_tiles - round * p.G);
+}
+
 // the kc/16 MMAs of one K chunk (16 K-elements = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) descriptor field), fully unrolled
 // for every chunk width so that the issuing lane runs straight-line code.  `acc0`: accumulate flag of the first MMA (the rest accumulate).
 template <int KM>
@@ -229,7 +256,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     named_bar_arrive(1, kNumThreads);
   } else {
     if (warp == 1) {
-      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     } else {
       const int nb_tot = p.n_tiles_n * p.BN;
       for (int i = threadIdx.x - 64; i < nb_tot; i += kEpiWarps * 32) bias_s[i] = __ldg(p.bias + i);
@@ -279,6 +306,56 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         if (leader) DBG_STAMP(1);
         it += n_valid;
+        continue;
+      }
+      if (MODE != 2 && p.pair) {
+        // two M tiles, one weight fetch: every stage holds [A of tile 0 | A of tile 1 | B]
+        const int nv = round < p.n_pair_rounds ? 2 : 1;
+        const TileCoord t0 = decode_rg(p, round, 0, tiles_per_img);
+        const TileCoord t1 = decode_rg(p, round, nv - 1, tiles_per_img);
+        const int a_half = p.a_stage_bytes >> 1;
+        if (leader) DBG_STAMP(0);
+        if (MODE == 1) {
+          for (int ky = 0; ky < 3; ++ky)
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+              mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin_ns);
+              __syncwarp();
+              if (leader) {
+                uint8_t* sa = smem_a + stage * p.a_stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[stage], nv * (p.tw + 2 * p.dil) * row_bytes + 3 * b_sub_bytes);
+                tma_load_4d(sa, &tmA0, &full_bar[stage], cb * p.kc, t0.x0 - p.dil, t0.y0 + (ky - 1) * p.dil, t0.b);
+                if (nv == 2) tma_load_4d(sa + a_half, &tmA0, &full_bar[stage], cb * p.kc, t1.x0 - p.dil, t1.y0 + (ky - 1) * p.dil, t1.b);
+                for (int kx = 0; kx < 3; ++kx)
+                  tma_load_2d(smem_b + stage * p.b_stage_bytes + kx * b_sub_bytes, &tmB, &full_bar[stage],
+                              ((ky * 3 + kx) * p.cblocks + cb) * p.kc, t0.n0);
+              }
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          int tap = 0, cb = 0, q = 0;
+          for (int ks = 0; ks < p.n_kstages; ++ks) {
+            mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, p.spin_ns);
+            __syncwarp();
+            const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], nch * (nv * a_sub_bytes + b_sub_bytes));
+            uint8_t* sa = smem_a + stage * p.a_stage_bytes;
+            uint8_t* sb = smem_b + stage * p.b_stage_bytes;
+            for (int j = 0; j < nch; ++j, ++q) {
+              const int mi = p.tap_map[tap];
+              const CUtensorMap* tm = mi == 0 ? &tmA0 : (mi == 1 ? &tmA1 : (mi == 2 ? &tmA2 : &tmA3));
+              if (leader) {
+                tma_load_4d(sa + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t0.x0 + p.tap_dx[tap], t0.y0 + p.tap_dy[tap], t0.b);
+                if (nv == 2)
+                  tma_load_4d(sa + a_half + j * a_sub_bytes, tm, &full_bar[stage], cb * p.kc, t1.x0 + p.tap_dx[tap], t1.y0 + p.tap_dy[tap], t1.b);
+                tma_load_2d(sb + j * b_sub_bytes, &tmB, &full_bar[stage], q * p.kc, t0.n0);
+              }
+              if (++cb == p.cblocks) { cb = 0; ++tap; }
+            }
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (leader) DBG_STAMP(1);
+        ++it;
         continue;
       }
       for (int g = 0; g < p.G; ++g) {
@@ -379,6 +456,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             if (leader) umma_commit(&empty_bar[stage]);
             if (++stage == S) { stage = 0; phase ^= 1; }
           }
+      } else if (p.pair) {
+        const int nv = round < p.n_pair_rounds ? 2 : 1;
+        const uint32_t a_half16 = (uint32_t)(p.a_stage_bytes >> 5);
+        const uint32_t tmem_r = tmem_base + as * p.acc_stride;
+        if (MODE == 1) {
+          uint32_t first = 0;
+          for (int ky = 0; ky < 3; ++ky)
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+              mbar_wait(&full_bar[stage], phase);
+              __syncwarp();
+              tcgen05_fence_after();
+              const uint32_t la = la_base + (uint32_t)stage * a_stage16;
+              const uint32_t lb0 = lb_base + (uint32_t)stage * b_stage16;
+              for (int g = 0; g < nv; ++g) {
+                uint32_t lb = lb0;
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                  if (leader) mma_chunk(kmma, tmem_r + g * p.BN, la + g * a_half16 + kx * p.dil * row16, lb, dhi, idesc, kx == 0 ? first : 1u);
+                  lb += (uint32_t)bsub16;
+                }
+              }
+              first = 1;
+              if (leader) umma_commit(&empty_bar[stage]);
+              if (++stage == S) { stage = 0; phase ^= 1; }
+            }
+        } else {
+          int q = 0;
+          for (int ks = 0; ks < p.n_kstages; ++ks) {
+            mbar_wait(&full_bar[stage], phase);
+            __syncwarp();
+            tcgen05_fence_after();
+            if (ks == 0 && leader) DBG_STAMP(4);
+            const int nch = min(p.chunks_per_stage, p.n_chunks - q);
+            for (int g = 0; g < nv; ++g) {
+              uint32_t la = la_base + (uint32_t)stage * a_stage16 + g * a_half16;
+              uint32_t lb = lb_base + (uint32_t)stage * b_stage16;
+              for (int j = 0; j < nch; ++j) {
+                if (leader) mma_chunk(kmma, tmem_r + g * p.BN, la, lb, dhi, idesc, (uint32_t)((ks | j) != 0));
+                la += asub16;
+                lb += bsub16;
+              }
+            }
+            q += nch;
+            if (leader) umma_commit(&empty_bar[stage]);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
       } else {
         for (int g = 0; g < p.G; ++g) {
           if (round * p.G + g >= p.total_tiles) break;
@@ -444,7 +568,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int c_lo = p.ep_split_cols ? half * nchunks_w : 0;
     const int g_first = p.ep_split_cols ? 0 : half;
     const int g_step = p.ep_split_cols ? 1 : 2;
-    const bool idle_half = (!p.ep_split_cols && p.G == 1 && half == 1);
+    const bool idle_half = (!p.ep_split_cols && p.G == 1 && !p.pair && half == 1);
     constexpr bool has_res = RES;
     int as = 0;
     uint32_t aphase = 0;
@@ -458,13 +582,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int r = round - fdiv(round, p.fd_rpi) * p.rounds_per_img;
         n_valid = min(p.G, p.Ho - fdiv(r, p.fd_tx) * p.G);
       } else {
-        n_valid = min(p.G, p.total_tiles - round * p.G);
+        n_valid = round_tiles(p, round);
       }
       if (warp == 2 && lane == 0) DBG_STAMP(6);
       bool waited = false;
       if (!idle_half) {
         for (int g = g_first; g < n_valid; g += g_step) {
-          const TileCoord tc = MODE == 2 ? decode_vround(p, round, g) : decode_tile(p, round * p.G + g, tiles_per_img);
+          const TileCoord tc = MODE == 2 ? decode_vround(p, round, g) : decode_rg(p, round, g, tiles_per_img);
           const int py = tc.y0 + ry, px = tc.x0 + rx;
           const bool pix_ok = (py < p.Ho) && (px < p.Wo);
           const size_t pix = ((size_t)tc.b * p.Ho + py) * p.Wo + px;
@@ -496,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             waited = true;
             if (warp == 2 && lane == 0) DBG_STAMP(7);
           }
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * kAccStride + g * p.BN;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * p.acc_stride + g * p.BN;
           const uint32_t stg = stg0 + sbuf * stg_warp_bytes;
           for (int cp = 0; cp < nchunks_w; cp += 2) {
             const bool two = cp + 1 < nchunks_w;
@@ -556,7 +680,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   DBG_STAMP0(14);
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(*tmem_slot, kTmemCols);
+    tmem_dealloc(*tmem_slot, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -648,6 +772,8 @@ bool conv_tc_eligible(const ConvOp& op) {
   return true;
 }
 
+int g_conv_tc_force_pair = 0;
+
 int conv_tc_prepare(ConvOp& op, int num_sms) {
   ConvTcParams& p = op.p;
   memset(&p, 0, sizeof(p));
@@ -733,10 +859,16 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   p.b_res_bytes = p.ws_mode ? (int)align_up(w_bytes, 1024) : 0;
   // accumulator rounds: G tiles share one TMEM stage when the layer is big enough to keep every CTA busy
   const int cta_budget = ws_big ? num_sms : max_ctas;
+  // (rounds >= g_rounds_x100 / 100 per CTA: with fewer, a CTA's tiles no longer overlap each other's load / MMA / epilogue phases)
+  static int g_rounds_x100 = -1;
+  if (g_rounds_x100 < 0) {
+    const char* e = getenv("MYOLO_G_ROUNDS_X100");
+    g_rounds_x100 = e ? atoi(e) : 200;
+  }
   p.G = 1;
   if (p.n_tiles_n == 1) {
     for (int g = 4; g >= 2; g >>= 1)
-      if (g * p.BN <= kAccStride && p.total_tiles / g >= 2 * cta_budget) { p.G = g; break; }
+      if (g * p.BN <= kAccStride && (long)(p.total_tiles / g) * 100 >= (long)g_rounds_x100 * cta_budget) { p.G = g; break; }
   }
   p.total_rounds = ceil_div(p.total_tiles, p.G);
   // vertical rounds: the G tiles of a round are G consecutive image rows, so G+2 strips feed 3*G (row, filter-row) pairs
@@ -750,6 +882,43 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     p.rounds_per_img = p.tiles_x * ceil_div(Ho, p.G);
     p.total_rounds = p.B * p.rounds_per_img;
   }
+  // pair mode (see ConvTcParams): for layers whose shared-memory fill is dominated by weight re-loads (one [BN x K] fetch per 128-pixel
+  // tile: FFM 3x3, the stride-2 3x3 convs, the P4 bottleneck 3x3s).  One CTA per SM; full waves of pair rounds, the remainder as single
+  // tiles so that the makespan in tile-times never grows
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("MYOLO_PAIR");
+    pair_env = e ? atoi(e) : 1;
+  }
+  p.m_tiles = p.B * p.tiles_x * p.tiles_y;
+  p.pair = 0;
+  p.n_pair_rounds = 0;
+  p.m_done = 0;
+  p.acc_stride = kAccStride;
+  p.tmem_cols = kTmemCols;
+  {
+    const long a_tile = p.strip ? 3L * p.cblocks * (p.tw + 2 * op.dil) * p.kc * 2 : (long)p.n_chunks * kTileM * p.kc * 2;
+    const long b_tile = (long)p.n_chunks * p.BN * p.kc * 2;
+    const int pairs_total = (p.m_tiles / 2) * p.n_tiles_n;
+    // measured per layer on B200 (bench.py --profile-ops, MYOLO_PAIR=0/1): wins where the weight tile is big - N tile 128 and K >= 1024 or
+    // stride 2 (L3/L5/L7/L18 -2..-4 us each, FFM 3x3 -8 us, SPP.cv2 -1.6 us); loses 1-3 us on 64-channel 3x3 strips and K <= 512 1x1 convs,
+    // whose two co-resident CTAs hide each other's epilogue better than one CTA with a pair does
+    const long k_total = (long)p.n_chunks * p.kc;
+    const bool legal = !p.ws_mode && p.G == 1 && !p.vround && p.out_mode == 0 && p.m_tiles % 2 == 0 && pairs_total >= 2;
+    const bool wins = p.BN == 128 && (k_total >= 1024 || op.stride == 2) && 2 * b_tile >= a_tile && pairs_total * 100 >= 80 * num_sms;
+    if (legal && ((pair_env && wins) || pair_env == 2 || g_conv_tc_force_pair)) {
+      p.pair = 1;
+      const int grid = std::min(pairs_total, num_sms);
+      const int tail_pairs = pairs_total % grid;
+      int npr = pairs_total;                                     // all pairs ...
+      if (tail_pairs > 0 && 2 * tail_pairs <= grid)              // ... unless the last partial wave is cheaper as single tiles (one wave)
+        npr = ((pairs_total - tail_pairs) / p.n_tiles_n) * p.n_tiles_n;
+      p.n_pair_rounds = npr;
+      p.m_done = 2 * (npr / p.n_tiles_n);
+      p.total_rounds = npr + (p.m_tiles - p.m_done) * p.n_tiles_n;
+      if (2 * p.BN > kAccStride) { p.acc_stride = 256; p.tmem_cols = 512; }
+    }
+  }
   static int spin_ns = -1;
   if (spin_ns < 0) {
     const char* e = getenv("MYOLO_SPIN_NS");
@@ -762,7 +931,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   p.fd_rpi = make_fastdiv((unsigned)std::max(1, p.rounds_per_img));
   // epilogue work split between the two warps of a TMEM lane quarter
   const int nchunk16 = p.BN / 16;
-  if (p.G >= 2) { p.ep_split_cols = 0; p.ep_cols = p.BN; }
+  if (p.G >= 2 || (p.pair && nchunk16 % 2 != 0)) { p.ep_split_cols = 0; p.ep_cols = p.BN; }
   else if (nchunk16 % 2 == 0) { p.ep_split_cols = 1; p.ep_cols = p.BN / 2; }
   else { p.ep_split_cols = 0; p.ep_cols = p.BN; }
   p.ow = p.ep_cols % 64 == 0 ? 64 : (p.ep_cols % 32 == 0 ? 32 : 16);
@@ -779,6 +948,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     p.a_stage_bytes = kTileM * kKStage * 2;
     p.b_stage_bytes = p.ws_mode ? 0 : (int)align_up(p.BN * kKStage * 2, 1024);
   }
+  if (p.pair) p.a_stage_bytes *= 2;        // [tile 0 | tile 1] halves, one weight block
   // shared memory budget: two co-resident CTAs per SM (<= 112 KB each, their epilogues / TMA latencies overlap) for multi-wave layers;
   // ONE CTA per SM with a deep operand ring when the layer has at most `one_cta_x100`/100 rounds per SM (P4/P5 maps: the pipeline depth,
   // i.e. bytes in flight per SM, is what bounds those launches) or when two CTAs would leave fewer than 2 stages
@@ -790,7 +960,7 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
     const char* e = getenv("MYOLO_ONE_CTA_X100");
     one_cta_x100 = e ? atoi(e) : 100;
   }
-  int ctas_per_sm = (ws_big || (long)p.total_rounds * 100 <= (long)one_cta_x100 * num_sms) ? 1 : 2;
+  int ctas_per_sm = (ws_big || p.pair || (long)p.total_rounds * 100 <= (long)one_cta_x100 * num_sms) ? 1 : 2;
   int S = 0;
   if (ctas_per_sm == 2) {
     p.n_stg = p.out_mode == 0 ? 2 : 0;
@@ -803,9 +973,13 @@ int conv_tc_prepare(ConvOp& op, int num_sms) {
   }
   if (ctas_per_sm == 1) {
     // a CTA that runs a single round in which every epilogue warp stores at most one tile never reuses its staging buffer
-    const bool single_use = p.total_rounds <= num_sms && (p.G == 1 || (p.G == 2 && !p.ep_split_cols));
+    const bool single_use = !p.pair && p.total_rounds <= num_sms && (p.G == 1 || (p.G == 2 && !p.ep_split_cols));
     p.n_stg = p.out_mode == 0 ? (single_use ? 1 : 2) : 0;
     S = (220 * 1024 - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+    if (p.pair && S < 3 && p.n_stg == 2) {          // operand stages before a second staging buffer
+      p.n_stg = 1;
+      S = (220 * 1024 - p.b_res_bytes - p.n_stg * stg1 - misc) / stage_bytes;
+    }
   }
   if (S > 8) S = 8;
   MYOLO_REQUIRE(S >= 2, "conv_tc: not enough shared memory for 2 stages");

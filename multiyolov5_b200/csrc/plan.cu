@@ -1442,13 +1442,15 @@ extern "C" int myolo_conv_bn_silu(const void* x, int B, int H, int W, int ci, co
   c.Co = co;
   if (!rc) {
     const bool elig = conv_tc_eligible(c);
-    if (path == 1 && !elig) {
+    if ((path == 1 || path == 3) && !elig) {
       set_error("conv_bn_silu: shape not eligible for the tcgen05 path");
       rc = MYOLO_E_INVALID;
     } else if (path == 2 || (path == 0 && !elig)) {
       rc = conv_simt_launch(c, s);
     } else {
+      g_conv_tc_force_pair = path == 3;
       rc = conv_tc_prepare(c, sms);
+      g_conv_tc_force_pair = 0;
       const char* tl = getenv("MYOLO_CONV_TIMELINE");
       long long* dbg = nullptr;
       if (!rc && tl && tl[0] == '1') {

@@ -40,6 +40,12 @@ SHAPES = [
     (8, 37, 512, 32, 32, 3, 1, 1, False),     # vertical rounds with a ragged last row group (Ho = 37)
     (16, 64, 256, 32, 32, 1, 1, 1, False),    # many tiles, BN=32 -> 4 tiles per accumulator round
     (8, 64, 128, 64, 64, 1, 1, 1, True),      # 2 tiles per round + residual
+    # pair mode (two M tiles per weight fetch; needs >= ~120 pair rounds: layers at bench scale)
+    (16, 32, 64, 128, 128, 3, 1, 1, True),    # P4 bottleneck 3x3: 128 pair rounds, taps, 2 x 128 TMEM columns per stage, residual
+    (16, 64, 128, 64, 64, 3, 1, 2, False),    # strip + dilation 2: 444 pair rounds + 136 single-tile tail rounds
+    (16, 64, 128, 128, 256, 3, 2, 1, False),  # stride 2, two N tiles: pairs share the N tile
+    (16, 32, 64, 128, 80, 3, 1, 1, False),    # five 16-column chunks: the epilogue halves split the pair's tiles instead of columns
+    (6, 64, 128, 256, 128, 3, 1, 1, False),   # FFM class: strip, 4 channel blocks, 384 tiles -> 148 pair rounds + 88 singles
 ]
 
 
@@ -56,8 +62,13 @@ def torch_ref(x_nhwc, w, bn, stride, dil, residual, eps=1e-3):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("path,shape", [(p, s) for p in (2, 1) for s in SHAPES],
-                         ids=[f"{'simt' if p == 2 else 'tc'}-{i}" for p in (2, 1) for i in range(len(SHAPES))])
+# path 2: CUDA-core kernel, 1: tcgen05 kernel with the planner's tiling rules, 3: tcgen05 with pair mode wherever it is legal
+PAIR_SHAPES = [s for s in SHAPES if s[0] >= 6 and s[5] == 3][-5:] + [(16, 32, 64, 256, 128, 1, 1, 1, False), (2, 32, 64, 64, 64, 1, 1, 1, False)]
+
+
+@pytest.mark.parametrize("path,shape", [(p, s) for p in (2, 1) for s in SHAPES] + [(3, s) for s in PAIR_SHAPES],
+                         ids=[f"{'simt' if p == 2 else 'tc'}-{i}" for p in (2, 1) for i in range(len(SHAPES))]
+                         + [f"pair-{i}" for i in range(len(PAIR_SHAPES))])
 def test_conv_bn_silu(shape, path):
     from multiyolov5_b200 import ops
     B, H, W, Ci, Co, k, s, d, res = shape
