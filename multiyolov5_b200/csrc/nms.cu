@@ -128,6 +128,7 @@ __global__ void __launch_bounds__(1024) nms_kernel(NmsParams p) {
   unsigned* mat = reinterpret_cast<unsigned*>(karea + kMaxKept);                 // kChunk x 8 words
   __shared__ int s_nkept, s_alive_words[8];
   __shared__ unsigned s_keepmask[8];
+  __shared__ unsigned char s_alive[kChunk];
 
   const int b = blockIdx.x;
   long n = p.counts[b];
@@ -158,21 +159,32 @@ __global__ void __launch_bounds__(1024) nms_kernel(NmsParams p) {
     if (nkept0 >= max_det) break;
     const int m = (int)((n - c0) < kChunk ? (n - c0) : kChunk);
     Cand me;
-    bool alive = false;
-    if (t < m) {
-      me = load_cand(p, b, in_smem ? skeys[c0 + t] : gkeys[c0 + t]);
-      alive = true;
-      for (int k = 0; k < nkept0; ++k) {
-        const float4 kb = kbox[k];
-        if (iou_gt(kb.x, kb.y, kb.z, kb.w, karea[k], me.ox1, me.oy1, me.ox2, me.oy2, me.area, p.iou_thres)) { alive = false; break; }
-      }
-    }
-    // publish chunk boxes for the intra-chunk matrix (reuse the kept arrays' tail is not safe -> separate staging in `mat` area)
+    if (t < m) me = load_cand(p, b, in_smem ? skeys[c0 + t] : gkeys[c0 + t]);
+    // chunk boxes in shared memory: read by the kept-list check (4 threads per candidate) and by the intra-chunk matrix
     float4* cbox = reinterpret_cast<float4*>(mat + kChunk * 8);
     float* carea = reinterpret_cast<float*>(cbox + kChunk);
+    if (t < m) { cbox[t] = make_float4(me.ox1, me.oy1, me.ox2, me.oy2); carea[t] = me.area; }
+    __syncthreads();
+    {
+      // candidate r = t/4 against the kept list: its 4 threads take every fourth kept box (the list reaches max_det = 300 entries)
+      const int r = t >> 2, q = t & 3;
+      bool dead = false;
+      if (r < m) {
+        const float4 rb = cbox[r];
+        const float ra = carea[r];
+        for (int k = q; k < nkept0; k += 4) {
+          const float4 kb = kbox[k];
+          if (iou_gt(kb.x, kb.y, kb.z, kb.w, karea[k], rb.x, rb.y, rb.z, rb.w, ra, p.iou_thres)) { dead = true; break; }
+        }
+      }
+      unsigned d = dead ? 1u : 0u;
+      d |= __shfl_xor_sync(0xffffffffu, d, 1);
+      d |= __shfl_xor_sync(0xffffffffu, d, 2);
+      if (q == 0) s_alive[r] = (r < m && !d) ? 1 : 0;
+    }
+    __syncthreads();
     if (t < kChunk) {
-      if (t < m) { cbox[t] = make_float4(me.ox1, me.oy1, me.ox2, me.oy2); carea[t] = me.area; }
-      const unsigned bal = __ballot_sync(0xffffffffu, alive);
+      const unsigned bal = __ballot_sync(0xffffffffu, s_alive[t] != 0);
       if ((t & 31) == 0) s_alive_words[t >> 5] = (int)bal;
     }
     __syncthreads();
