@@ -197,7 +197,13 @@ class FusedComputeLoss:
         dp = [torch.empty_like(t) for t in p]
         items = torch.empty(4, dtype=torch.float32, device=p[0].device)
         vp = C.c_void_p
-        anchors = (C.c_float * (nl * na * 2))(*[float(v) for v in r.anchors.reshape(-1).tolist()])
+        # the anchors are a device buffer of the Detect layer: read them back ONCE (a .tolist() per step is a host-device synchronisation
+        # in the middle of the step - it kept the host from running ahead of the GPU)
+        akey = (r.anchors.data_ptr(), r.anchors._version)
+        if getattr(self, "_anchors_key", None) != akey:
+            self._anchors_host = [float(v) for v in r.anchors.reshape(-1).tolist()]
+            self._anchors_key = akey
+        anchors = (C.c_float * (nl * na * 2))(*self._anchors_host)
         balance = (C.c_float * nl)(*[float(b) for b in r.balance])
         _lib.check(L.myolo_det_loss((vp * nl)(*[_lib.ptr(t) for t in p]), (vp * nl)(*[_lib.ptr(t) for t in dp]), _lib.ptr(targets),
                                     int(targets.shape[0]), B, na, no, nl, ny, nx, anchors, balance, float(r.hyp["box"]), float(r.hyp["obj"]),
