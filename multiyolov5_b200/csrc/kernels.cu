@@ -217,36 +217,69 @@ __device__ __forceinline__ float bilerp(float a, float b, float c, float d, cons
   return __fadd_rn(__fmul_rn(ly.l0, top), __fmul_rn(ly.l1, bot));
 }
 
-__device__ __forceinline__ void bilinear_nhwc_body(const TensorView& in, const TensorView& out, const RowIdx& r) {
-  if (!r.ok) return;
-  const int v = r.v, b = r.b;
-  const Lerp ly = lerp_axis(r.y, in.H, out.H), lx = lerp_axis(r.x, in.W, out.W);
-  const uint4 qa = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i0)) + v);
-  const uint4 qb = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, lx.i1)) + v);
-  const uint4 qc = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i0)) + v);
-  const uint4 qd = __ldg(reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, lx.i1)) + v);
-  const __half* ha = reinterpret_cast<const __half*>(&qa);
-  const __half* hb = reinterpret_cast<const __half*>(&qb);
-  const __half* hc = reinterpret_cast<const __half*>(&qc);
-  const __half* hd = reinterpret_cast<const __half*>(&qd);
-  uint4 o;
-  __half* ho = reinterpret_cast<__half*>(&o);
-#pragma unroll
-  for (int k = 0; k < 8; ++k)
-    ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
-  reinterpret_cast<uint4*>(vptr(out, b, r.y, r.x))[v] = o;
+// kPpt consecutive output pixels of one 8-channel vector per thread: the row interpolation, the scale divisions and the index arithmetic are
+// shared, a source column that serves two neighbouring outputs is loaded once (same arithmetic per output: results are bit-identical)
+static constexpr int kBilPpt = 4;
+__device__ __forceinline__ Lerp lerp_axis_s(int dst, int n_in, float scale) {
+  const float src = __fmul_rn(scale, (float)dst);
+  Lerp r;
+  r.i0 = min((int)src, n_in - 1);
+  r.i1 = r.i0 + (r.i0 < n_in - 1 ? 1 : 0);
+  r.l1 = __fsub_rn(src, (float)r.i0);
+  r.l0 = __fsub_rn(1.0f, r.l1);
+  return r;
 }
+__device__ __forceinline__ void bilinear_nhwc_body4(const TensorView& in, const TensorView& out, int b, int y) {
+  const int nv = out.C / 8;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int xg = i / nv, v = i - xg * nv;
+  const int x0 = xg * kBilPpt;
+  if (x0 >= out.W) return;
+  const float sy = out.H > 1 ? (float)(in.H - 1) / (float)(out.H - 1) : 0.f;
+  const float sx = out.W > 1 ? (float)(in.W - 1) / (float)(out.W - 1) : 0.f;
+  const Lerp ly = lerp_axis_s(y, in.H, sy);
+  const uint4* top = reinterpret_cast<const uint4*>(vptr(in, b, ly.i0, 0)) + v;
+  const uint4* bot = reinterpret_cast<const uint4*>(vptr(in, b, ly.i1, 0)) + v;
+  const int cstride = in.ctot / 8;                    // uint4 units between neighbouring pixels
+  uint4* dst = reinterpret_cast<uint4*>(vptr(out, b, y, x0)) + v;
+  const int ostride = out.ctot / 8;
+  int ca = -1, cb = -1;                                // cached source columns
+  uint4 ta, ba, tb, bb;
+  ta = ba = tb = bb = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int p = 0; p < kBilPpt; ++p) {
+    if (x0 + p >= out.W) break;
+    const Lerp lx = lerp_axis_s(x0 + p, in.W, sx);
+    if (lx.i0 != ca) {
+      if (lx.i0 == cb) { ca = cb; ta = tb; ba = bb; }
+      else { ca = lx.i0; ta = __ldg(top + (size_t)ca * cstride); ba = __ldg(bot + (size_t)ca * cstride); }
+    }
+    if (lx.i1 != cb) {
+      if (lx.i1 == ca) { cb = ca; tb = ta; bb = ba; }
+      else { cb = lx.i1; tb = __ldg(top + (size_t)cb * cstride); bb = __ldg(bot + (size_t)cb * cstride); }
+    }
+    const __half* ha = reinterpret_cast<const __half*>(&ta);
+    const __half* hb = reinterpret_cast<const __half*>(&tb);
+    const __half* hc = reinterpret_cast<const __half*>(&ba);
+    const __half* hd = reinterpret_cast<const __half*>(&bb);
+    uint4 o;
+    __half* ho = reinterpret_cast<__half*>(&o);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      ho[k] = __float2half_rn(bilerp(__half2float(ha[k]), __half2float(hb[k]), __half2float(hc[k]), __half2float(hd[k]), ly, lx));
+    dst[(size_t)p * ostride] = o;
+  }
+}
+static inline dim3 row_grid4(const TensorView& out, int nv) { return dim3(ceil_div(ceil_div(out.W, kBilPpt) * nv, 256), out.H, out.B); }
 __global__ void bilinear_nhwc_kernel(TensorView in, TensorView out) {
-  pdl_enter(); bilinear_nhwc_body(in, out, row_index(out.W, out.C / 8)); }
+  pdl_enter(); bilinear_nhwc_body4(in, out, blockIdx.z, blockIdx.y); }
 // up to 4 independent resamplings with identical output extents in ONE launch (the four levels of PyramidPooling): blockIdx.y = level*H + y
 struct BilinearGroup { TensorView in[4], out[4]; int n; };
 __global__ void bilinear_nhwc_group_kernel(BilinearGroup g) {
   pdl_enter();
   const int H = g.out[0].H;
   const int level = blockIdx.y / H;
-  RowIdx r = row_index(g.out[0].W, g.out[0].C / 8);
-  r.y = blockIdx.y - level * H;
-  bilinear_nhwc_body(g.in[level], g.out[level], r);
+  bilinear_nhwc_body4(g.in[level], g.out[level], blockIdx.z, blockIdx.y - level * H);
 }
 int launch_bilinear_nhwc_group(const TensorView* in, const TensorView* out, int n, cudaStream_t s) {
   MYOLO_REQUIRE(n >= 1 && n <= 4, "bilinear_nhwc_group: %d members", n);
@@ -259,7 +292,7 @@ int launch_bilinear_nhwc_group(const TensorView* in, const TensorView* out, int 
     g.in[i] = in[i];
     g.out[i] = out[i];
   }
-  dim3 grid = row_grid(out[0], out[0].C / 8);
+  dim3 grid = row_grid4(out[0], out[0].C / 8);
   grid.y *= n;
   MYOLO_CHECK_CUDA(launch_pdl(bilinear_nhwc_group_kernel, grid, dim3(256), 0, s, g));
   MYOLO_LAUNCH_CHECK();
@@ -269,7 +302,7 @@ int launch_bilinear_nhwc(const TensorView& in, const TensorView& out, cudaStream
   MYOLO_REQUIRE(in.C == out.C && in.C % 8 == 0 && in.ctot % 8 == 0 && out.ctot % 8 == 0 && in.dtype == MYOLO_F16 &&
                     out.dtype == MYOLO_F16,
                 "bilinear_nhwc: bad views");
-  MYOLO_CHECK_CUDA(launch_pdl(bilinear_nhwc_kernel, row_grid(out, out.C / 8), dim3(256), 0, s, in, out));
+  MYOLO_CHECK_CUDA(launch_pdl(bilinear_nhwc_kernel, row_grid4(out, out.C / 8), dim3(256), 0, s, in, out));
   MYOLO_LAUNCH_CHECK();
   return 0;
 }

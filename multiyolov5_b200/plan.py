@@ -269,8 +269,10 @@ class PlanBuilder:
         REGION_SUM aux = [ybounds_off, ny, xbounds_off, nx];  REGION_COMBINE aux = [bins_off, nbins, atoms_nx]."""
         ys = sorted({e for k in ks for be in adaptive_bins(x.h, k) for e in be})
         xs = sorted({e for k in ks for be in adaptive_bins(x.w, k) for e in be})
-        if len(ys) == 2 and x.h >= 16:      # a single huge bin (global pool): split into strips for parallelism
+        if len(ys) == 2 and x.h >= 16:      # a single huge bin (global pool): split into 16 x 4 tiles for parallelism (one CTA per atom)
             ys = sorted(set(list(range(0, x.h, max(1, x.h // 16))) + [x.h]))
+            if len(xs) == 2 and x.w >= 32:
+                xs = sorted(set(list(range(0, x.w, max(1, x.w // 4))) + [x.w]))
         ny, nx = len(ys) - 1, len(xs) - 1
         atoms = self.new_buf(ny, nx, x.c, F32)
         rec = OpRec(OP_REGION_SUM, x, None, atoms)
