@@ -477,20 +477,7 @@ int launch_broadcast(const TensorView& in, const TensorView& out, cudaStream_t s
 // Detect.forward (eval): view (bs,na,no,ny,nx) -> permute (bs,na,ny,nx,no); sigmoid; xy=(s*2-0.5+grid)*stride;
 // wh=(s*2)^2*anchor; z = cat over levels                                     [reference models/yolo.py:211-225]
 // ------------------------------------------------------------------------------------------------
-template <int NO>
-__global__ void detect_decode_kernel(TensorView in, int na, int no_rt, float stride, const float* __restrict__ anchors, float* raw,
-                                     float* z, int z_off, int z_rows) {
-  // grid = (chunks of W*no, H, B*na); o fastest -> reads, raw writes and z writes are all contiguous per warp
-  const int no = NO > 0 ? NO : no_rt;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int x = i / no, o = i - x * no;
-  if (x >= in.W) return;
-  const int y = blockIdx.y;
-  const int b = blockIdx.z / na, a = blockIdx.z - b * na;
-  const float v = vptr_f(in, b, y, x)[a * no + o];
-  const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W + x;
-  if (raw) raw[row * no + o] = v;
-  if (!z) return;     // train mode: only the raw, permuted head outputs (reference models/yolo.py:225 `return x if self.training`)
+__device__ __forceinline__ float detect_decode_one(float v, int o, int x, int y, int a, float stride, const float* __restrict__ anchors) {
   float sg = __fdividef(1.0f, 1.0f + __expf(-v));
   if (o == 0) sg = (sg * 2.0f - 0.5f + (float)x) * stride;
   else if (o == 1) sg = (sg * 2.0f - 0.5f + (float)y) * stride;
@@ -498,14 +485,50 @@ __global__ void detect_decode_kernel(TensorView in, int na, int no_rt, float str
     const float t = sg * 2.0f;
     sg = t * t * anchors[a * 2 + (o - 2)];
   }
-  z[((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W + x) * no + o] = sg;
+  return sg;
+}
+// grid = (chunks of W*no/4, H, B*na).  For a fixed (image, anchor, row) both outputs are contiguous over (x, o): a thread takes FOUR consecutive
+// (x, o) positions - scalar reads of the head conv's fp32 NHWC rows (just written: L2), one 16-byte store each to raw and z.
+template <int NO>
+__global__ void detect_decode_kernel(TensorView in, int na, int no_rt, float stride, const float* __restrict__ anchors, float* raw,
+                                     float* z, int z_off, int z_rows, int vec) {
+  const int no = NO > 0 ? NO : no_rt;
+  const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int row_elems = in.W * no;
+  if (j0 >= row_elems) return;
+  const int y = blockIdx.y;
+  const int b = blockIdx.z / na, a = blockIdx.z - b * na;
+  const float* src = vptr_f(in, b, y, 0) + a * no;
+  const size_t row = ((size_t)(b * na + a) * in.H + y) * in.W;
+  float v[4], d[4];
+  int x = j0 / no, o = j0 - x * no;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const bool ok = j0 + k < row_elems;
+    v[k] = ok ? src[(size_t)x * in.ctot + o] : 0.f;
+    d[k] = (z && ok) ? detect_decode_one(v[k], o, x, y, a, stride, anchors) : 0.f;
+    if (++o == no) { o = 0; ++x; }
+  }
+  const bool full = vec && j0 + 3 < row_elems;       // rows that are not a multiple of 16 bytes (odd maps) take scalar stores
+  if (raw) {
+    float* p = raw + row * no + j0;
+    if (full) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else for (int k = 0; k < 4 && j0 + k < row_elems; ++k) p[k] = v[k];
+  }
+  if (!z) return;     // train mode: only the raw, permuted head outputs (reference models/yolo.py:225 `return x if self.training`)
+  float* q = z + ((size_t)b * z_rows + z_off + ((size_t)a * in.H + y) * in.W) * no + j0;
+  if (full) *reinterpret_cast<float4*>(q) = make_float4(d[0], d[1], d[2], d[3]);
+  else for (int k = 0; k < 4 && j0 + k < row_elems; ++k) q[k] = d[k];
 }
 int launch_detect_decode(const TensorView& in, int na, int no, float stride, const float* d_anchors, float* raw, float* z,
                          int z_row_offset, int z_rows_total, cudaStream_t s) {
   MYOLO_REQUIRE(in.dtype == MYOLO_F32 && in.C >= na * no, "detect_decode: bad view");
-  const dim3 grid(ceil_div(in.W * no, 256), in.H, in.B * na);
-  if (no == 15) detect_decode_kernel<15><<<grid, 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total);
-  else detect_decode_kernel<0><<<grid, 256, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total);
+  // 16-byte stores need (W * no) % 4 == 0 rows and 16-byte aligned bases (torch allocations are; z_row_offset * no * 4 must be too)
+  const bool vec_ok = (in.W * no) % 4 == 0 && ((size_t)z_row_offset * no) % 4 == 0 && ((size_t)z_rows_total * no) % 4 == 0 &&
+                      (!raw || (reinterpret_cast<uintptr_t>(raw) & 15) == 0) && (!z || (reinterpret_cast<uintptr_t>(z) & 15) == 0);
+  const dim3 grid(ceil_div(ceil_div(in.W * no, 4), 128), in.H, in.B * na);
+  if (no == 15) detect_decode_kernel<15><<<grid, 128, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total, (int)vec_ok);
+  else detect_decode_kernel<0><<<grid, 128, 0, s>>>(in, na, no, stride, d_anchors, raw, z, z_row_offset, z_rows_total, (int)vec_ok);
   MYOLO_LAUNCH_CHECK();
   return 0;
 }

@@ -100,7 +100,7 @@ struct myolo_plan {
   std::vector<cudaStream_t> lanes;
   std::vector<cudaEvent_t> op_ev;
   cudaEvent_t ev_start = nullptr;
-  cudaEvent_t ev_tail[2] = {nullptr, nullptr};   // fork / join of the Detect decodes next to the seg upsample
+  cudaEvent_t ev_tail[3] = {nullptr, nullptr, nullptr};   // fork / join of the Detect decodes and the seg upsample behind the graph
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
   int n_graph_ops = 0;
@@ -126,6 +126,7 @@ struct myolo_plan {
   PackJob* d_pack_jobs = nullptr;
   int n_pack_jobs = 0, n_pack_chunks = 0, pack_jobs_cap = 0;
   bool pack_table_dirty = true;
+  cudaStream_t decode_stream = nullptr;   // low-priority side stream of the Detect decodes (myolo_plan_forward)
   // deferred running statistics (myolo_plan_set_defer_running / myolo_plan_apply_running)
   bool defer_running = false;
   RunningJob* d_run_jobs = nullptr;
@@ -229,6 +230,7 @@ extern "C" void myolo_plan_destroy(myolo_plan* pl) {
   }
   if (pl->ws) cudaFree(pl->ws);
   if (pl->d_extra) cudaFree(pl->d_extra);
+  if (pl->decode_stream) cudaStreamDestroy(pl->decode_stream);
   if (pl->d_pack_jobs) cudaFree(pl->d_pack_jobs);
   if (pl->d_run_jobs) cudaFree(pl->d_run_jobs);
   if (pl->graph_exec) cudaGraphExecDestroy(pl->graph_exec);
@@ -681,18 +683,28 @@ extern "C" int myolo_plan_forward(myolo_plan* pl, const void* x, int x_dtype, fl
   if (fork) {
     if (!pl->ev_tail[0])
       for (auto& e : pl->ev_tail) MYOLO_CHECK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if (!pl->decode_stream) {      // lowest priority: the decodes fill the SMs the seg upsample (the step's tail) leaves free, not the reverse
+      int least = 0, greatest = 0;
+      MYOLO_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      MYOLO_CHECK_CUDA(cudaStreamCreateWithPriority(&pl->decode_stream, cudaStreamNonBlocking, least));
+      // (measured, CUPTI: a kernel that follows a graph launch in the SAME stream starts ~24 us after the graph's last node, one on another
+      // stream waiting for an event behind the graph after ~2 us.  Moving the seg upsample to a side stream as well made both kernels start
+      // together and share the HBM bandwidth: the starved decode chain then ended the step later than it does now - not adopted)
+    }
     MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_tail[0], s));
-    MYOLO_CHECK_CUDA(cudaStreamWaitEvent(pl->lanes[1], pl->ev_tail[0], 0));
+    MYOLO_CHECK_CUDA(cudaStreamWaitEvent(pl->decode_stream, pl->ev_tail[0], 0));
   }
+  // the seg upsample first (it is the longest kernel of the tail), then the decodes on the low-priority side stream
+  for (int pass = 0; pass < 2; ++pass)
   for (size_t i = 0; i < pl->ops.size(); ++i)
-    if (pl->ops[i].kind == MYOLO_OP_DETECT_DECODE || pl->ops[i].kind == MYOLO_OP_SEG_UPSAMPLE) {
-      cudaStream_t st = (fork && pl->ops[i].kind == MYOLO_OP_DETECT_DECODE) ? pl->lanes[1] : s;
+    if (pl->ops[i].kind == (pass == 0 ? MYOLO_OP_SEG_UPSAMPLE : MYOLO_OP_DETECT_DECODE)) {
+      cudaStream_t st = (fork && pl->ops[i].kind == MYOLO_OP_DETECT_DECODE) ? pl->decode_stream : s;
       int rc = run_op(pl, (int)i, x, x_dtype, z, raw, seg, seg_dtype, seg_argmax, st);
       if (rc) return rc;
       ++n_ext;
     }
   if (fork) {
-    MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_tail[1], pl->lanes[1]));
+    MYOLO_CHECK_CUDA(cudaEventRecord(pl->ev_tail[1], pl->decode_stream));
     MYOLO_CHECK_CUDA(cudaStreamWaitEvent(s, pl->ev_tail[1], 0));
   }
   pl->last_launches = pl->n_graph_ops + n_ext;

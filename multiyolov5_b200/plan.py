@@ -581,7 +581,18 @@ def build_plan(model, B: int, H: int, W: int, noalias: bool = False, train: bool
         return cat_buf[j].sub(off, ch[i])
 
     outs: List[Optional[V]] = [None] * n
-    for i, m in enumerate(layers):
+    # execution order = yaml order, except that an inference plan lowers the Detect layer BEFORE the seg head it follows (neither reads the
+    # other): the graph then ends with the seg classifier conv and the x8 seg upsample - the longest caller-output kernel, run after the
+    # graph - no longer waits behind the three Detect convs
+    order = list(range(n))
+    if not train and os.environ.get("MYOLO_DETECT_FIRST", "1") == "1":
+        for i in range(1, n):
+            seg_types = (Y.SegMaskPSP, Y.SegMaskLab, Y.SegMaskBiSe, Y.SegMaskBase)
+            if isinstance(layers[i], Y.Detect) and isinstance(layers[i - 1], seg_types) and \
+                    all(absf(i, j) < i - 1 for j in ([layers[i].f] if isinstance(layers[i].f, int) else layers[i].f)):
+                order[i - 1], order[i] = i, i - 1
+    for i in order:
+        m = layers[i]
         pb.tag = f"L{i}:{type(m).__name__}"
         f = m.f
         x = None
