@@ -199,3 +199,44 @@ def test_c3_pair_fusion_plan(monkeypatch):
     assert torch.equal(merged[0].conv.weight, torch.cat([c3.cv1.conv.weight, c3.cv2.conv.weight], 0))
     assert torch.equal(merged[0].bn.running_var, torch.cat([c3.cv1.bn.running_var, c3.cv2.bn.running_var], 0))
     assert len(P.build_plan(model, 1, 64, 64, train=True).ops) > len(base.ops)          # train plans are never fused
+
+
+def test_inference_plan_lowers_detect_before_the_seg_head(monkeypatch):
+    """execution order is a planner decision: the Detect layer (yaml index 25) is lowered before the seg head (24) it follows - neither reads
+    the other - so that the captured graph ends with the seg classifier conv; train plans keep the yaml order; MYOLO_DETECT_FIRST=0 too"""
+    from multiyolov5_b200 import _lib, plan as P
+    from multiyolov5_b200.models.yolo import Model
+    model = Model("yolov5s_city_seg.yaml")
+
+    def first_last(pb):
+        det = [i for i, o in enumerate(pb.ops) if o.tag.startswith("L25:")]
+        seg = [i for i, o in enumerate(pb.ops) if o.tag.startswith("L24:")]
+        return det, seg
+    det, seg = first_last(P.build_plan(model, 1, 64, 128))
+    assert det and seg and max(det) < min(seg)
+    det, seg = first_last(P.build_plan(model, 1, 64, 128, train=True))
+    assert max(seg) < min(det)
+    monkeypatch.setenv("MYOLO_DETECT_FIRST", "0")
+    det, seg = first_last(P.build_plan(model, 1, 64, 128))
+    assert max(seg) < min(det)
+    # whatever the order, the ops reading caller-owned outputs keep their inputs alive to the end of the plan
+    monkeypatch.delenv("MYOLO_DETECT_FIRST")
+    pb = P.build_plan(model, 1, 64, 128)
+    for o in pb.ops:
+        if o.kind in (_lib.OP_DETECT_DECODE, _lib.OP_SEG_UPSAMPLE):
+            assert o.in_.buf.last > len(pb.ops)
+
+
+def test_global_average_pool_is_split_into_atoms():
+    """AdaptiveAvgPool2d(1) of the FFM attention: one bin per image would be one CTA per image; the planner cuts it into 16 x 4 atoms whose
+    fp32 sums the combine step adds up (REGION_SUM aux = [ybounds, ny, xbounds, nx])"""
+    from multiyolov5_b200 import _lib, plan as P
+    from multiyolov5_b200.models.yolo import Model
+    pb = P.build_plan(Model("yolov5s_city_seg.yaml"), 2, 512, 1024)
+    sums = [o for o in pb.ops if o.kind == _lib.OP_REGION_SUM]
+    assert len(sums) == 2                                                        # the pooling pyramid and the FFM global pool
+    ny, nx = sums[-1].aux[1], sums[-1].aux[3]
+    assert (ny, nx) == (16, 4)
+    ys = pb.extra[sums[-1].aux[0]: sums[-1].aux[0] + ny + 1]
+    xs = pb.extra[sums[-1].aux[2]: sums[-1].aux[2] + nx + 1]
+    assert ys[0] == 0 and ys[-1] == 64 and xs[0] == 0 and xs[-1] == 128 and list(ys) == sorted(set(ys)) and list(xs) == sorted(set(xs))
